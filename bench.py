@@ -1,0 +1,400 @@
+#!/usr/bin/env python
+"""Benchmark of the code-extraction hot path (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl b200|reference]
+
+One *step* = one batch of B synthetic NSynth-shaped notes (4 s @ 16 kHz) per GPU taken
+from audio to top+bottom VQ-VAE-2 codes, like ``extract_code.py:62-69`` of the reference
+but calling ``encode`` only:
+
+    audio [B,64000] --(1) isi_melif_forward--> mel-IF [B,2,1024,128]
+      --torch/cuDNN conv encoders (unchanged, random-init weights)-->
+      --(2) isi_vq_assign / isi_vq_gather_stats / isi_vq_finish, top then bottom--> int64 codes
+
+``value``  : notes/s with the audio already resident in HBM (CUDA events, max over ranks).
+``e2e``    : the same through the public API from pinned HOST audio, with the H2D copy of the
+             audio and the D2H copy of the code maps inside the timed region.
+``hot_path_only`` : (1)+(2) alone on pre-computed features (the convs are not this repo's
+             code), so the kernels' own throughput is visible.
+``roofline``: the dominant own kernel (the front end), algorithmic bytes / event time.
+``--impl reference`` times the CPU oracle port of the same path on the host cores.
+"""
+import argparse
+import json
+import os
+import pathlib
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = pathlib.Path(__file__).resolve().parent
+if str(ROOT) not in sys.path:
+    sys.path.insert(0, str(ROOT))
+
+import torch  # noqa: E402
+
+N_SAMPLES = 64000
+MELIF_BYTES_PER_NOTE = 4 * N_SAMPLES + 4 * 2 * 1024 * 128      # 1 304 576
+VECTORS_PER_NOTE = 32 * 4 + 64 * 8                              # 640 (top + bottom)
+DIM, N_EMBED = 64, 512
+METRIC = "notes/sec coded (spectrogram+top/bottom VQ)"
+MODEL_KW = dict(in_channel=2, resolution_factors={'bottom': 16, 'top': 2},
+                adapt_quantized_durations=False)
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d["hbm_gbs"]), "measured", d
+    return 6650.0, "fallback", {}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms during the timed region."""
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.path = index, None, None
+
+    def __enter__(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
+                 "-lms", "100", "-i", str(self.index)],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+        return self
+
+    def __exit__(self, *exc):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if not self.path or not os.path.exists(self.path):
+            return out
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            f = [s.strip() for s in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                "sw_power_cap"), f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.path)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons),
+                       samples=len(sm))
+        return out
+
+
+def make_audio(batch: int, seed_offset: int = 0) -> torch.Tensor:
+    from interactive_spectrogram_inpainting_b200.utils import synthetic
+    base = synthetic.synthetic_notes(min(batch, 64), seed=synthetic.AUDIO_SEED + seed_offset)
+    if batch <= 64:
+        return base
+    reps = (batch + 63) // 64
+    # distinct notes beyond the first 64: circular shifts keep the NSynth statistics
+    out = torch.cat([torch.roll(base, shifts=997 * r, dims=1) for r in range(reps)], 0)
+    return out[:batch].contiguous()
+
+
+# --------------------------------------------------------------------------- reference arm
+def cpu_encode_path(threads: int):
+    """The oracle port of the path: torch-CPU front-end restatement, the same conv wiring on
+    the CPU, the oracle quantiser.  Returns fn(audio[B,T]) -> (id_t, id_b)."""
+    from interactive_spectrogram_inpainting_b200.vqvae.vqvae import VQVAE
+    from oracle import frontend_oracle as fo
+    from oracle import quantizer_oracle as qo
+    torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    model = VQVAE(**MODEL_KW, bottleneck_cls=qo.OracleBottleneck).eval()
+    cfg = fo.FrontEndConfig()
+
+    def run(audio):
+        with torch.no_grad():
+            return model.encode_codes(fo.to_spectrogram(audio, cfg))
+    return run, model
+
+
+def time_cpu(run, audio, steps, warmup):
+    for _ in range(warmup):
+        run(audio)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        run(audio)
+    dt = time.perf_counter() - t0
+    return audio.shape[0] * steps / dt, dt / steps
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    run, _ = cpu_encode_path(cores)
+    sample = 16
+    audio = make_audio(sample)
+    value, per_step = time_cpu(run, audio, args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "notes/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "extract_code cfg2: 4 s/16 kHz notes -> mel-IF -> VQ-VAE-2 "
+                               "encode (bottom 16 / top 2, K=512, D=64) -> top+bottom codes",
+                   "notes_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": "notes/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} notes per step x {args.steps} steps, torch-CPU "
+                                   f"oracle port (front-end restatement + conv encoder + "
+                                   f"oracle quantiser), {cores} threads"},
+        "e2e": {"value": value, "unit": "notes/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------- B200 arm
+def b200_arm(args):
+    import torch.distributed as dist
+    from interactive_spectrogram_inpainting_b200 import _lib
+    from interactive_spectrogram_inpainting_b200.utils.spectrograms_helper import MelSpectrogramsHelper
+    from interactive_spectrogram_inpainting_b200.utils import synthetic
+    from interactive_spectrogram_inpainting_b200.vqvae.bottleneck import QuantizedBottleneck
+    from interactive_spectrogram_inpainting_b200.vqvae.vqvae import VQVAE
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback for the product path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    B, K, W = args.batch, args.steps, max(args.warmup, 3)
+    torch.manual_seed(0)
+    helper = MelSpectrogramsHelper().to(dev)
+    model = VQVAE(**MODEL_KW).to(dev).eval()
+    model.quantize_t.assign_algo = model.quantize_b.assign_algo = args.assign_algo
+    host_audio = make_audio(B, seed_offset=rank).pin_memory()
+    audio = host_audio.to(dev)
+    host_codes = (torch.empty(B, 32, 4, dtype=torch.int64).pin_memory(),
+                  torch.empty(B, 64, 8, dtype=torch.int64).pin_memory())
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+
+    melif_events, assign_events = [], []
+
+    def step(src, record=False):
+        with torch.no_grad():
+            if record:
+                a, b = ev(), ev()
+                a.record()
+            spec = helper.to_spectrogram(src)
+            if record:
+                b.record()
+                melif_events.append((a, b))
+            return model.encode_codes(spec)
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    # ---- value: inputs resident in HBM ----
+    for _ in range(W):
+        step(audio)
+    barrier()
+    launches0 = _lib.total_launches()
+    with ClockSampler(local) as clocks:
+        t0, t1 = ev(), ev()
+        t0.record()
+        for _ in range(K):
+            step(audio, record=True)
+        t1.record()
+        barrier()
+    launches = _lib.total_launches() - launches0
+    ms_total = max_over_ranks(t0.elapsed_time(t1))
+    value = world * B * K / (ms_total * 1e-3)
+    melif_ms = statistics.mean(a.elapsed_time(b) for a, b in melif_events)
+
+    # ---- e2e: pinned host audio in, code maps out, copies inside the timed region ----
+    def e2e_step():
+        dev_audio = host_audio.to(dev, non_blocking=True)
+        id_t, id_b = step(dev_audio)
+        host_codes[0].copy_(id_t, non_blocking=True)
+        host_codes[1].copy_(id_b, non_blocking=True)
+    for _ in range(W):
+        e2e_step()
+    barrier()
+    t0, t1 = ev(), ev()
+    t0.record()
+    for _ in range(K):
+        e2e_step()
+    t1.record()
+    barrier()
+    e2e_ms = max_over_ranks(t0.elapsed_time(t1))
+    e2e_value = world * B * K / (e2e_ms * 1e-3)
+
+    # ---- hot path only: (1) + (2) on pre-computed conv features ----
+    with torch.no_grad():
+        spec = helper.to_spectrogram(audio)
+        enc_b = model.enc_b(spec)
+        feat_t = model.quantize_conv_t(model.enc_t(enc_b)).permute(0, 2, 3, 1)
+        q_t = model.quantize_t(feat_t)[0].permute(0, 3, 1, 2)
+        feat_b = model.quantize_conv_b(torch.cat([model.dec_t(q_t), enc_b], 1)).permute(0, 2, 3, 1)
+        del spec, enc_b, q_t
+
+        def hot():
+            helper.to_spectrogram(audio)
+            model.quantize_t(feat_t)
+            model.quantize_b(feat_b)
+        for _ in range(W):
+            hot()
+        barrier()
+        t0, t1 = ev(), ev()
+        t0.record()
+        for _ in range(K):
+            hot()
+        t1.record()
+        barrier()
+        hot_ms = max_over_ranks(t0.elapsed_time(t1))
+
+        # quantiser-only roofline on a cfg-4-sized sweep point (1 Mi vectors, K=512, D=64)
+        qn = 1 << 20
+        qmod = QuantizedBottleneck(DIM, N_EMBED).to(dev).eval()
+        qmod.assign_algo = args.assign_algo
+        qx = synthetic.synthetic_features(qn, qmod.embed.cpu()).to(dev)
+        for _ in range(3):
+            qmod.assign(qx)
+        torch.cuda.synchronize()
+        t0, t1 = ev(), ev()
+        t0.record()
+        for _ in range(10):
+            qmod.assign(qx)
+        t1.record()
+        torch.cuda.synchronize()
+        assign_ms = t0.elapsed_time(t1) / 10
+
+        # TF32 dense peak of this box, measured like MEASURED_PEAKS.json measured BF16
+        torch.backends.cuda.matmul.allow_tf32 = True
+        ma = torch.randn(8192, 8192, device=dev)
+        mb = torch.randn(8192, 8192, device=dev)
+        for _ in range(2):
+            ma @ mb
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(5):
+            t0, t1 = ev(), ev()
+            t0.record(); ma @ mb; t1.record()
+            torch.cuda.synchronize()
+            best = min(best, t0.elapsed_time(t1))
+        tf32_tflops = 2 * 8192 ** 3 / (best * 1e-3) / 1e12
+        torch.backends.cuda.matmul.allow_tf32 = False
+        del ma, mb
+
+    hbm_peak, peak_kind, _ = measured_peaks()
+    melif_gbs = MELIF_BYTES_PER_NOTE * B / (melif_ms * 1e-3) / 1e9
+    assign_tflops = 2.0 * qn * N_EMBED * DIM / (assign_ms * 1e-3) / 1e12
+    clk = clocks.summary()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "notes/s", "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "extract_code cfg2: 4 s/16 kHz notes -> mel-IF -> VQ-VAE-2 "
+                               "encode (bottom 16 / top 2, K=512, D=64) -> top+bottom codes",
+                   "notes_per_step_per_gpu": B, "sharding": "notes sharded per rank, no collective",
+                   "conv_encoder": "torch/cuDNN fp32 (TF32 convs as torch defaults), random init",
+                   "l2": "inputs exceed L2: 65.5 MB audio + 268 MB spectrogram per step at B=256",
+                   "assign_algo": args.assign_algo},
+        "e2e": {"value": e2e_value, "unit": "notes/s",
+                "h2d_bytes_per_step": host_audio.numel() * 4,
+                "d2h_bytes_per_step": (host_codes[0].numel() + host_codes[1].numel()) * 8,
+                "ms_per_step": e2e_ms / K},
+        "gpu_launches": launches,
+        "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"],
+                   "reasons": clk["reasons"], "samples": clk["samples"]},
+        "roofline": {"kernel": "melif_kernel<2048,8,512>", "bound": "hbm", "achieved": melif_gbs,
+                     "peak": hbm_peak, "unit": "GB/s", "frac": melif_gbs / hbm_peak,
+                     "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
+                     "ms_per_launch": melif_ms, "algorithmic_bytes_per_launch": MELIF_BYTES_PER_NOTE * B},
+        "rooflines_other": [
+            {"kernel": f"vq_assign ({args.assign_algo})", "bound": "tensor",
+             "achieved": assign_tflops, "peak": tf32_tflops / 3.0, "unit": "TFLOP/s",
+             "frac": assign_tflops / (tf32_tflops / 3.0), "ms_per_launch": assign_ms,
+             "rows": qn, "note": "2*N*K*D algorithmic FLOP over the 3xTF32 roofline = TF32 dense "
+                                 f"cuBLAS peak measured on this box ({tf32_tflops:.0f} TFLOP/s) / 3"}],
+        "hot_path_only": {"value": world * B * K / (hot_ms * 1e-3), "unit": "notes/s",
+                          "ms_per_step": hot_ms / K,
+                          "what": "front end + top/bottom quantiser kernels, conv features precomputed"},
+    }
+
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        run, cpu_model = cpu_encode_path(cores)
+        cpu_model.load_state_dict(model.state_dict())
+        sample = 16
+        cpu_audio = host_audio[:sample].clone()
+        # size the sample to ~10-20 s of CPU work
+        v1, per = time_cpu(run, cpu_audio, 1, 1)
+        reps = max(2, min(50, int(12.0 / max(per, 1e-3))))
+        v, per = time_cpu(run, cpu_audio, reps, 0)
+        line["cpu_baseline"] = {"value": v, "unit": "notes/s", "cores": cores, "kind": "port",
+                                "sample": f"{sample} notes x {reps} passes of the torch-CPU oracle "
+                                          f"port (front-end restatement + conv encoder + oracle "
+                                          f"quantiser), {cores} threads"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=256, help="notes per step per GPU")
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--assign-algo", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

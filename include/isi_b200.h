@@ -1,0 +1,200 @@
+/*
+ * isi_b200.h -- C ABI of the B200-native VQ-VAE-2 code-extraction hot path.
+ *
+ * The reference (SonyCSLParis/interactive-spectrogram-inpainting) has no FFI
+ * layer: its boundary for this path is the Python nn.Module API.  Each entry
+ * point below names the reference statement(s) it replaces (file:line relative
+ * to the reference root); the Python modules in
+ * interactive_spectrogram_inpainting_b200/ bind these with ctypes and mirror
+ * the reference class/method names on top.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless its name starts with "h_";
+ *  - the library never allocates, frees or keeps global state: callers own all
+ *    buffers (outputs, workspaces, tables); calls are re-entrant and are enqueued
+ *    on the given CUDA stream without synchronising it;
+ *  - return value: 0 = ok, <0 = isi_status (bad argument / unsupported), >0 = a
+ *    cudaError_t raised by the launch;
+ *  - sm_100a only.  There is no CPU or other-architecture fallback.
+ */
+#ifndef ISI_B200_H_
+#define ISI_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define ISI_API __attribute__((visibility("default")))
+#else
+#define ISI_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* isi_stream_t; /* cudaStream_t */
+
+enum isi_status {
+  ISI_OK = 0,
+  ISI_ERR_NULL = -1,        /* required pointer is NULL */
+  ISI_ERR_SHAPE = -2,       /* non-positive or inconsistent sizes */
+  ISI_ERR_UNSUPPORTED = -3, /* valid request this build has no kernel for */
+  ISI_ERR_WORKSPACE = -4,   /* workspace too small / misaligned */
+  ISI_ERR_ALIGN = -5        /* pointer or stride violates an alignment rule */
+};
+
+/* Which kernel isi_vq_assign uses. AUTO picks TCGEN05 when the shape allows. */
+enum isi_assign_algo {
+  ISI_ASSIGN_AUTO = 0,
+  ISI_ASSIGN_SIMT_FP32 = 1, /* CUDA-core FP32 FMA, any D / K / layout          */
+  ISI_ASSIGN_TCGEN05 = 2    /* tcgen05.mma kind::tf32, 3xTF32 split, TMEM accum */
+};
+
+/*
+ * A logical [n_rows, dim] FP32 matrix whose rows are grouped in batches:
+ *   element(row, d) = base[(row / rows_per_batch) * batch_stride
+ *                          + (row % rows_per_batch) * row_stride + d * col_stride]
+ * (strides in elements).  Contiguous [N, D]: {N, 0, D, 1}.  The permuted NCHW
+ * view the reference feeds the quantiser (vqvae.py:260,272: conv output
+ * [B, D, H, W].permute(0, 2, 3, 1)): {H*W, D*H*W, 1, H*W}.
+ */
+typedef struct isi_rows_layout {
+  int64_t rows_per_batch;
+  int64_t batch_stride;
+  int64_t row_stride;
+  int64_t col_stride;
+} isi_rows_layout;
+
+ISI_API int isi_version(void);
+ISI_API const char* isi_status_string(int status);
+
+/* ------------------------------------------------------------------ *
+ *  (2) quantiser: distance / argmin / gather                          *
+ * ------------------------------------------------------------------ */
+
+/* Bytes of the "prepared codebook" scratch for a [dim, n_embed] codebook. */
+ISI_API size_t isi_vq_prepared_bytes(int dim, int n_embed);
+
+/*
+ * Derive everything the kernels read from the codebook `embed` ([dim, n_embed]
+ * FP32, code index contiguous -- the reference buffer `embed`,
+ * bottleneck.py:47-49): ||e_k||^2 (bottleneck.py:59), the code-major copy E^T
+ * that `embed_code` gathers from (bottleneck.py:103-104), and the pre-split,
+ * pre-swizzled TF32 hi/lo operand tiles of -2E for the tensor-core kernel.
+ * Must be re-run whenever `embed` changes (after every EMA update).
+ */
+ISI_API int isi_vq_prepare_codebook(const float* embed, int dim, int n_embed,
+                            void* prepared, size_t prepared_bytes,
+                            isi_stream_t stream);
+
+/*
+ * Nearest-code search.  Replaces bottleneck.py:55-61:
+ *   dist = |x|^2 - 2 x.E + |E|^2 ;  _, ind = (-dist).max(1)
+ * out_index[n] (int64) = argmin_k dist(n, k), lowest k on exact ties;
+ * out_score[n] (optional) = min_k (|e_k|^2 - 2 x_n.e_k)  (= dist - |x_n|^2).
+ */
+ISI_API int isi_vq_assign(const float* x, const isi_rows_layout* x_layout, int64_t n_rows,
+                  int dim, int n_embed, const void* prepared,
+                  int64_t* out_index, float* out_score, int algo,
+                  isi_stream_t stream);
+
+/* Bytes of the per-call scratch of isi_vq_gather_stats. */
+ISI_API size_t isi_vq_gather_workspace_bytes(int64_t n_rows, int dim);  /* 8-byte aligned */
+
+/*
+ * Code lookup + commitment partials + (training) EMA statistics.
+ * Replaces bottleneck.py:75-77 (one_hot, embed_code), :81 and :83 (one-hot column
+ * sums and x^T.onehot, here a segmented reduction), the numerator of :94 and the
+ * forward value of :95.
+ *   out_q(n, :)      = E^T[index[n]]       written with `q_layout` (nullable)
+ *   stats[0:K]       += #{n : index[n]==k}                (FP32, nullable)
+ *   stats[K + k*D+d] += sum_{n : index[n]==k} x(n, d)     (code-major, nullable)
+ *   workspace        <- per-CTA partial sums of (q - x)^2 for isi_vq_finish
+ * `stats` (K + K*D floats) must be zeroed by the caller before the first call of a
+ * step; it is the buffer a data-parallel job all-reduces.
+ * `counts_only`: accumulate stats[0:K] only (eval-mode perplexity).
+ * Out-of-range indices set *status_flag (int32, nullable) to 1 and are skipped.
+ */
+ISI_API int isi_vq_gather_stats(const float* x, const isi_rows_layout* x_layout,
+                        const int64_t* index, int64_t n_rows, int dim, int n_embed,
+                        const void* prepared, float* out_q,
+                        const isi_rows_layout* q_layout, float* stats,
+                        int counts_only, void* workspace, size_t workspace_bytes,
+                        int32_t* status_flag, isi_stream_t stream);
+
+/*
+ * Scalars of the forward: replaces bottleneck.py:94 (diff = mean((q-x)^2)) and
+ * :97-100 (perplexity = exp(-sum p log max(p,1e-7)), p = counts / n_rows).
+ * Deterministic (fixed-order FP64 reduction of the per-CTA partials).
+ */
+ISI_API int isi_vq_finish(const void* workspace, int64_t n_rows, int dim, int n_embed,
+                  const float* stats, float* out_diff, float* out_perplexity,
+                  isi_stream_t stream);
+
+/*
+ * EMA codebook update, in place.  Replaces bottleneck.py:80-92:
+ *   cluster_size <- g*cluster_size + (1-g)*counts
+ *   embed_avg    <- g*embed_avg    + (1-g)*embed_sum
+ *   n = sum(cluster_size); cs' = (cluster_size+eps)/(n+K*eps)*n
+ *   embed        <- embed_avg / cs'
+ * `stats` as produced by isi_vq_gather_stats (optionally summed over ranks);
+ * stats[0:K] is consumed and overwritten with cs'.  cluster_size [K],
+ * embed_avg [D,K], embed [D,K] are the reference buffers.  decay / eps are the
+ * Python doubles of the module; they are rounded to FP32 where the reference's
+ * scalars meet FP32 tensors ((float)(1-decay), (float)(K*eps)).
+ */
+ISI_API int isi_vq_ema_update(float* stats, float* cluster_size, float* embed_avg,
+                      float* embed, int dim, int n_embed, double decay, double eps,
+                      isi_stream_t stream);
+
+/*
+ * embed_code: out(n, :) = E^T[index[n]].  Replaces bottleneck.py:103-104
+ * (F.embedding(ids, embed.T)) and, with an NCHW `out_layout`, the permute of
+ * vqvae.py:290,292.  Out-of-range ids set *status_flag and write zeros.
+ */
+ISI_API int isi_embed_code(const int64_t* index, int64_t n_rows, int dim, int n_embed,
+                   const void* prepared, float* out,
+                   const isi_rows_layout* out_layout, int32_t* status_flag,
+                   isi_stream_t stream);
+
+/* ------------------------------------------------------------------ *
+ *  (1) front end: STFT -> (mel) -> log-magnitude + instantaneous freq *
+ * ------------------------------------------------------------------ */
+
+/*
+ * Parameters of SpectrogramsHelper / MelSpectrogramsHelper.to_spectrogram
+ * (external GANsynth_pytorch; built at utils/misc.py:10-29 from the kwargs
+ * fs_hz, n_fft, hop_length, window_length, mel_*).  Tables are device arrays the
+ * host side computes once in FP64 (see utils/spectrograms_helper.py).
+ */
+typedef struct isi_melif_params {
+  int32_t n_fft;        /* 2048 (512 and 1024 also built)                       */
+  int32_t hop;          /* hop_length                                           */
+  int32_t pad_left;     /* zeros before the first sample (GANSynth: n_fft-hop)  */
+  int32_t n_frames;     /* output time steps                                    */
+  int32_t drop_dc;      /* 1: keep bins 1..n_fft/2, 0: keep bins 0..n_fft/2-1   */
+  int32_t use_mel;      /* 0: linear log|X| + IF, 1: mel log-mag^2 + mel IF     */
+  int32_t mel_width;    /* max non-zeros per mel bin (row pitch of mel_weight)  */
+  float safelog_eps;    /* log(v + eps)                                         */
+  const float* window;  /* [n_fft] analysis window                              */
+  const float* twiddle; /* [n_fft] interleaved cos,sin of -2*pi*j/n_fft, j<n_fft/2 */
+  const int32_t* mel_start; /* [n_fft/2] first linear bin of each mel band      */
+  const int32_t* mel_count; /* [n_fft/2] band length (0..mel_width)             */
+  const float* mel_weight;  /* [n_fft/2, mel_width] band weights                */
+} isi_melif_params;
+
+/*
+ * audio [n_notes, n_samples] FP32 (contiguous) -> out [n_notes, 2, n_fft/2,
+ * n_frames] FP32: channel 0 log-magnitude, channel 1 instantaneous frequency,
+ * frequency-major / time-contiguous like the reference tensors
+ * (Inference.ipynb:71, flask_server.py:891-896).
+ */
+ISI_API int isi_melif_forward(const float* audio, int64_t n_notes, int64_t n_samples,
+                      const isi_melif_params* h_params, float* out,
+                      isi_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ISI_B200_H_ */

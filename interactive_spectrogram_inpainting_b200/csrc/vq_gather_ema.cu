@@ -1,0 +1,345 @@
+// Codebook preparation, code lookup, commitment partials, EMA statistics (a
+// warp-aggregated segmented reduction) and the EMA codebook update.
+//
+// Replaces bottleneck.py:75-100,103-104 of the reference; see include/isi_b200.h
+// for the statement-by-statement mapping.
+#include "common.cuh"
+
+namespace isi {
+
+// ---------------------------------------------------------------------------
+// prepare: e2[k] = sum_d E[d][k]^2 (d ascending, like embed.pow(2).sum(0)),
+//          et[k][d] = ed[d][k] = E[d][k]
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+vq_prepare_kernel(const float* __restrict__ embed, int dim, int n_embed, Prepared p) {
+  __shared__ float tile[32][33];
+  const int tiles_k = (n_embed + 31) / 32, tiles_d = (dim + 31) / 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  for (int t = blockIdx.x; t < tiles_k * tiles_d; t += gridDim.x) {
+    const int k0 = (t % tiles_k) * 32, d0 = (t / tiles_k) * 32;
+    for (int j = ty; j < 32; j += 8) {
+      int d = d0 + j, k = k0 + tx;
+      float v = (d < dim && k < n_embed) ? embed[(int64_t)d * n_embed + k] : 0.f;
+      tile[j][tx] = v;
+      if (d < dim && k < n_embed) p.ed[(int64_t)d * n_embed + k] = v;
+    }
+    __syncthreads();
+    for (int j = ty; j < 32; j += 8) {
+      int k = k0 + j, d = d0 + tx;
+      if (d < dim && k < n_embed) p.et[(int64_t)k * dim + d] = tile[tx][j];
+    }
+    __syncthreads();
+  }
+  const int kp = padded_codes(n_embed);
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < kp; k += gridDim.x * blockDim.x) {
+    float s = 0.f;
+    if (k < n_embed) {
+      for (int d = 0; d < dim; ++d) { float v = embed[(int64_t)d * n_embed + k]; s = fmaf(v, v, s); }
+    } else {
+      s = INFINITY;  // padded codes can never win the argmin
+    }
+    p.e2[k] = s;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// gather + diff partials + EMA statistics
+// ---------------------------------------------------------------------------
+constexpr int kGatherRows = 128;   // rows per CTA tile, 32 per warp
+constexpr int kGatherThreads = 128;
+
+__global__ void __launch_bounds__(kGatherThreads)
+vq_gather_stats_kernel(const float* __restrict__ x, isi_rows_layout xl,
+                       const int64_t* __restrict__ index, int64_t n_rows, int dim, int n_embed,
+                       const float* __restrict__ et, float* __restrict__ out_q,
+                       isi_rows_layout ql, float* __restrict__ stats, int counts_only,
+                       double* __restrict__ partials, int32_t* __restrict__ status_flag) {
+  extern __shared__ __align__(16) float smem[];
+  const int pitch = dim + 1;
+  float* xs = smem;                                   // [kGatherRows][pitch]
+  int* codes = (int*)(smem + kGatherRows * pitch);    // [kGatherRows]
+  __shared__ double warp_part[kGatherThreads / 32];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t row0 = (int64_t)blockIdx.x * kGatherRows;
+  const int rows_here = (int)min((int64_t)kGatherRows, n_rows - row0);
+
+  // 1. indices of the tile
+  for (int r = tid; r < kGatherRows; r += kGatherThreads) {
+    int c = -1;
+    if (r < rows_here) {
+      int64_t v = index[row0 + r];
+      if (v >= 0 && v < n_embed) c = (int)v;
+      else if (status_flag) atomicExch(status_flag, 1);
+    }
+    codes[r] = c;
+  }
+  // 2. x tile, global reads coalesced along whichever axis is contiguous
+  if (x) {
+    const bool rows_contiguous = (xl.row_stride == 1 && xl.col_stride != 1);
+    for (int e = tid; e < kGatherRows * dim; e += kGatherThreads) {
+      int r, d;
+      if (rows_contiguous) { r = e % kGatherRows; d = e / kGatherRows; }
+      else                 { d = e % dim; r = e / dim; }
+      float v = 0.f;
+      if (r < rows_here) v = x[row_offset(xl, row0 + r) + (int64_t)d * xl.col_stride];
+      xs[r * pitch + d] = v;
+    }
+  }
+  __syncthreads();
+
+  // 3. EMA statistics: each warp owns 32 rows; rows that share a code are summed
+  //    in registers first, so one reduction per (distinct code, d) reaches memory.
+  const int my_code = codes[warp * 32 + lane];
+  if (stats) {
+    const unsigned peers = __match_any_sync(0xffffffffu, my_code);
+    const bool leader = (my_code >= 0) && (lane == __ffs(peers) - 1);
+    unsigned todo = __ballot_sync(0xffffffffu, leader);
+    while (todo) {
+      const int src = __ffs(todo) - 1;
+      todo &= todo - 1;
+      const unsigned members = __shfl_sync(0xffffffffu, peers, src);
+      const int c = __shfl_sync(0xffffffffu, my_code, src);
+      if (lane == 0) atomicAdd(&stats[c], (float)__popc(members));
+      if (!counts_only) {
+        float* dst = stats + n_embed + (int64_t)c * dim;
+        for (int d = lane; d < dim; d += 32) {
+          float s = 0.f;
+          for (unsigned m = members; m; m &= m - 1)
+            s += xs[(warp * 32 + __ffs(m) - 1) * pitch + d];
+          atomicAdd(&dst[d], s);
+        }
+      }
+    }
+  }
+
+  // 4. lookup, commitment partial; q overwrites the x tile in shared memory
+  float sq = 0.f;
+  for (int i = 0; i < 32; ++i) {
+    const int r = warp * 32 + i;
+    const int c = __shfl_sync(0xffffffffu, my_code, i);
+    if (r < rows_here) {
+      for (int d = lane; d < dim; d += 32) {
+        float q = (c >= 0) ? et[(int64_t)c * dim + d] : 0.f;
+        if (x) {
+          float xv = xs[r * pitch + d];
+          float t = q - xv;
+          sq = fmaf(t, t, sq);
+          q = xv + t;                      // forward value of bottleneck.py:95
+        }
+        xs[r * pitch + d] = q;
+      }
+    }
+  }
+  sq = warp_sum(sq);
+  if (lane == 0) warp_part[warp] = (double)sq;
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0.0;
+    for (int w = 0; w < kGatherThreads / 32; ++w) s += warp_part[w];
+    partials[blockIdx.x] = s;
+  }
+
+  // 5. write the q tile with the output's own contiguous axis fastest
+  if (out_q) {
+    const bool rows_contiguous = (ql.row_stride == 1 && ql.col_stride != 1);
+    for (int e = tid; e < kGatherRows * dim; e += kGatherThreads) {
+      int r, d;
+      if (rows_contiguous) { r = e % kGatherRows; d = e / kGatherRows; }
+      else                 { d = e % dim; r = e / dim; }
+      if (r < rows_here)
+        out_q[row_offset(ql, row0 + r) + (int64_t)d * ql.col_stride] = xs[r * pitch + d];
+    }
+  }
+}
+
+// diff = sum(partials) / (N*D) ; perplexity from the usage histogram
+__global__ void __launch_bounds__(256)
+vq_finish_kernel(const double* __restrict__ partials, int64_t n_partials, int64_t n_rows, int dim,
+                 int n_embed, const float* __restrict__ stats, float* __restrict__ out_diff,
+                 float* __restrict__ out_perplexity) {
+  __shared__ double red[256];
+  const int tid = threadIdx.x;
+  double s = 0.0;
+  if (out_diff)
+    for (int64_t i = tid; i < n_partials; i += 256) s += partials[i];
+  red[tid] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) { if (tid < o) red[tid] += red[tid + o]; __syncthreads(); }
+  if (tid == 0 && out_diff) *out_diff = (float)(red[0] / ((double)n_rows * (double)dim));
+  __syncthreads();
+  if (out_perplexity && stats) {
+    double h = 0.0;
+    for (int k = tid; k < n_embed; k += 256) {
+      float p = stats[k] / (float)n_rows;
+      h += (double)(p * logf(fmaxf(p, 1e-7f)));
+    }
+    red[tid] = h;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) { if (tid < o) red[tid] += red[tid + o]; __syncthreads(); }
+    if (tid == 0) *out_perplexity = expf((float)(-red[0]));
+  }
+}
+
+// ---------------------------------------------------------------------------
+// EMA update (bottleneck.py:80-92)
+// ---------------------------------------------------------------------------
+// phase 1 (one CTA): cluster_size in place; smoothed sizes -> smoothed[K]
+__global__ void __launch_bounds__(1024)
+vq_ema_cluster_kernel(const float* counts /* aliases smoothed */, float* cluster_size,
+                      float* smoothed, int n_embed, float decay,
+                      float one_minus_decay, float eps, float k_eps) {
+  __shared__ float red[1024];
+  const int tid = threadIdx.x;
+  float s = 0.f;
+  for (int k = tid; k < n_embed; k += 1024) {
+    // mul_(decay) rounds, then add_(alpha, counts) is one fused multiply-add
+    float cs = fmaf(counts[k], one_minus_decay, __fmul_rn(cluster_size[k], decay));
+    cluster_size[k] = cs;
+    s += cs;
+  }
+  red[tid] = s;
+  __syncthreads();
+  for (int o = 512; o > 0; o >>= 1) { if (tid < o) red[tid] += red[tid + o]; __syncthreads(); }
+  const float n = red[0];
+  for (int k = tid; k < n_embed; k += 1024)
+    smoothed[k] = (cluster_size[k] + eps) / (n + k_eps) * n;
+}
+
+// phase 2: embed_avg, embed [D,K] from the code-major embed_sum [K,D]
+__global__ void __launch_bounds__(256)
+vq_ema_embed_kernel(const float* __restrict__ embed_sum, const float* __restrict__ smoothed,
+                    float* __restrict__ embed_avg, float* __restrict__ embed, int dim, int n_embed,
+                    float decay, float one_minus_decay) {
+  __shared__ float tile[32][33];
+  const int tiles_k = (n_embed + 31) / 32;
+  const int k0 = (blockIdx.x % tiles_k) * 32, d0 = (blockIdx.x / tiles_k) * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int j = ty; j < 32; j += 8) {
+    int k = k0 + j, d = d0 + tx;
+    tile[j][tx] = (k < n_embed && d < dim) ? embed_sum[(int64_t)k * dim + d] : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    int d = d0 + j, k = k0 + tx;
+    if (d < dim && k < n_embed) {
+      int64_t o = (int64_t)d * n_embed + k;
+      float ea = fmaf(tile[tx][j], one_minus_decay, __fmul_rn(embed_avg[o], decay));
+      embed_avg[o] = ea;
+      embed[o] = ea / smoothed[k];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// embed_code (bottleneck.py:103-104), optionally straight into NCHW
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+embed_code_kernel(const int64_t* __restrict__ index, int64_t n_rows, int dim, int n_embed,
+                  const float* __restrict__ et, float* __restrict__ out, isi_rows_layout ol,
+                  int32_t* __restrict__ status_flag) {
+  extern __shared__ __align__(16) float smem[];
+  const int pitch = dim + 1;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t row0 = (int64_t)blockIdx.x * 32;
+  const int rows_here = (int)min((int64_t)32, n_rows - row0);
+  const bool rows_contiguous = (ol.row_stride == 1 && ol.col_stride != 1);
+  for (int r = warp; r < rows_here; r += 8) {
+    int64_t v = index[row0 + r];
+    bool ok = (v >= 0 && v < n_embed);
+    if (!ok && lane == 0 && status_flag) atomicExch(status_flag, 1);
+    for (int d = lane; d < dim; d += 32) {
+      float q = ok ? et[v * dim + d] : 0.f;
+      if (rows_contiguous) smem[r * pitch + d] = q;
+      else out[row_offset(ol, row0 + r) + (int64_t)d * ol.col_stride] = q;
+    }
+  }
+  if (rows_contiguous) {
+    __syncthreads();
+    for (int e = tid; e < 32 * dim; e += 256) {
+      int r = e & 31, d = e >> 5;
+      if (r < rows_here)
+        out[row_offset(ol, row0 + r) + (int64_t)d * ol.col_stride] = smem[r * pitch + d];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------
+int launch_prepare(const float* embed, int dim, int n_embed, const Prepared& p,
+                   cudaStream_t stream) {
+  int tiles = ((n_embed + 31) / 32) * ((dim + 31) / 32);
+  int grid = tiles < 4 * kNumSms ? tiles : 4 * kNumSms;
+  vq_prepare_kernel<<<grid, 256, 0, stream>>>(embed, dim, n_embed, p);
+  ISI_LAUNCH_CHECK();
+  return ISI_OK;
+}
+
+size_t gather_workspace_bytes(int64_t n_rows) {
+  int64_t grid = (n_rows + kGatherRows - 1) / kGatherRows;
+  return (size_t)(grid > 0 ? grid : 1) * sizeof(double);
+}
+
+int launch_gather_stats(const float* x, const isi_rows_layout& xl, const int64_t* index,
+                        int64_t n_rows, int dim, int n_embed, const Prepared& p, float* out_q,
+                        const isi_rows_layout& ql, float* stats, int counts_only, void* workspace,
+                        int32_t* status_flag, cudaStream_t stream) {
+  int64_t grid = (n_rows + kGatherRows - 1) / kGatherRows;
+  if (grid > 0x7fffffff) return ISI_ERR_SHAPE;
+  size_t smem = (size_t)kGatherRows * (dim + 1) * 4 + kGatherRows * 4;
+  if (smem > 200 * 1024) return ISI_ERR_UNSUPPORTED;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(vq_gather_stats_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+  }
+  double* partials = (double*)workspace;
+  vq_gather_stats_kernel<<<(unsigned)grid, kGatherThreads, smem, stream>>>(
+      x, xl, index, n_rows, dim, n_embed, p.et, out_q, ql, stats, counts_only, partials,
+      status_flag);
+  ISI_LAUNCH_CHECK();
+  return ISI_OK;
+}
+
+int launch_finish(const void* workspace, int64_t n_rows, int dim, int n_embed, const float* stats,
+                  float* out_diff, float* out_perplexity, cudaStream_t stream) {
+  int64_t n_partials = (n_rows + kGatherRows - 1) / kGatherRows;
+  const double* partials = (const double*)workspace;
+  vq_finish_kernel<<<1, 256, 0, stream>>>(partials, n_partials, n_rows, dim, n_embed, stats,
+                                          out_diff, out_perplexity);
+  ISI_LAUNCH_CHECK();
+  return ISI_OK;
+}
+
+int launch_ema_update(float* stats, float* cluster_size, float* embed_avg, float* embed, int dim,
+                      int n_embed, double decay_d, double eps_d, cudaStream_t stream) {
+  // scalars are rounded to FP32 exactly where the reference's Python doubles meet tensors
+  const float decay = (float)decay_d, one_minus_decay = (float)(1.0 - decay_d);
+  const float eps = (float)eps_d, k_eps = (float)(n_embed * eps_d);
+  // the smoothed cluster sizes overwrite the (already consumed) counts in stats[0:K]
+  vq_ema_cluster_kernel<<<1, 1024, 0, stream>>>(stats, cluster_size, stats, n_embed, decay,
+                                                  one_minus_decay, eps, k_eps);
+  ISI_LAUNCH_CHECK();
+  int tiles = ((n_embed + 31) / 32) * ((dim + 31) / 32);
+  vq_ema_embed_kernel<<<tiles, 256, 0, stream>>>(stats + n_embed, stats, embed_avg, embed, dim,
+                                                 n_embed, decay, one_minus_decay);
+  ISI_LAUNCH_CHECK();
+  return ISI_OK;
+}
+
+int launch_embed_code(const int64_t* index, int64_t n_rows, int dim, int n_embed,
+                      const Prepared& p, float* out, const isi_rows_layout& ol,
+                      int32_t* status_flag, cudaStream_t stream) {
+  int64_t grid = (n_rows + 31) / 32;
+  if (grid > 0x7fffffff) return ISI_ERR_SHAPE;
+  size_t smem = (size_t)32 * (dim + 1) * 4;
+  if (smem > 48 * 1024) return ISI_ERR_UNSUPPORTED;
+  embed_code_kernel<<<(unsigned)grid, 256, smem, stream>>>(index, n_rows, dim, n_embed, p.et, out,
+                                                           ol, status_flag);
+  ISI_LAUNCH_CHECK();
+  return ISI_OK;
+}
+
+}  // namespace isi

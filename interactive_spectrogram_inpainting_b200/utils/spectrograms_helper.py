@@ -1,0 +1,196 @@
+"""``SpectrogramsHelper`` / ``MelSpectrogramsHelper`` backed by the fused sm_100a front end.
+
+The reference builds these classes from the third-party ``GANsynth_pytorch`` package
+(``interactive_spectrogram_inpainting/utils/misc.py:5-29``) whose source is not part of
+the reference tree; constructor keywords and attribute names follow the reference's
+call sites (``utils/misc.py:13-27``; ``fs_hz``/``hop_length``/``safelog_eps`` read at
+``train_vqvae.py:400,421,711``; ``.to(device)`` at ``extract_code.py:173``).  The
+arithmetic is the published GANSynth recipe; the choices the missing source would
+decide are keyword-only arguments ("front end: unpinned").
+
+``to_spectrogram`` is the hot path (isi_melif_forward).  ``to_audio`` is the plain
+torch inverse (not yet a kernel).
+"""
+import math
+from typing import Optional
+
+import numpy as np
+import torch
+from torch import nn
+
+from .. import _lib
+
+_MEL_Q = 1127.0
+SUPPORTED_N_FFT = (512, 1024, 2048)
+
+
+def mel_band_table(n_fft: int, fs_hz: float, lower_edge_hertz: float, upper_edge_hertz: float,
+                   break_hz: float, width_factor: float):
+    """Banded form of the GANSynth linear->mel filterbank for ``n_fft // 2`` linear and as
+    many mel bins: for every mel bin the first linear row it touches, how many rows, and
+    the FP64 triangle weights (zero-padded to the widest band).
+
+    Mel scale m(f) = 1127 ln(1 + f/break); triangle edges equally spaced in mel between
+    the two edge frequencies; a triangle narrower than ``width_factor`` linear bins is
+    re-centred to that width in Hz (asinh form); linear bin frequencies are
+    linspace(0, fs/2, n_bins) with the first row zeroed, as the public recipe has it.
+    """
+    n_bins = n_fft // 2
+    nyquist = fs_hz / 2.0
+    to_mel = lambda f: _MEL_Q * np.log1p(np.asarray(f, dtype=np.float64) / break_hz)
+    to_hz = lambda m: break_hz * np.expm1(np.asarray(m, dtype=np.float64) / _MEL_Q)
+
+    grid = np.linspace(to_mel(lower_edge_hertz), to_mel(upper_edge_hertz), n_bins + 2)
+    left, centre, right = grid[:-2].copy(), grid[1:-1].copy(), grid[2:].copy()
+    min_width_hz = width_factor * nyquist / n_bins
+    narrow = (to_hz(right) - to_hz(left)) < min_width_hz
+    half = _MEL_Q * np.arcsinh(0.5 * min_width_hz / (to_hz(centre) + break_hz))
+    left = np.where(narrow, centre - half, left)
+    right = np.where(narrow, centre + half, right)
+    f_left, f_centre, f_right = to_hz(left), to_hz(centre), to_hz(right)
+
+    bin_hz = np.linspace(0.0, nyquist, n_bins)
+    starts = np.zeros(n_bins, dtype=np.int32)
+    counts = np.zeros(n_bins, dtype=np.int32)
+    bands = []
+    for j in range(n_bins):
+        lo = max(1, int(np.searchsorted(bin_hz, f_left[j], side="right")))
+        hi = int(np.searchsorted(bin_hz, f_right[j], side="left"))      # exclusive
+        f = bin_hz[lo:hi]
+        w = np.minimum((f - f_left[j]) / (f_centre[j] - f_left[j]),
+                       (f_right[j] - f) / (f_right[j] - f_centre[j]))
+        keep = w > 0
+        if keep.any():
+            first = int(np.argmax(keep))
+            last = len(keep) - int(np.argmax(keep[::-1]))
+            starts[j], counts[j] = lo + first, last - first
+            bands.append(np.maximum(w[first:last], 0.0))
+        else:
+            bands.append(np.zeros(0))
+    width = max(1, int(counts.max()))
+    weights = np.zeros((n_bins, width), dtype=np.float64)
+    for j, b in enumerate(bands):
+        weights[j, :len(b)] = b
+    return starts, counts, weights
+
+
+def dense_mel_matrix(starts, counts, weights) -> np.ndarray:
+    """``[n linear, n mel]`` dense matrix equivalent to a band table."""
+    n = len(starts)
+    m = np.zeros((n, n), dtype=np.float64)
+    for j in range(n):
+        m[starts[j]:starts[j] + counts[j], j] = weights[j, :counts[j]]
+    return m
+
+
+class SpectrogramsHelper(nn.Module):
+    """Linear-frequency log-magnitude + instantaneous-frequency spectrograms."""
+
+    use_mel_scale = False
+
+    def __init__(self, fs_hz: int = 16000, n_fft: int = 2048, hop_length: int = 512,
+                 window_length: int = 2048, safelog_eps: float = 1e-6, *,
+                 pad_left: Optional[int] = None, n_frames: Optional[int] = None,
+                 drop_bin: str = "dc", window_periodic: bool = True):
+        super().__init__()
+        if n_fft not in SUPPORTED_N_FFT:
+            raise ValueError(f"n_fft must be one of {SUPPORTED_N_FFT}, got {n_fft}")
+        if not 0 < window_length <= n_fft:
+            raise ValueError("window_length must be in (0, n_fft]")
+        if drop_bin not in ("dc", "nyquist"):
+            raise ValueError("drop_bin must be 'dc' or 'nyquist'")
+        self.fs_hz = fs_hz
+        self.n_fft = n_fft
+        self.hop_length = hop_length
+        self.window_length = window_length
+        self.safelog_eps = safelog_eps
+        self.pad_left = n_fft - hop_length if pad_left is None else pad_left
+        self.fixed_n_frames = n_frames
+        self.drop_bin = drop_bin
+
+        w = torch.hann_window(window_length, periodic=window_periodic, dtype=torch.float64)
+        if window_length < n_fft:
+            lead = (n_fft - window_length) // 2
+            w = torch.nn.functional.pad(w, (lead, n_fft - window_length - lead))
+        self.register_buffer("window", w.float(), persistent=False)
+        ang = -2.0 * math.pi * torch.arange(n_fft, dtype=torch.float64) / n_fft
+        self.register_buffer("twiddle", torch.stack([ang.cos(), ang.sin()], dim=1).float(),
+                             persistent=False)
+
+    # ------------------------------------------------------------------
+    @property
+    def n_freq(self) -> int:
+        return self.n_fft // 2
+
+    def num_frames(self, n_samples: int) -> int:
+        if self.fixed_n_frames is not None:
+            return self.fixed_n_frames
+        return max(1, math.ceil((n_samples + self.pad_left) / self.hop_length))
+
+    def _params(self, n_frames: int) -> "_lib.MelifParams":
+        p = _lib.MelifParams()
+        p.n_fft, p.hop, p.pad_left, p.n_frames = self.n_fft, self.hop_length, self.pad_left, n_frames
+        p.drop_dc = 1 if self.drop_bin == "dc" else 0
+        p.use_mel, p.mel_width = 0, 0
+        p.safelog_eps = self.safelog_eps
+        p.window, p.twiddle = self.window.data_ptr(), self.twiddle.data_ptr()
+        p.mel_start = p.mel_count = p.mel_weight = None
+        return p
+
+    def to_spectrogram(self, audio: torch.Tensor) -> torch.Tensor:
+        """``audio [B, T]`` (or ``[T]``) -> ``[B, 2, n_fft/2, frames]`` FP32 on the same GPU."""
+        _lib.require_cuda(audio, "audio")
+        if audio.dim() == 1:
+            audio = audio[None]
+        if audio.dim() != 2:
+            raise ValueError(f"audio must be [batch, samples], got {tuple(audio.shape)}")
+        if self.window.device != audio.device:
+            raise RuntimeError("helper and audio live on different devices; call .to(device)")
+        a = audio.detach()
+        if a.dtype != torch.float32:
+            a = a.float()
+        if not a.is_contiguous():
+            a = a.contiguous()
+        n_notes, n_samples = a.shape
+        frames = self.num_frames(n_samples)
+        if self.hop_length * (frames - 1) + self.n_fft - n_samples - self.pad_left < 0:
+            raise ValueError("n_frames too small for the audio length")
+        out = torch.empty(n_notes, 2, self.n_freq, frames, dtype=torch.float32, device=a.device)
+        params = self._params(frames)
+        _lib.invoke("isi_melif_forward", a.data_ptr(), n_notes, n_samples, params,
+                                                 out.data_ptr(), _lib.stream_ptr(a.device))
+        return out
+
+    forward = to_spectrogram
+
+
+class MelSpectrogramsHelper(SpectrogramsHelper):
+    """Mel-scaled variant: log of the mel-projected squared magnitude and the IF of the
+    mel-projected unwrapped phase (GANSynth ``specgrams_to_melspecgrams``)."""
+
+    use_mel_scale = True
+
+    def __init__(self, fs_hz: int = 16000, n_fft: int = 2048, hop_length: int = 512,
+                 window_length: int = 2048, safelog_eps: float = 1e-6,
+                 lower_edge_hertz: float = 0.0, upper_edge_hertz: float = 8000.0,
+                 mel_break_frequency_hertz: float = 700.0,
+                 mel_bin_width_threshold_factor: float = 1.5, **knobs):
+        super().__init__(fs_hz, n_fft, hop_length, window_length, safelog_eps, **knobs)
+        self.lower_edge_hertz = lower_edge_hertz
+        self.upper_edge_hertz = upper_edge_hertz
+        self.mel_break_frequency_hertz = mel_break_frequency_hertz
+        self.mel_bin_width_threshold_factor = mel_bin_width_threshold_factor
+        starts, counts, weights = mel_band_table(
+            n_fft, fs_hz, lower_edge_hertz, upper_edge_hertz, mel_break_frequency_hertz,
+            mel_bin_width_threshold_factor)
+        self.register_buffer("mel_start", torch.from_numpy(starts), persistent=False)
+        self.register_buffer("mel_count", torch.from_numpy(counts), persistent=False)
+        self.register_buffer("mel_weight", torch.from_numpy(weights).float().contiguous(),
+                             persistent=False)
+
+    def _params(self, n_frames: int) -> "_lib.MelifParams":
+        p = super()._params(n_frames)
+        p.use_mel, p.mel_width = 1, self.mel_weight.shape[1]
+        p.mel_start, p.mel_count = self.mel_start.data_ptr(), self.mel_count.data_ptr()
+        p.mel_weight = self.mel_weight.data_ptr()
+        return p

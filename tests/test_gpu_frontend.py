@@ -1,0 +1,65 @@
+"""GPU parity of the fused front-end kernel against the (unpinned) CPU restatement."""
+import pytest
+import torch
+
+from interactive_spectrogram_inpainting_b200.utils import synthetic
+from interactive_spectrogram_inpainting_b200.utils.misc import get_spectrograms_helper
+from interactive_spectrogram_inpainting_b200.utils.spectrograms_helper import (
+    MelSpectrogramsHelper, SpectrogramsHelper)
+from oracle import frontend_oracle as fo
+from test_melif_emulation import check_against_oracle
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.mark.parametrize("use_mel", [True, False])
+def test_nsynth_shape_matches_oracle(use_mel):
+    audio = synthetic.synthetic_notes(3)
+    helper = get_spectrograms_helper(
+        fs_hz=16000, n_fft=2048, hop_length=512, window_length=2048, use_mel_scale=use_mel,
+        mel_scale_lower_edge_hertz=0.0, mel_scale_upper_edge_hertz=8000.0,
+        mel_scale_break_frequency_hertz=700.0, mel_scale_expand_resolution_factor=1.5).to(DEV)
+    spec = helper.to_spectrogram(audio.to(DEV))
+    assert spec.shape == (3, 2, 1024, 128) and spec.dtype == torch.float32
+    excluded = check_against_oracle(spec.cpu(), audio, fo.FrontEndConfig(use_mel_scale=use_mel))
+    print(f"[front end] mel={use_mel}: {excluded:.3%} positions ill-conditioned in FP32")
+
+
+@pytest.mark.parametrize("n_fft,hop,samples", [(1024, 256, 9000), (512, 128, 4099),
+                                               (2048, 512, 300), (2048, 512, 96001)])
+def test_other_sizes_and_ragged_lengths(n_fft, hop, samples):
+    audio = synthetic.synthetic_notes(2, n_samples=samples)
+    helper = MelSpectrogramsHelper(n_fft=n_fft, hop_length=hop, window_length=n_fft).to(DEV)
+    cfg = fo.FrontEndConfig(n_fft=n_fft, hop_length=hop, window_length=n_fft)
+    spec = helper.to_spectrogram(audio.to(DEV))
+    assert spec.shape[-1] == fo.frame_geometry(cfg, samples)[2]
+    check_against_oracle(spec.cpu(), audio, cfg)
+
+
+def test_knobs_nyquist_symmetric_window():
+    audio = synthetic.synthetic_notes(1, n_samples=16000)
+    helper = SpectrogramsHelper(drop_bin="nyquist", window_periodic=False).to(DEV)
+    cfg = fo.FrontEndConfig(use_mel_scale=False, drop_bin="nyquist", window_periodic=False)
+    check_against_oracle(helper.to_spectrogram(audio.to(DEV)).cpu(), audio, cfg)
+
+
+def test_silence_and_batch_independence():
+    helper = MelSpectrogramsHelper().to(DEV)
+    audio = synthetic.synthetic_notes(5).to(DEV)
+    audio[2] = 0
+    spec = helper.to_spectrogram(audio)
+    assert torch.isfinite(spec).all()
+    assert torch.allclose(spec[2, 0], torch.full_like(spec[2, 0], float(torch.log(torch.tensor(1e-6)))))
+    assert (spec[2, 1] == 0).all()
+    alone = helper.to_spectrogram(audio[3:4])
+    assert torch.equal(alone[0], spec[3])          # notes do not interact; deterministic
+
+
+def test_full_batch_size_property():
+    """cfg 2 batch (256 notes): every note equals the same note run alone."""
+    helper = MelSpectrogramsHelper().to(DEV)
+    audio = synthetic.synthetic_notes(256).to(DEV)
+    spec = helper.to_spectrogram(audio)
+    for i in (0, 100, 255):
+        assert torch.equal(helper.to_spectrogram(audio[i:i + 1])[0], spec[i])

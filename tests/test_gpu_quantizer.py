@@ -1,0 +1,172 @@
+"""GPU parity of the quantiser kernels (through the C ABI) against the golden fixtures
+generated from the unmodified reference class and against the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from interactive_spectrogram_inpainting_b200.utils import synthetic
+from interactive_spectrogram_inpainting_b200.vqvae.bottleneck import QuantizedBottleneck
+from oracle import quantizer_oracle as qo
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+NEAR_TIE = 1e-5          # BASELINE.json north_star: relative distance gap of a near tie
+ALGOS = ["simt", "auto"]
+
+
+def make(dim, n_embed, embed, algo="auto", **kw):
+    m = QuantizedBottleneck(dim, n_embed, **kw).to(DEV)
+    m.embed.copy_(torch.as_tensor(embed))
+    m.embed_avg.copy_(torch.as_tensor(embed))
+    m.assign_algo = algo
+    return m
+
+
+def assert_indices_match(got, rows_cpu, embed_cpu, want=None):
+    """bit-exact outside FP64 near ties; returns (near_ties, mismatches_inside_near_ties)."""
+    ind64, gap = qo.assign_fp64(rows_cpu, embed_cpu)
+    want = ind64 if want is None else want.reshape(-1)
+    got = got.reshape(-1).cpu()
+    clear = gap > NEAR_TIE
+    assert torch.equal(got[clear], want[clear]), \
+        f"{(got[clear] != want[clear]).sum().item()} mismatches outside near ties"
+    return int((~clear).sum()), int((got[~clear] != want[~clear]).sum())
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_eval_golden_cfg1(golden_dir, algo):
+    g = np.load(golden_dir / "quantizer_eval_cfg1.npz")
+    m = make(64, 512, g["embed"], algo).eval()
+    for name in ("top", "bottom"):
+        x = torch.from_numpy(g[f"x_{name}"])
+        quant, diff, ind, perp = m(x.to(DEV))
+        assert ind.dtype == torch.int64 and ind.shape == x.shape[:-1] and quant.shape == x.shape
+        near, _ = assert_indices_match(ind, x.reshape(-1, 64), torch.from_numpy(g["embed"]),
+                                       torch.from_numpy(g[f"ind_{name}"]))
+        assert near <= 0.005 * ind.numel()
+        same = (ind.cpu() == torch.from_numpy(g[f"ind_{name}"]))
+        np.testing.assert_array_equal(quant.cpu()[same].numpy(), g[f"quantize_{name}"][same.numpy()])
+        if bool(same.all()):
+            np.testing.assert_allclose(diff.item(), g[f"diff_{name}"], rtol=1e-5)
+            np.testing.assert_allclose(perp.item(), g[f"perplexity_{name}"], rtol=1e-5)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_train_golden_three_ema_steps(golden_dir, algo):
+    g = np.load(golden_dir / "quantizer_train_3steps.npz")
+    m = make(64, 512, g["embed0"], algo).train()
+    m_embed_before = torch.from_numpy(g["embed0"])
+    for step in range(3):
+        x = torch.from_numpy(g[f"x{step}"])
+        quant, diff, ind, perp = m(x.to(DEV))
+        if not np.array_equal(ind.cpu().numpy(), g[f"ind{step}"]):
+            assert_indices_match(ind, x, m_embed_before, torch.from_numpy(g[f"ind{step}"]))
+            pytest.skip("near-tie flip changed the EMA trajectory; covered by the oracle test")
+        np.testing.assert_allclose(m.cluster_size.cpu().numpy(), g[f"cluster_size_after{step}"],
+                                   rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(m.embed_avg.cpu().numpy(), g[f"embed_avg_after{step}"],
+                                   rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(m.embed.cpu().numpy(), g[f"embed_after{step}"],
+                                   rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(diff.item(), g[f"diff{step}"], rtol=1e-5)
+        np.testing.assert_allclose(perp.item(), g[f"perplexity{step}"], rtol=1e-5)
+        m_embed_before = m.embed.cpu().clone()
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+def test_edge_golden_ties_strided_input_and_embed_code(golden_dir, algo):
+    g = np.load(golden_dir / "quantizer_edge.npz")
+    m = make(8, 20, g["embed"], algo).eval()
+    x = torch.from_numpy(g["nchw"]).to(DEV).permute(0, 2, 3, 1)
+    assert not x.is_contiguous()
+    quant, diff, ind, perp = m(x)
+    np.testing.assert_array_equal(ind.cpu().numpy(), g["ind"])      # duplicates -> lowest index
+    np.testing.assert_array_equal(quant.cpu().numpy(), g["quantize"])
+    assert quant.permute(0, 3, 1, 2).is_contiguous()                 # same strides as the input
+    np.testing.assert_allclose(diff.item(), g["diff"], rtol=1e-6)
+    np.testing.assert_allclose(perp.item(), g["perplexity"], rtol=1e-6)
+    looked = m.embed_code(torch.from_numpy(g["codes"]).to(DEV))
+    np.testing.assert_array_equal(looked.cpu().numpy(), g["looked_up"])
+    assert looked.permute(0, 3, 1, 2).is_contiguous()                # NCHW storage for the decoder
+    m.embed_code_channels_first = False
+    flat = m.embed_code(torch.from_numpy(g["codes"]).to(DEV))
+    assert flat.is_contiguous() and torch.equal(flat, looked)
+
+
+@pytest.mark.parametrize("algo", ALGOS)
+@pytest.mark.parametrize("dim,n_embed,rows", [(64, 512, 40960), (128, 4096, 8192), (64, 512, 1),
+                                              (64, 512, 130), (24, 100, 1000), (64, 1000, 777)])
+def test_against_oracle_seeded(dim, n_embed, rows, algo):
+    embed = synthetic.synthetic_codebook(dim, n_embed)
+    x = synthetic.synthetic_features(rows, embed)
+    m = make(dim, n_embed, embed, algo).eval()
+    quant, diff, ind, perp = m(x.to(DEV))
+    near, flipped = assert_indices_match(ind, x, embed)
+    print(f"[near-ties] D={dim} K={n_embed} N={rows} algo={algo}: {near} near ties, "
+          f"{flipped} resolved differently from FP64")
+    st = qo.CodebookState(embed.clone(), torch.zeros(n_embed), embed.clone())
+    oq, od, oi, op = qo.forward(st, x)
+    same = ind.cpu() == oi
+    assert torch.equal(quant.cpu()[same], oq[same])
+    scale = oq.abs().max()
+    assert (quant.cpu() - qo.dequantise(ind.cpu(), embed)).abs().max() <= 1e-4 * scale
+    if bool(same.all()):
+        assert abs(diff.item() - od.item()) <= 1e-5 * od.item()
+        assert abs(perp.item() - op.item()) <= 1e-5 * op.item()
+
+
+def test_ema_100_steps_against_oracle():
+    dim, n_embed = 64, 512
+    embed = synthetic.synthetic_codebook(dim, n_embed)
+    m = make(dim, n_embed, embed, "simt").train()
+    st = qo.CodebookState(embed.clone(), torch.zeros(n_embed), embed.clone())
+    for step in range(100):
+        x = synthetic.synthetic_features(2048, st.embed, 5000 + step)
+        _, _, ind, _ = m(x.to(DEV))
+        # drive the oracle with the kernel's own indices so a near-tie flip cannot fork the
+        # trajectories; index parity itself is tested above
+        qo.ema_update(st, x, ind.cpu(), 0.99, 1e-5)
+    for got, want in ((m.cluster_size, st.cluster_size), (m.embed_avg, st.embed_avg),
+                      (m.embed, st.embed)):
+        err = (got.cpu() - want).abs().max() / want.abs().max()
+        assert err <= 1e-5, err
+
+
+def test_straight_through_gradients():
+    dim, n_embed = 64, 512
+    embed = synthetic.synthetic_codebook(dim, n_embed)
+    x = synthetic.synthetic_features(512, embed).view(2, 16, 16, dim)
+    m = make(dim, n_embed, embed).eval()
+    xg = x.to(DEV).requires_grad_(True)
+    quant, diff, ind, perp = m(xg)
+    w = torch.linspace(-1, 1, x.numel()).view_as(x)
+    (quant * w.to(DEV)).sum().add(0.25 * diff).backward()
+    xc = x.clone().requires_grad_(True)
+    q = qo.dequantise(ind.cpu(), embed)
+    ((xc + (q - xc).detach()) * w).sum().add(0.25 * ((q.detach() - xc) ** 2).mean()).backward()
+    torch.testing.assert_close(xg.grad.cpu(), xc.grad, rtol=1e-5, atol=1e-7)
+
+
+def test_corruption_shifts_by_at_most_one():
+    dim, n_embed = 64, 512
+    embed = synthetic.synthetic_codebook(dim, n_embed)
+    x = synthetic.synthetic_features(4096, embed).to(DEV)
+    clean = make(dim, n_embed, embed).eval()(x)[2]
+    noisy = make(dim, n_embed, embed, corruption_weights=[0.1, 0.8, 0.1]).train()(x)[2]
+    d = (noisy - clean) % n_embed
+    assert set(d.unique().tolist()) <= {0, 1, n_embed - 1}
+    assert 0.1 < (d != 0).float().mean().item() < 0.3
+
+
+def test_full_size_properties_cfg2_batch():
+    """BASELINE cfg 2/4 sizes, checked through size-independent properties: re-quantising a
+    code word returns its own index (idempotence), and the usage histogram sums to N."""
+    dim, n_embed = 64, 512
+    embed = synthetic.synthetic_codebook(dim, n_embed)
+    m = make(dim, n_embed, embed).eval()
+    x = synthetic.synthetic_features(1 << 20, embed).to(DEV)
+    quant, diff, ind, perp = m(x)
+    q2, diff2, ind2, _ = m(m.embed_code(ind))
+    assert torch.equal(ind2, ind) and diff2.item() < 1e-12
+    assert torch.bincount(ind.view(-1), minlength=n_embed).sum().item() == x.shape[0]
+    assert 1.0 <= perp.item() <= n_embed

@@ -1,0 +1,117 @@
+"""CPU checks of the front-end device code: the per-thread phases of
+csrc/melif_core.cuh are compiled with g++ (tests/emu/melif_emu.cpp) and run in kernel
+order, then compared with the oracle.  Also pins the host-side mel band table."""
+import ctypes
+import math
+import pathlib
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from interactive_spectrogram_inpainting_b200.utils import spectrograms_helper as sh
+from interactive_spectrogram_inpainting_b200.utils import synthetic
+from oracle import frontend_oracle as fo
+
+ROOT = pathlib.Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    so = tmp_path_factory.mktemp("emu") / "melif_emu.so"
+    subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-std=c++17",
+                    f"-I{ROOT / 'interactive_spectrogram_inpainting_b200' / 'csrc'}",
+                    "-o", str(so), str(ROOT / "tests" / "emu" / "melif_emu.cpp")], check=True)
+    lib = ctypes.CDLL(str(so))
+    lib.melif_emulate.restype = ctypes.c_int
+    return lib
+
+
+def _run(emu, helper, audio):
+    n_notes, n_samples = audio.shape
+    frames = helper.num_frames(n_samples)
+    out = np.zeros((n_notes, 2, helper.n_freq, frames), dtype=np.float32)
+    a = np.ascontiguousarray(audio.numpy())
+    ptr = lambda arr: arr.ctypes.data_as(ctypes.c_void_p)
+    win = helper.window.numpy()
+    tw = helper.twiddle.numpy()
+    if helper.use_mel_scale:
+        ms, mc, mw = helper.mel_start.numpy(), helper.mel_count.numpy(), helper.mel_weight.numpy()
+        width = mw.shape[1]
+        mel_args = (ptr(ms), ptr(mc), ptr(mw))
+    else:
+        width, mel_args = 0, (None, None, None)
+    rc = emu.melif_emulate(ptr(a), ctypes.c_int64(n_notes), ctypes.c_int64(n_samples),
+                           helper.n_fft, helper.hop_length, helper.pad_left, frames,
+                           1 if helper.drop_bin == "dc" else 0, int(helper.use_mel_scale), width,
+                           ctypes.c_float(helper.safelog_eps), ptr(win), ptr(tw), *mel_args,
+                           ptr(out))
+    assert rc == 0
+    return torch.from_numpy(out)
+
+
+def check_against_oracle(got, audio, cfg, max_excluded=0.35):
+    """Shared with the GPU parity test.  Tolerance of BASELINE.json's north star: 1e-4
+    relative to the channel's max-abs, against the FP64 evaluation of the oracle.
+
+    FP32 cannot meet 1e-4 at *every* position of this transform -- the FP32 torch
+    restatement itself misses it at ~0.2 % of positions, where a bin sits > 80 dB under
+    its frame's peak (phase = atan2 of rounding noise) or a phase step sits on the +-pi
+    wrap (the IF is discontinuous there).  So:
+      * log-magnitude: <= 1e-4 x max-abs at >= 99.9 % of positions, never worse than 0.05;
+      * IF on well-conditioned positions (FP64 mask: bin within 80 dB of its frame peak,
+        step not within 1e-3 rad of the wrap; 65-90 % of positions on the synthetic notes): <= 1e-4 x max-abs
+        at >= 99.97 %, never worse than 5e-4;
+      * IF everywhere: <= 1e-3 at >= 99.97 %, wrap flips (error ~2) at <= 5e-5.
+    Returns the excluded (ill-conditioned) fraction."""
+    want = fo.to_spectrogram(audio.double(), cfg)
+    stable = fo.stability_mask(audio, cfg, wrap_margin=1e-3, mag_floor=1e-4)
+    err0 = (got[:, 0].double() - want[:, 0]).abs()
+    tol0 = 1e-4 * want[:, 0].abs().max()
+    assert err0.max() < 0.05, err0.max()
+    assert (err0 > tol0).double().mean() < 1e-3
+    err1 = (got[:, 1].double() - want[:, 1]).abs()
+    tol1 = 1e-4 * want[:, 1].abs().max().clamp_min(1.0)
+    assert err1[stable].max() <= 5 * tol1, err1[stable].max()
+    assert (err1[stable] > tol1).double().mean() < 3e-4
+    assert (err1 > 10 * tol1).double().mean() < 3e-4
+    assert (err1 > 100 * tol1).double().mean() < 5e-5
+    excluded = 1.0 - stable.double().mean().item()
+    assert excluded < max_excluded, excluded
+    return excluded
+
+
+def test_band_table_equals_dense_recipe():
+    cfg = fo.FrontEndConfig()
+    starts, counts, weights = sh.mel_band_table(2048, 16000, 0.0, 8000.0, 700.0, 1.5)
+    np.testing.assert_allclose(sh.dense_mel_matrix(starts, counts, weights),
+                               fo.linear_to_mel_matrix(cfg), rtol=0, atol=1e-12)
+    assert weights.shape[1] <= 8
+
+
+@pytest.mark.parametrize("use_mel", [True, False])
+def test_emulated_kernel_matches_oracle_2048(emu, use_mel):
+    audio = synthetic.synthetic_notes(2)
+    helper = (sh.MelSpectrogramsHelper() if use_mel else sh.SpectrogramsHelper())
+    got = _run(emu, helper, audio)
+    assert got.shape == (2, 2, 1024, 128)
+    check_against_oracle(got, audio, fo.FrontEndConfig(use_mel_scale=use_mel))
+
+
+@pytest.mark.parametrize("n_fft,hop,samples", [(1024, 256, 9000), (512, 128, 4099)])
+def test_emulated_kernel_other_sizes_and_ragged_lengths(emu, n_fft, hop, samples):
+    audio = synthetic.synthetic_notes(1, n_samples=samples)
+    helper = sh.MelSpectrogramsHelper(n_fft=n_fft, hop_length=hop, window_length=n_fft)
+    got = _run(emu, helper, audio)
+    cfg = fo.FrontEndConfig(n_fft=n_fft, hop_length=hop, window_length=n_fft)
+    assert got.shape[-1] == fo.frame_geometry(cfg, samples)[2]
+    check_against_oracle(got, audio, cfg)
+
+
+def test_emulated_kernel_nyquist_knob(emu):
+    audio = synthetic.synthetic_notes(1, n_samples=16000)
+    helper = sh.SpectrogramsHelper(drop_bin="nyquist", window_periodic=False)
+    got = _run(emu, helper, audio)
+    cfg = fo.FrontEndConfig(use_mel_scale=False, drop_bin="nyquist", window_periodic=False)
+    check_against_oracle(got, audio, cfg)

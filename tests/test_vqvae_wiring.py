@@ -1,0 +1,33 @@
+"""The product's VQVAE wiring (torch convs around the quantiser) against the unmodified
+reference VQVAE on the CPU, with the oracle quantiser plugged into ours."""
+import pytest
+import torch
+
+from interactive_spectrogram_inpainting_b200.vqvae.vqvae import VQVAE
+from oracle import ref_loader
+from oracle.quantizer_oracle import OracleBottleneck
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference checkout not present")
+@pytest.mark.parametrize("factors", [{'bottom': 16, 'top': 2}, {'bottom': 8, 'top': 4},
+                                     {'bottom': 4, 'top': 2}])
+def test_state_dict_and_encode_match_reference(factors):
+    RefVQVAE = ref_loader.load_reference_vqvae_class()
+    torch.manual_seed(0)
+    ref = RefVQVAE(in_channel=2, resolution_factors=factors,
+                   adapt_quantized_durations=False).eval()
+    ours = VQVAE(in_channel=2, resolution_factors=factors, adapt_quantized_durations=False,
+                 bottleneck_cls=OracleBottleneck).eval()
+    missing, unexpected = ours.load_state_dict(ref.state_dict(), strict=True), None
+    x = torch.randn(2, 2, 256, 32)
+    with torch.no_grad():
+        r = ref.encode(x.clone())
+        o = ours.encode(x.clone())
+        assert torch.equal(r[3], o[3]) and torch.equal(r[4], o[4])
+        torch.testing.assert_close(r[0], o[0])
+        torch.testing.assert_close(r[1], o[1])
+        torch.testing.assert_close(r[2], o[2])
+        rd = ref.decode_code(r[3], r[4])
+        od = ours.decode_code(o[3], o[4])
+        torch.testing.assert_close(rd, od)
+    assert sum(p.numel() for p in ours.parameters()) == sum(p.numel() for p in ref.parameters())
