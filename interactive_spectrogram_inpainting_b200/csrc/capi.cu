@@ -52,7 +52,7 @@ ISI_API int isi_vq_prepare_codebook(const float* embed, int dim, int n_embed, vo
   if (!embed || !prepared) return ISI_ERR_NULL;
   if (dim <= 0 || n_embed <= 0) return ISI_ERR_SHAPE;
   if (prepared_bytes < isi_vq_prepared_bytes(dim, n_embed)) return ISI_ERR_WORKSPACE;
-  if ((uintptr_t)prepared % 1024) return ISI_ERR_ALIGN;
+  if ((uintptr_t)prepared % 256) return ISI_ERR_ALIGN;
   Prepared p = prepared_view(prepared, dim, n_embed);
   int rc = launch_prepare(embed, dim, n_embed, p, (cudaStream_t)stream);
   if (rc) return rc;

@@ -2,86 +2,211 @@
 //
 // Replaces SpectrogramsHelper / MelSpectrogramsHelper.to_spectrogram (external
 // GANsynth_pytorch; reference call sites utils/misc.py:10-29, extract_code.py:199-206,
-// train_vqvae.py:604-611).  One CTA owns one note and walks its frames in batches of
-// FB: the audio samples are read once per overlapping frame (L1/L2 hits), the complex
-// spectrum, magnitudes and phases never leave shared memory / registers, and the only
-// HBM write is the final [2, F, T'] tensor, FB consecutive time steps per row at a time.
+// train_vqvae.py:604-611).
+//
+// One CTA owns one note and walks its frames in batches of FB.  Per batch the audio span
+// (FB-1)*hop + n_fft samples is brought into shared memory by ONE bulk async copy
+// (cp.async.bulk, the 1-D TMA path, completion on an mbarrier) issued a whole batch ahead,
+// so HBM latency is hidden behind the previous batch's FFT.  Twiddles and the window sit in
+// shared memory, the mel band of each output row in registers; the complex spectrum,
+// magnitudes and phases never leave shared memory / registers.  The only HBM traffic is
+// the audio once (plus the frame overlap from L2) and the final [2, F, T'] tensor, written
+// FB consecutive time steps (one 32-byte sector at FB = 8) per row at a time.
 #include "common.cuh"
 #include "melif_core.cuh"
 
 namespace isi {
 using namespace melif;
 
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes,
+                                         uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+struct MelifSmem {
+  // byte offsets into dynamic shared memory
+  int tw, win, stage, za, zb, bar, total;
+};
+
+template <int NFFT, int FB>
+__host__ __device__ inline MelifSmem melif_smem_layout(int hop) {
+  using P = Plan<NFFT>;
+  MelifSmem s;
+  int off = 0;
+  s.tw = off;    off += NFFT * 8;
+  s.win = off;   off += NFFT * 4;
+  s.stage = off; off += (((FB - 1) * hop + NFFT + 3) / 4) * 16;
+  s.za = off;    off += FB * P::kPitchA * 8;
+  s.zb = off;    off += FB * P::kPitchB * 8;
+  s.bar = off;   off += 16;
+  s.total = off;
+  return s;
+}
+
 template <int NFFT, int FB, int NT>
-__global__ void __launch_bounds__(NT)
+__global__ void __launch_bounds__(NT, 1)
 melif_kernel(const float* __restrict__ audio, int64_t n_samples, isi_melif_params p,
-             float* __restrict__ out) {
+             float* __restrict__ out, int bulk_ok) {
   using P = Plan<NFFT>;
   constexpr int M = P::M;
-  constexpr int IPT = (M / 2) / NT;   // polar work items per thread
-  constexpr int RPT = M / NT;         // output rows per thread
-  static_assert(IPT >= 1 && (M / 2) % NT == 0, "thread count must divide the item count");
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  cpx* zbuf = reinterpret_cast<cpx*>(smem_raw);   // [FB][M]
+  constexpr int RPT = M / NT;                 // output rows per thread
+  constexpr int kGroups = NT / 64;            // frames transformed concurrently
+  static_assert(NT == M / 2, "one polar work item per thread");
+  extern __shared__ __align__(128) unsigned char smem[];
+  const MelifSmem L = melif_smem_layout<NFFT, FB>(p.hop);
+  cpx* tw = reinterpret_cast<cpx*>(smem + L.tw);
+  float* win = reinterpret_cast<float*>(smem + L.win);
+  float* stage = reinterpret_cast<float*>(smem + L.stage);
+  cpx* zA = reinterpret_cast<cpx*>(smem + L.za);
+  cpx* zB = reinterpret_cast<cpx*>(smem + L.zb);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar);
 
   const int tid = threadIdx.x;
   const float* note = audio + (int64_t)blockIdx.x * n_samples;
   float* out0 = out + (int64_t)blockIdx.x * 2 * M * p.n_frames;
   float* out1 = out0 + (int64_t)M * p.n_frames;
-  const cpx* tw = reinterpret_cast<const cpx*>(p.twiddle);
-  const bool use_mel = p.use_mel != 0, drop_dc = p.drop_dc != 0;
+  const bool use_mel = p.use_mel != 0;
+  const int dc = p.drop_dc ? 1 : 0;
+  const float eps = p.safelog_eps;
+  const int span = (FB - 1) * p.hop + NFFT;
 
-  BinState sa[IPT], sb[IPT];
-  RowState rs[RPT];
+  // ---- one-time setup: tables to shared memory, per-thread constants to registers ----
+  for (int i = tid; i < NFFT; i += NT) {
+    tw[i] = reinterpret_cast<const cpx*>(p.twiddle)[i];
+    win[i] = p.window[i];
+  }
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  const cpx w_item = reinterpret_cast<const cpx*>(p.twiddle)[tid];
+  int row_bin[RPT], row_cnt[RPT];
+  float row_w[RPT][kMaxMelWidth];
+  float row_prev[RPT];
 #pragma unroll
-  for (int i = 0; i < IPT; ++i) { sa[i] = BinState{0.f, 0.f}; sb[i] = BinState{0.f, 0.f}; }
+  for (int r = 0; r < RPT; ++r) {
+    const int row = tid + r * NT;
+    row_prev[r] = 0.f;
+    row_cnt[r] = 0;
+    row_bin[r] = row + dc;
 #pragma unroll
-  for (int r = 0; r < RPT; ++r) rs[r] = RowState{0.f};
-
-  for (int f0 = 0; f0 < p.n_frames; f0 += FB) {
-    const int nf = min(FB, p.n_frames - f0);
-    // A: window + pack
-    for (int fb = 0; fb < nf; ++fb)
-      pack_frame<P>(tid, NT, zbuf + fb * M, note, n_samples,
-                    (int64_t)(f0 + fb) * p.hop - p.pad_left, p.window);
-    __syncthreads();
-    // B: in-place FFT, 64 threads per frame
-    for (int fb = tid / 64; fb < nf; fb += NT / 64) fft_pass1<P>(tid & 63, zbuf + fb * M, tw);
-    __syncthreads();
-    for (int fb = tid / 64; fb < nf; fb += NT / 64) fft_pass2<P>(tid & 63, zbuf + fb * M, tw);
-    __syncthreads();
-    for (int fb = tid / 64; fb < nf; fb += NT / 64) fft_pass3<P>(tid & 63, zbuf + fb * M);
-    __syncthreads();
-    // C: untangle + polar + time unwrap (state in registers, frames in order)
-    for (int fb = 0; fb < nf; ++fb) {
+    for (int i = 0; i < kMaxMelWidth; ++i) row_w[r][i] = 0.f;
+    if (use_mel) {
+      row_bin[r] = p.mel_start[row] + dc;
+      row_cnt[r] = p.mel_count[row];
 #pragma unroll
-      for (int i = 0; i < IPT; ++i)
-        polar_item<P>(tid + i * NT, zbuf + fb * M, tw, f0 + fb == 0, use_mel, drop_dc,
-                      p.safelog_eps, sa[i], sb[i]);
+      for (int i = 0; i < kMaxMelWidth; ++i)
+        if (i < p.mel_width) row_w[r][i] = p.mel_weight[(int64_t)row * p.mel_width + i];
     }
+  }
+  BinState sa{1.f, 0.f, 0.f}, sb{1.f, 0.f, 0.f}, sc{1.f, 0.f, 0.f};
+  __syncthreads();
+
+  // stage the audio span of batch `b`: zero-fill what lies outside the note, one bulk copy
+  // for the rest (thread 0), completion signalled on `bar`
+  auto prefetch = [&](int b) {
+    const int64_t s0 = (int64_t)b * FB * p.hop - p.pad_left;
+    const int64_t lo = s0 < 0 ? -s0 : 0;                                   // first valid index
+    int64_t hi = n_samples - s0;                                           // one past last valid
+    hi = hi < 0 ? 0 : (hi > span ? span : hi);
+    const int64_t vlo = lo < hi ? lo : hi;
+    for (int i = tid; i < vlo; i += NT) stage[i] = 0.f;
+    for (int i = (int)hi + tid; i < span; i += NT) stage[i] = 0.f;
+    if (tid == 0) {
+      if (hi > lo) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const uint32_t bytes = (uint32_t)(hi - lo) * 4u;
+        mbar_expect_tx(bar, bytes);
+        bulk_g2s(stage + lo, note + s0 + lo, bytes, bar);
+      } else {
+        mbar_arrive(bar);
+      }
+    }
+  };
+
+  const int n_batches = (p.n_frames + FB - 1) / FB;
+  if (bulk_ok) prefetch(0);
+
+  for (int b = 0; b < n_batches; ++b) {
+    const int f0 = b * FB;
+    const int nf = min(FB, p.n_frames - f0);
+    if (bulk_ok) {
+      mbar_wait(bar, b & 1);
+      if (b == 0) __syncthreads();   // batch 0's zero-filled pad was written by other threads;
+                                     // later batches' pads are ordered by the syncs below
+    } else {
+      __syncthreads();
+      stage_fill(tid, NT, stage, span, note, n_samples, (int64_t)f0 * p.hop - p.pad_left);
+      __syncthreads();
+    }
+    // pass 1: window + pack + radix R1 (64 threads per frame)
+    for (int fb = tid / 64; fb < nf; fb += kGroups)
+      fft_pass1<P>(tid & 63, stage + fb * p.hop, win, tw, zA + fb * P::kPitchA);
     __syncthreads();
-    // D: project / copy rows and write FB consecutive time steps per row
+    if (bulk_ok && b + 1 < n_batches) prefetch(b + 1);
+    for (int fb = tid / 64; fb < nf; fb += kGroups) fft_pass2<P>(tid & 63, tw, zA + fb * P::kPitchA);
+    __syncthreads();
+    for (int fb = tid / 64; fb < nf; fb += kGroups)
+      fft_pass3<P>(tid & 63, zA + fb * P::kPitchA, zB + fb * P::kPitchB);
+    __syncthreads();
+    // polar: frames in order, unwrap state in registers
+    for (int fb = 0; fb < nf; ++fb)
+      polar_item<P>(tid, zB + fb * P::kPitchB, w_item, f0 + fb == 0, use_mel, eps, sa, sb, sc);
+    __syncthreads();
+    // emit: FB consecutive time steps per row
 #pragma unroll
     for (int r = 0; r < RPT; ++r) {
       const int row = tid + r * NT;
-      int ms = 0, mc = 0;
-      const float* mw = nullptr;
-      if (use_mel) { ms = p.mel_start[row]; mc = p.mel_count[row]; mw = p.mel_weight + (int64_t)row * p.mel_width; }
       float v0[FB], v1[FB];
 #pragma unroll
       for (int fb = 0; fb < FB; ++fb) {
         v0[fb] = 0.f; v1[fb] = 0.f;
-        if (fb < nf)
-          emit_row<P>(row, zbuf + fb * M, f0 + fb == 0, use_mel, drop_dc, p.safelog_eps, ms, mc,
-                      mw, rs[r], v0[fb], v1[fb]);
+        if (fb < nf) {
+          if (use_mel)
+            emit_mel(zB + fb * P::kPitchB, row_bin[r], row_cnt[r], row_w[r], f0 + fb == 0, eps,
+                     row_prev[r], v0[fb], v1[fb]);
+          else
+            emit_linear(zB + fb * P::kPitchB, row_bin[r], v0[fb], v1[fb]);
+        }
       }
       float* d0 = out0 + (int64_t)row * p.n_frames + f0;
       float* d1 = out1 + (int64_t)row * p.n_frames + f0;
       if (nf == FB && (FB % 4 == 0) && (p.n_frames % 4 == 0)) {
 #pragma unroll
         for (int q = 0; q < FB / 4; ++q) {
-          reinterpret_cast<float4*>(d0)[q] = make_float4(v0[4 * q], v0[4 * q + 1], v0[4 * q + 2], v0[4 * q + 3]);
-          reinterpret_cast<float4*>(d1)[q] = make_float4(v1[4 * q], v1[4 * q + 1], v1[4 * q + 2], v1[4 * q + 3]);
+          __stcs(reinterpret_cast<float4*>(d0) + q,
+                 make_float4(v0[4 * q], v0[4 * q + 1], v0[4 * q + 2], v0[4 * q + 3]));
+          __stcs(reinterpret_cast<float4*>(d1) + q,
+                 make_float4(v1[4 * q], v1[4 * q + 1], v1[4 * q + 2], v1[4 * q + 3]));
         }
       } else {
 #pragma unroll
@@ -89,18 +214,22 @@ melif_kernel(const float* __restrict__ audio, int64_t n_samples, isi_melif_param
           if (fb < nf) { d0[fb] = v0[fb]; d1[fb] = v1[fb]; }
       }
     }
-    __syncthreads();
   }
 }
 
 template <int NFFT, int FB, int NT>
 static int launch_melif_t(const float* audio, int64_t n_notes, int64_t n_samples,
                           const isi_melif_params& p, float* out, cudaStream_t stream) {
-  size_t smem = (size_t)FB * (NFFT / 2) * sizeof(cpx);
+  const MelifSmem L = melif_smem_layout<NFFT, FB>(p.hop);
+  if (L.total > 227 * 1024) return ISI_ERR_UNSUPPORTED;
   cudaError_t e = cudaFuncSetAttribute(melif_kernel<NFFT, FB, NT>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
   if (e != cudaSuccess) return (int)e;
-  melif_kernel<NFFT, FB, NT><<<(unsigned)n_notes, NT, smem, stream>>>(audio, n_samples, p, out);
+  // the bulk copy needs 16-byte aligned global addresses and sizes
+  const int bulk_ok = (n_samples % 4 == 0) && (p.hop % 4 == 0) && (p.pad_left % 4 == 0) &&
+                      ((uintptr_t)audio % 16 == 0);
+  melif_kernel<NFFT, FB, NT><<<(unsigned)n_notes, NT, L.total, stream>>>(audio, n_samples, p, out,
+                                                                        bulk_ok);
   ISI_LAUNCH_CHECK();
   return ISI_OK;
 }
@@ -108,6 +237,7 @@ static int launch_melif_t(const float* audio, int64_t n_notes, int64_t n_samples
 int launch_melif(const float* audio, int64_t n_notes, int64_t n_samples,
                  const isi_melif_params& p, float* out, cudaStream_t stream) {
   if (n_notes > 0x7fffffff) return ISI_ERR_SHAPE;
+  if (p.use_mel && p.mel_width > kMaxMelWidth) return ISI_ERR_UNSUPPORTED;
   switch (p.n_fft) {
     case 2048: return launch_melif_t<2048, 8, 512>(audio, n_notes, n_samples, p, out, stream);
     case 1024: return launch_melif_t<1024, 8, 256>(audio, n_notes, n_samples, p, out, stream);

@@ -1,17 +1,19 @@
 // Per-thread phases of the fused STFT -> (mel) -> log-magnitude + IF kernel.
 //
-// Everything here is written against an abstract "thread id + shared buffer" so the
+// Everything here is written against an abstract "thread id + shared buffers" so the
 // very same code is compiled by nvcc into melif.cu and by g++ into the CPU emulation
 // that tests/test_melif_emulation.py uses to check the index arithmetic against the
 // oracle without a GPU (the emulation is test infrastructure, not a product path).
 //
 // Transform plan for an n_fft-point real frame (M = n_fft/2 complex points):
-//   pack    z[m] = w[2m] a[2m] + i w[2m+1] a[2m+1]
-//   FFT     in place, decimation in frequency, radices (R1, 16, 4) with R1 = M/64;
-//           bin k = p1 + R1*p2 + 16*R1*p3 ends up at slot (M/R1)*p1 + 4*p2 + p3
-//   untangle X[k], X[M-k] from Z[k], Z[M-k] (one complex multiply per pair)
-//   polar   |X|, angle(X); time-unwrapped phase carried in registers across frames
-//   mel     banded projections of (|X|+eps)^2 and of the unwrapped phase
+//   pass 1  window + pack z[m] = w[2m] a[2m] + i w[2m+1] a[2m+1] straight from the staged
+//           audio, radix R1 = M/64 over stride 64, twiddle, into zA (64-blocks padded by 4)
+//   pass 2  radix 16 over stride 4 inside each 64-block of zA, twiddle, in place
+//   pass 3  radix 4 on consecutive quadruples of zA, written in natural bin order to zB
+//   polar   untangle X[k], X[M-k] from Z[k], Z[M-k]; |X|, phase step = arg(X_t conj X_t-1);
+//           time-unwrapped phase carried in registers; (v0, v1) overwrite zB in place
+//   emit    banded mel projections of (|X|+eps)^2 and of the unwrapped phase (or a copy
+//           in linear mode), log and mel-IF, FB consecutive time steps per row
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -33,8 +35,54 @@ ISI_HD cpx csub(cpx a, cpx b) { return {a.re - b.re, a.im - b.im}; }
 ISI_HD cpx mul_neg_i(cpx a) { return {a.im, -a.re}; }   // a * (-i)
 
 constexpr float kPi = 3.14159265358979323846f;
+constexpr float kHalfPi = 1.57079632679489661923f;
 constexpr float kTwoPi = 6.28318530717958647692f;
+constexpr float kInvTwoPi = 0.15915494309189533577f;
 constexpr float kInvPi = 0.31830988618379067154f;
+
+// ---- fast scalar math (device: MUFU-based; host emulation: libm) ----
+ISI_HD float fast_rcp(float x) {
+#ifdef __CUDA_ARCH__
+  return __frcp_rn(x);
+#else
+  return 1.0f / x;
+#endif
+}
+ISI_HD float fast_rsqrt(float x) {
+#ifdef __CUDA_ARCH__
+  return rsqrtf(x);
+#else
+  return 1.0f / sqrtf(x);
+#endif
+}
+ISI_HD float fast_log(float x) {
+#ifdef __CUDA_ARCH__
+  return __logf(x);
+#else
+  return logf(x);
+#endif
+}
+
+// atan2 with a degree-7 (in a^2) minimax polynomial on [0,1]: |err| < 2e-7 rad.
+// atan2(0, 0) = 0 like torch.angle(0).
+ISI_HD float fast_atan2(float y, float x) {
+  const float ax = fabsf(x), ay = fabsf(y);
+  const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+  const float a = (mx == 0.f) ? 0.f : mn * fast_rcp(mx);
+  const float s = a * a;
+  float p = -0.0040545654483139515f;
+  p = fmaf(p, s, 0.021862952038645744f);
+  p = fmaf(p, s, -0.0559123195707798f);
+  p = fmaf(p, s, 0.0964219719171524f);
+  p = fmaf(p, s, -0.1390862911939621f);
+  p = fmaf(p, s, 0.19946566224098206f);
+  p = fmaf(p, s, -0.33329859375953674f);
+  p = fmaf(p, s, 0.9999993443489075f);
+  float r = p * a;
+  if (ay > ax) r = kHalfPi - r;
+  if (x < 0.f) r = kPi - r;
+  return copysignf(r, y);
+}
 
 // forward 4-point DFT, outputs in natural order
 ISI_HD void dft4(cpx& a0, cpx& a1, cpx& a2, cpx& a3) {
@@ -49,7 +97,6 @@ ISI_HD void dft16(cpx* v) {
   const float h = 0.70710678118654752440f;
 #pragma unroll
   for (int a = 0; a < 4; ++a) dft4(v[a], v[a + 4], v[a + 8], v[a + 12]);      // index a + 4c now
-  // twiddles W16^(a c), W16 = exp(-i pi/8)
   v[1 + 4] = cmul(v[1 + 4], cpx{c1, -s1});      // a=1,c=1 : W^1
   v[1 + 8] = cmul(v[1 + 8], cpx{h, -h});        // a=1,c=2 : W^2
   v[1 + 12] = cmul(v[1 + 12], cpx{s1, -c1});    // a=1,c=3 : W^3
@@ -61,24 +108,20 @@ ISI_HD void dft16(cpx* v) {
   v[3 + 12] = cmul(v[3 + 12], cpx{-c1, s1});    // a=3,c=3 : W^9
 #pragma unroll
   for (int c = 0; c < 4; ++c) dft4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);  // c + 4d at 4c+d
-  // un-transpose: element for k = c + 4d sits at 4c + d
   cpx t;
 #define ISI_SWAP(i, j) t = v[i]; v[i] = v[j]; v[j] = t;
   ISI_SWAP(1, 4) ISI_SWAP(2, 8) ISI_SWAP(3, 12) ISI_SWAP(6, 9) ISI_SWAP(7, 13) ISI_SWAP(11, 14)
 #undef ISI_SWAP
 }
 
-// 8-point and smaller first radices are built from dft4 + one radix-2 layer
 ISI_HD void dft8(cpx* v) {
   // n = a + 2b (a<2, b<4), k = c + 4d (c<4, d<2)
   const float h = 0.70710678118654752440f;
   dft4(v[0], v[2], v[4], v[6]);
   dft4(v[1], v[3], v[5], v[7]);
-  // odd branch twiddles W8^c
   v[3] = cmul(v[3], cpx{h, -h});
   v[5] = mul_neg_i(v[5]);
   v[7] = cmul(v[7], cpx{-h, -h});
-  // v[2c] = even[c], v[2c+1] = odd[c] ; X[c] = e+o, X[c+4] = e-o
   cpx out[8];
 #pragma unroll
   for (int c = 0; c < 4; ++c) { out[c] = cadd(v[2 * c], v[2 * c + 1]); out[c + 4] = csub(v[2 * c], v[2 * c + 1]); }
@@ -95,154 +138,157 @@ template <> ISI_HD void dft_small<4>(cpx* v) { dft4(v[0], v[1], v[2], v[3]); }
 template <int NFFT>
 struct Plan {
   static constexpr int N = NFFT;
-  static constexpr int M = NFFT / 2;      // complex points / output bins
-  static constexpr int R1 = M / 64;       // first radix: 16 (2048), 8 (1024), 4 (512)
-  static constexpr int Q1 = 64;           // M / R1
-  static constexpr int kFftThreads = 64;  // threads cooperating on one frame's FFT
+  static constexpr int M = NFFT / 2;        // complex points; bins 0..M
+  static constexpr int R1 = M / 64;         // first radix: 16 (2048), 8 (1024), 4 (512)
+  static constexpr int kFftThreads = 64;    // threads cooperating on one frame's FFT
+  static constexpr int kPitchA = M + 4 * R1;  // zA: every 64-block padded by 4 (pass-2 banks)
+  static constexpr int kPitchB = M + 2;       // zB: bins 0..M in natural order
   static_assert(R1 == 16 || R1 == 8 || R1 == 4, "n_fft must be 2048, 1024 or 512");
-  // slot of bin k after the three in-place passes
-  static ISI_HD int slot(int k) { return Q1 * (k % R1) + 4 * ((k / R1) % 16) + k / (16 * R1); }
 };
 
-// ---- phase A: window + pack one frame into z[0..M) (thread t of NT) ----
-template <typename P>
-ISI_HD void pack_frame(int t, int nt, cpx* z, const float* audio, int64_t n_samples,
-                       int64_t first_sample, const float* window) {
-  for (int m = t; m < P::M; m += nt) {
-    int64_t i0 = first_sample + 2 * m;
-    float a0 = (i0 >= 0 && i0 < n_samples) ? audio[i0] : 0.f;
-    float a1 = (i0 + 1 >= 0 && i0 + 1 < n_samples) ? audio[i0 + 1] : 0.f;
-    z[m] = cpx{a0 * window[2 * m], a1 * window[2 * m + 1]};
+// ---- synchronous staging of the audio span of one frame batch (emulation, and the
+//      device path when the span is not 16-byte copyable) ----
+ISI_HD void stage_fill(int t, int nt, float* stage, int span, const float* audio,
+                       int64_t n_samples, int64_t first_sample) {
+  for (int i = t; i < span; i += nt) {
+    int64_t s = first_sample + i;
+    stage[i] = (s >= 0 && s < n_samples) ? audio[s] : 0.f;
   }
 }
 
-// twiddle table: tw[j] = exp(-2 pi i j / N) for j in [0, N)
-// ---- phase B1: first pass, radix R1 over stride Q1 (thread j of 64) ----
+// twiddle table: tw[j] = exp(-2 pi i j / N), j in [0, N)
+// ---- pass 1 (thread j of 64): window, pack, radix R1 over stride 64 ----
 template <typename P>
-ISI_HD void fft_pass1(int j, cpx* z, const cpx* tw) {
+ISI_HD void fft_pass1(int j, const float* frame /* stage + fb*hop */, const float* win,
+                      const cpx* tw, cpx* zA) {
   cpx v[P::R1];
 #pragma unroll
-  for (int r = 0; r < P::R1; ++r) v[r] = z[j + P::Q1 * r];
+  for (int r = 0; r < P::R1; ++r) {
+    const int m = j + 64 * r;
+    v[r] = cpx{frame[2 * m] * win[2 * m], frame[2 * m + 1] * win[2 * m + 1]};
+  }
   dft_small<P::R1>(v);
 #pragma unroll
   for (int p = 1; p < P::R1; ++p) v[p] = cmul(v[p], tw[2 * j * p]);   // W_M^(j p) = W_N^(2 j p)
 #pragma unroll
-  for (int p = 0; p < P::R1; ++p) z[j + P::Q1 * p] = v[p];
+  for (int p = 0; p < P::R1; ++p) zA[j + 68 * p] = v[p];
 }
 
-// ---- phase B2: inside each block of 64, radix 16 over stride 4.  64 threads cover
-//      R1 blocks x 4 columns = 4*R1 work items (one, or a half/quarter, per thread) ----
+// ---- pass 2: inside each (padded) 64-block, radix 16 over stride 4 ----
 template <typename P>
-ISI_HD void fft_pass2(int t, cpx* z, const cpx* tw) {
+ISI_HD void fft_pass2(int t, const cpx* tw, cpx* zA) {
   for (int item = t; item < 4 * P::R1; item += P::kFftThreads) {
     const int b = item >> 2, j = item & 3;
-    cpx* blk = z + 64 * b;
+    cpx* blk = zA + 68 * b;
     cpx v[16];
 #pragma unroll
     for (int r = 0; r < 16; ++r) v[r] = blk[j + 4 * r];
     dft16(v);
+    if (j != 0) {
 #pragma unroll
-    for (int p = 1; p < 16; ++p) v[p] = cmul(v[p], tw[(P::N / 64) * j * p]);   // W_64^(j p)
+      for (int p = 1; p < 16; ++p) v[p] = cmul(v[p], tw[(P::N / 64) * j * p]);   // W_64^(j p)
+    }
 #pragma unroll
     for (int p = 0; p < 16; ++p) blk[j + 4 * p] = v[p];
   }
 }
 
-// ---- phase B3: radix-4 on consecutive quadruples ----
+// ---- pass 3: radix 4 on quadruple (p1, p2) of zA -> bins p1 + R1 p2 + 16 R1 p3 of zB.
+//      Lanes run along p1 so the natural-order stores are contiguous. ----
 template <typename P>
-ISI_HD void fft_pass3(int t, cpx* z) {
-  for (int b = t; b < P::M / 4; b += P::kFftThreads) {
-    cpx* q = z + 4 * b;
+ISI_HD void fft_pass3(int t, const cpx* zA, cpx* zB) {
+  constexpr int kStep = P::kFftThreads / P::R1;          // p2 values covered per sweep
+  const int p1 = t % P::R1;
+  for (int p2 = t / P::R1; p2 < 16; p2 += kStep) {
+    const cpx* q = zA + 68 * p1 + 4 * p2;
     cpx a0 = q[0], a1 = q[1], a2 = q[2], a3 = q[3];
     dft4(a0, a1, a2, a3);
-    q[0] = a0; q[1] = a1; q[2] = a2; q[3] = a3;
+    cpx* o = zB + p1 + P::R1 * p2;
+    o[0] = a0; o[16 * P::R1] = a1; o[32 * P::R1] = a2; o[48 * P::R1] = a3;
   }
 }
 
-// numpy-style wrapped phase step (magenta spectral_ops.unwrap): the value that the
-// time-unwrapped phase advances by, given the raw step dd
-ISI_HD float wrapped_step(float dd) {
-  if (fabsf(dd) < kPi) return dd;
-  float m = dd + kPi;
-  m = m - kTwoPi * floorf(m / kTwoPi) - kPi;       // python-style remainder into [-pi, pi)
-  if (m == -kPi && dd > 0.f) m = kPi;
-  return m;
+// phase step folded into [-pi, pi] (round-to-nearest multiple of 2 pi; equals the
+// numpy/magenta unwrap rule except on exact +-pi ties)
+ISI_HD float wrap_step(float dd) {
+  return fmaf(-kTwoPi, rintf(dd * kInvTwoPi), dd);
 }
 
-// running state of one spectrogram bin across frames
-struct BinState { float prev_phase; float unwrapped; };
+// running state of one spectrogram bin across frames: previous spectrum value (exact
+// zeros replaced by 1+0i, whose phase is also 0) and the time-unwrapped phase
+struct BinState { float pre, pim, unwrapped; };
 
-// ---- phase C: work item `it` (0..M/2) of one frame: two bins in, two (v0, v1) out.
-//      Item 0 owns bin M/2 and the real-only bin (Nyquist when drop_dc, else DC);
-//      item it>0 owns bins it and M-it.  Results overwrite the FFT slots they came from.
-//      mel mode : v0 = (|X|+eps)^2, v1 = unwrapped phase
-//      linear   : v0 = log(|X|+eps), v1 = instantaneous frequency
-template <typename P>
-ISI_HD void polar_item(int it, cpx* z, const cpx* tw, bool first_frame, bool use_mel,
-                       bool drop_dc, float eps, BinState& sa, BinState& sb) {
-  const int M = P::M;
-  cpx xa, xb;
-  int slot_a, slot_b;
-  if (it == 0) {
-    cpx z0 = z[P::slot(0)], zh = z[P::slot(M / 2)];
-    xa = cpx{zh.re, -zh.im};                                  // X[M/2] = conj(Z[M/2])
-    xb = drop_dc ? cpx{z0.re - z0.im, 0.f} : cpx{z0.re + z0.im, 0.f};
-    slot_a = P::slot(M / 2); slot_b = P::slot(0);
+ISI_HD void polar_bin(cpx x, bool first_frame, bool use_mel, float eps, BinState& st, cpx& out) {
+  const float m2 = fmaf(x.re, x.re, x.im * x.im);
+  const float mag = (m2 > 0.f) ? m2 * fast_rsqrt(m2) : 0.f;
+  if (x.re == 0.f && x.im == 0.f) x.re = 1.f;
+  float step;
+  if (first_frame) {
+    step = fast_atan2(x.im, x.re);
+    st.unwrapped = step;
   } else {
-    slot_a = P::slot(it); slot_b = P::slot(M - it);
-    cpx a = z[slot_a], b = z[slot_b];
-    cpx e = cpx{0.5f * (a.re + b.re), 0.5f * (a.im - b.im)};  // (A + conj B)/2
-    cpx d = cpx{0.5f * (a.re - b.re), 0.5f * (a.im + b.im)};  // (A - conj B)/2
-    cpx p = cmul(tw[it], mul_neg_i(d));                       // W_N^k * (-i) * d
-    xa = cadd(e, p);
-    cpx m = csub(e, p);
-    xb = cpx{m.re, -m.im};
+    // arg(X_t conj X_{t-1}) is the wrapped phase advance
+    step = fast_atan2(x.im * st.pre - x.re * st.pim, x.re * st.pre + x.im * st.pim);
+    st.unwrapped += step;
   }
-  cpx xs[2] = {xa, xb};
-  BinState* st[2] = {&sa, &sb};
-  cpx out[2];
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    float mag = sqrtf(xs[i].re * xs[i].re + xs[i].im * xs[i].im);
-    float ph = atan2f(xs[i].im, xs[i].re);
-    float step = first_frame ? ph : wrapped_step(ph - st[i]->prev_phase);
-    st[i]->prev_phase = ph;
-    st[i]->unwrapped = first_frame ? ph : st[i]->unwrapped + step;
-    if (use_mel) { float a = mag + eps; out[i] = cpx{a * a, st[i]->unwrapped}; }
-    else         { out[i] = cpx{logf(mag + eps), step * kInvPi}; }
-  }
-  z[slot_a] = out[0];
-  z[slot_b] = out[1];
+  st.pre = x.re; st.pim = x.im;
+  if (use_mel) { const float a = mag + eps; out = cpx{a * a, st.unwrapped}; }
+  else         { out = cpx{fast_log(mag + eps), step * kInvPi}; }
 }
 
-// slot that holds output row `row` (0..M) after phase C
+// ---- polar: work item `it` (0..M/2-1) of one frame.  Item 0 owns bin M/2 and the two
+//      purely real bins 0 and M; item it>0 owns bins it and M-it.  zB[k] <- (v0, v1):
+//      mel mode (|X|+eps)^2 and unwrapped phase, linear mode log(|X|+eps) and IF. ----
 template <typename P>
-ISI_HD int row_slot(int row, bool drop_dc) {
-  int k = drop_dc ? row + 1 : row;            // FFT bin of this row
-  return P::slot(k == P::M ? 0 : k);          // the Nyquist bin lives in DC's slot
+ISI_HD void polar_item(int it, cpx* zB, cpx w /* tw[it] */, bool first_frame, bool use_mel,
+                       float eps, BinState& sa, BinState& sb, BinState& sc) {
+  constexpr int M = P::M;
+  if (it == 0) {
+    const cpx z0 = zB[0], zh = zB[M / 2];
+    cpx o;
+    polar_bin(cpx{zh.re, -zh.im}, first_frame, use_mel, eps, sa, o);          // X[M/2]
+    zB[M / 2] = o;
+    polar_bin(cpx{z0.re + z0.im, 0.f}, first_frame, use_mel, eps, sb, o);     // X[0]
+    zB[0] = o;
+    polar_bin(cpx{z0.re - z0.im, 0.f}, first_frame, use_mel, eps, sc, o);     // X[M]
+    zB[M] = o;
+  } else {
+    const cpx a = zB[it], b = zB[M - it];
+    const cpx e = cpx{0.5f * (a.re + b.re), 0.5f * (a.im - b.im)};            // (A + conj B)/2
+    const cpx d = cpx{0.5f * (a.re - b.re), 0.5f * (a.im + b.im)};            // (A - conj B)/2
+    const cpx p = cmul(w, mul_neg_i(d));                                      // W_N^k (-i) d
+    const cpx m = csub(e, p);
+    cpx o;
+    polar_bin(cadd(e, p), first_frame, use_mel, eps, sa, o);
+    zB[it] = o;
+    polar_bin(cpx{m.re, -m.im}, first_frame, use_mel, eps, sb, o);
+    zB[M - it] = o;
+  }
 }
 
-// ---- phase D: one output row of one frame ----
-struct RowState { float prev; };
+// ---- emit: one output row of one frame.  `bin0` is the FFT bin of the row (linear
+//      mode) or of the first band element (mel mode); mel weights live in registers. ----
+constexpr int kMaxMelWidth = 8;
 
-template <typename P>
-ISI_HD void emit_row(int row, const cpx* z, bool first_frame, bool use_mel, bool drop_dc,
-                     float eps, int mel_start, int mel_count, const float* mel_w,
-                     RowState& st, float& out0, float& out1) {
-  if (!use_mel) {
-    cpx v = z[row_slot<P>(row, drop_dc)];
-    out0 = v.re; out1 = v.im;
-    return;
-  }
+ISI_HD void emit_linear(const cpx* zB, int bin0, float& out0, float& out1) {
+  const cpx v = zB[bin0];
+  out0 = v.re; out1 = v.im;
+}
+
+ISI_HD void emit_mel(const cpx* zB, int bin0, int count, const float* w, bool first_frame,
+                     float eps, float& prev, float& out0, float& out1) {
   float m2 = 0.f, mp = 0.f;
-  for (int i = 0; i < mel_count; ++i) {
-    cpx v = z[row_slot<P>(mel_start + i, drop_dc)];
-    m2 = fmaf(mel_w[i], v.re, m2);
-    mp = fmaf(mel_w[i], v.im, mp);
+#pragma unroll
+  for (int i = 0; i < kMaxMelWidth; ++i) {
+    if (i < count) {
+      const cpx v = zB[bin0 + i];
+      m2 = fmaf(w[i], v.re, m2);
+      mp = fmaf(w[i], v.im, mp);
+    }
   }
-  out0 = logf(m2 + eps);
-  float step = first_frame ? mp : wrapped_step(mp - st.prev);
-  st.prev = mp;
+  out0 = fast_log(m2 + eps);
+  const float step = first_frame ? mp : wrap_step(mp - prev);
+  prev = mp;
   out1 = step * kInvPi;
 }
 

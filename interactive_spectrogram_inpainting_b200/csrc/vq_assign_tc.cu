@@ -1,15 +1,379 @@
-// tcgen05 (3xTF32) nearest-code search -- placeholder until the kernel lands.
+// Nearest-code search on the 5th-generation tensor cores (tcgen05, kind::tf32) with a
+// 3xTF32 split for FP32-equivalent accuracy.  Replaces bottleneck.py:55-61.
+//
+//   score(n, k) = |e_k|^2 - 2 x_n . e_k      (the |x_n|^2 term cannot change the argmin)
+//   x = x_hi + x_lo,  B = -2E = b_hi + b_lo  (each part exactly representable in TF32)
+//   acc = x_hi b_hi + x_hi b_lo + x_lo b_hi  (the dropped x_lo b_lo term is ~2^-22 relative)
+//
+// Persistent CTAs, one per SM, each owning tiles of 256 rows (two M=128 accumulators).
+// Warp roles:
+//   warps 0-3  epilogue   tcgen05.ld the 128 x 64 accumulators, add |e|^2, running argmin
+//   warps 4-7  x loader   coalesced global reads of the row tile in the caller's layout,
+//                         hi/lo split, st.shared into the SWIZZLE_128B K-major UMMA layout
+//   warp  8    B producer streams pre-split, pre-swizzled 64-code operand tiles of the
+//                         codebook through a 2-stage ring with cp.async.bulk + mbarrier
+//   warp  9    MMA issuer one elected lane issues the tcgen05.mma chain; owns TMEM
+// The accumulators live in TMEM (2 stages x 2 row tiles x 64 columns), so the argmin of
+// tile j overlaps the MMAs of tile j+1.
 #include "common.cuh"
 
 namespace isi {
 
-bool assign_tc_supported(const isi_rows_layout&, int64_t, int, int) { return false; }
+namespace tc {
 
-int launch_prepare_tc(const float*, int, int, const Prepared&, cudaStream_t) { return ISI_OK; }
+constexpr int kRowsPerMma = 128;
+constexpr int kMmaPerTile = 2;                       // row tiles per CTA tile
+constexpr int kTileRows = kRowsPerMma * kMmaPerTile;  // 256
+constexpr int kTileCodes = 64;                       // codes per B stage (UMMA N)
+constexpr int kDim = 64;                             // feature dimension this kernel is built for
+constexpr int kSlabs = kDim / 32;                    // 128-byte K slabs per row
+constexpr int kABytesPart = kSlabs * kRowsPerMma * 128;        // one (m, hi|lo) operand: 32 KB
+constexpr int kABytes = kMmaPerTile * 2 * kABytesPart;          // 128 KB
+constexpr int kBBytesPart = kSlabs * kTileCodes * 128;         // one (hi|lo) code tile: 16 KB
+constexpr int kBStageBytes = 2 * kBBytesPart;                   // 32 KB
+constexpr int kBStages = 2;
+constexpr int kAccStages = 2;
+constexpr int kTmemCols = kAccStages * kMmaPerTile * kTileCodes;  // 256
+constexpr int kThreads = 320;
+constexpr int kMaxCodes = 4096;                      // |e|^2 table held in shared memory
 
-int launch_assign_tc(const float*, const isi_rows_layout&, int64_t, int, int, const Prepared&,
-                     int64_t*, float*, cudaStream_t) {
-  return ISI_ERR_UNSUPPORTED;
+// instruction descriptor: D=F32, A=B=TF32, both K-major, N=64, M=128
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kTileCodes >> 3) << 17) |
+                            ((uint32_t)(kRowsPerMma >> 4) << 24);
+
+struct Smem {
+  static constexpr int a = 0;                                   // 1024-aligned operand tiles
+  static constexpr int b = a + kABytes;
+  static constexpr int e2 = b + kBStages * kBStageBytes;
+  static constexpr int bars = e2 + kMaxCodes * 4;
+  static constexpr int total = bars + 128;
+};
+
+__device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "W_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra D_%=;\n\t"
+      "bra W_%=;\n\t"
+      "D_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ float to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
+// K-major SWIZZLE_128B shared-memory matrix descriptor (sm_100 format, version 1):
+// start address >> 4, leading byte offset unused, stride byte offset 1024 (8 rows x 128 B)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;      // descriptor version
+  d |= (uint64_t)2 << 61;      // SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc,
+                                          uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
+        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
+        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// byte offset of element (row r, feature d) inside one (rows x 64) K-major SW128 operand
+__host__ __device__ __forceinline__ uint32_t operand_offset(int rows, int r, int d) {
+  const int slab = d >> 5, chunk = (d & 31) >> 2;
+  return (uint32_t)(slab * rows * 128 + (r >> 3) * 1024 + (r & 7) * 128 + ((chunk ^ (r & 7)) << 4) +
+                    ((d & 3) << 2));
+}
+
+}  // namespace tc
+
+using namespace tc;
+
+// ---------------------------------------------------------------------------
+// codebook -> operand tiles:  b_hi / b_lo hold, per 64-code tile, the TF32 hi and lo
+// parts of -2E in exactly the bytes the kernel's shared-memory stage expects
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+vq_prepare_tc_kernel(const float* __restrict__ embed, int n_embed, Prepared p) {
+  const int n_tiles = (n_embed + kTileCodes - 1) / kTileCodes;
+  const int total = n_tiles * kTileCodes * kDim;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int code = e % (n_tiles * kTileCodes), d = e / (n_tiles * kTileCodes);
+    const float v = code < n_embed ? -2.f * embed[(int64_t)d * n_embed + code] : 0.f;
+    const float hi = to_tf32(v);
+    const float lo = to_tf32(v - hi);
+    const int tile = code / kTileCodes, n = code % kTileCodes;
+    const size_t off = (size_t)tile * kBStageBytes + operand_offset(kTileCodes, n, d);
+    *reinterpret_cast<float*>(reinterpret_cast<char*>(p.b_hi) + off) = hi;
+    *reinterpret_cast<float*>(reinterpret_cast<char*>(p.b_hi) + off + kBBytesPart) = lo;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// the search kernel
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1)
+vq_assign_tc_kernel(const float* __restrict__ x, isi_rows_layout lay, int64_t n_rows, int n_embed,
+                    const char* __restrict__ b_tiles, const float* __restrict__ e2_global,
+                    int64_t* __restrict__ out_index, float* __restrict__ out_score) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const uint32_t smem_base = s32(smem);
+  float* e2s = reinterpret_cast<float*>(smem + Smem::e2);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::bars);
+  // barrier slots
+  const uint32_t bar_b_full = s32(bars + 0);     // [2]
+  const uint32_t bar_b_empty = s32(bars + 2);    // [2]
+  const uint32_t bar_acc_full = s32(bars + 4);   // [2]
+  const uint32_t bar_acc_empty = s32(bars + 6);  // [2]
+  const uint32_t bar_a_full = s32(bars + 8);
+  const uint32_t bar_a_empty = s32(bars + 9);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_code_tiles = (n_embed + kTileCodes - 1) / kTileCodes;
+  const int64_t n_row_tiles = (n_rows + kTileRows - 1) / kTileRows;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_b_full + 8 * i, 1);
+      mbar_init(bar_b_empty + 8 * i, 1);
+      mbar_init(bar_acc_full + 8 * i, 1);
+      mbar_init(bar_acc_empty + 8 * i, 128);
+    }
+    mbar_init(bar_a_full, 128);
+    mbar_init(bar_a_empty, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 9) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)),
+                 "n"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  for (int k = threadIdx.x; k < n_code_tiles * kTileCodes; k += kThreads) e2s[k] = e2_global[k];
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= 4 && warp < 8) {
+    // ===================== x loader / splitter =====================
+    const int t = threadIdx.x - 128;                      // 0..127
+    const bool rows_contiguous = (lay.row_stride == 1 && lay.col_stride != 1);
+    uint32_t it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_row_tiles; tile += gridDim.x, ++it) {
+      mbar_wait(bar_a_empty, (it & 1) ^ 1);               // MMAs of the previous tile are done
+      const int64_t row0 = tile * kTileRows;
+      // 256 rows x 16 chunks (float4 of 4 consecutive features)
+      for (int e = t; e < kTileRows * (kDim / 4); e += 128) {
+        int r, c;
+        if (rows_contiguous) { r = e % kTileRows; c = e / kTileRows; }
+        else                 { c = e % (kDim / 4); r = e / (kDim / 4); }
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int64_t row = row0 + r;
+        if (row < n_rows) {
+          const float* src = x + row_offset(lay, row) + (int64_t)(4 * c) * lay.col_stride;
+          if (lay.col_stride == 1 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+            v = *reinterpret_cast<const float4*>(src);
+          } else {
+            v.x = src[0]; v.y = src[lay.col_stride]; v.z = src[2 * lay.col_stride];
+            v.w = src[3 * lay.col_stride];
+          }
+        }
+        float4 hi = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+        float4 lo = make_float4(to_tf32(v.x - hi.x), to_tf32(v.y - hi.y), to_tf32(v.z - hi.z),
+                                to_tf32(v.w - hi.w));
+        const int m = r >> 7, rr = r & 127;
+        const uint32_t off = Smem::a + (uint32_t)(m * 2) * kABytesPart + operand_offset(kRowsPerMma, rr, 4 * c);
+        *reinterpret_cast<float4*>(smem + off) = hi;
+        *reinterpret_cast<float4*>(smem + off + kABytesPart) = lo;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy
+      mbar_arrive(bar_a_full);
+    }
+  } else if (warp == 8) {
+    // ===================== B producer =====================
+    if (lane == 0) {
+      uint32_t step = 0;
+      for (int64_t tile = blockIdx.x; tile < n_row_tiles; tile += gridDim.x) {
+        for (int j = 0; j < n_code_tiles; ++j, ++step) {
+          const uint32_t s = step & 1, ph = (step >> 1) & 1;
+          mbar_wait(bar_b_empty + 8 * s, ph ^ 1);
+          mbar_expect_tx(bar_b_full + 8 * s, kBStageBytes);
+          bulk_g2s(smem_base + Smem::b + s * kBStageBytes, b_tiles + (size_t)j * kBStageBytes,
+                   kBStageBytes, bar_b_full + 8 * s);
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t step = 0, it = 0;
+      for (int64_t tile = blockIdx.x; tile < n_row_tiles; tile += gridDim.x, ++it) {
+        mbar_wait(bar_a_full, it & 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        for (int j = 0; j < n_code_tiles; ++j, ++step) {
+          const uint32_t s = step & 1, ph = (step >> 1) & 1;
+          mbar_wait(bar_b_full + 8 * s, ph);
+          mbar_wait(bar_acc_empty + 8 * s, ph ^ 1);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t b_base = smem_base + Smem::b + s * kBStageBytes;
+#pragma unroll
+          for (int m = 0; m < kMmaPerTile; ++m) {
+            const uint32_t d_tmem = tmem_base + (uint32_t)((s * kMmaPerTile + m) * kTileCodes);
+            const uint32_t a_base = smem_base + Smem::a + (uint32_t)(m * 2) * kABytesPart;
+            uint32_t acc = 0;
+#pragma unroll
+            for (int term = 0; term < 3; ++term) {
+              // (x_lo, b_hi), (x_hi, b_lo), (x_hi, b_hi): small terms first
+              const uint32_t a_part = a_base + (term == 0 ? kABytesPart : 0);
+              const uint32_t b_part = b_base + (term == 1 ? kBBytesPart : 0);
+#pragma unroll
+              for (int slab = 0; slab < kSlabs; ++slab) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                  const uint64_t ad = umma_desc(a_part + slab * (kRowsPerMma * 128) + kk * 32);
+                  const uint64_t bd = umma_desc(b_part + slab * (kTileCodes * 128) + kk * 32);
+                  umma_tf32(d_tmem, ad, bd, kIdesc, acc);
+                  acc = 1;
+                }
+              }
+            }
+          }
+          umma_commit(bar_b_empty + 8 * s);       // the B stage may be refilled
+          umma_commit(bar_acc_full + 8 * s);      // the accumulators may be read
+        }
+        umma_commit(bar_a_empty);                  // the row tile may be overwritten
+      }
+    }
+  } else {
+    // ===================== epilogue: argmin =====================
+    uint32_t step = 0;
+    const uint32_t lane_field = (uint32_t)(warp * 32) << 16;
+    for (int64_t tile = blockIdx.x; tile < n_row_tiles; tile += gridDim.x) {
+      float best_s[kMmaPerTile];
+      int best_i[kMmaPerTile];
+#pragma unroll
+      for (int m = 0; m < kMmaPerTile; ++m) { best_s[m] = INFINITY; best_i[m] = 0; }
+      for (int j = 0; j < n_code_tiles; ++j, ++step) {
+        const uint32_t s = step & 1, ph = (step >> 1) & 1;
+        mbar_wait(bar_acc_full + 8 * s, ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const float* e2t = e2s + j * kTileCodes;
+#pragma unroll
+        for (int m = 0; m < kMmaPerTile; ++m) {
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {
+            float v[32];
+            tmem_ld32(tmem_base + lane_field + (uint32_t)((s * kMmaPerTile + m) * kTileCodes + half * 32), v);
+#pragma unroll
+            for (int c = 0; c < 32; c += 4) {
+              const float4 ee = *reinterpret_cast<const float4*>(e2t + half * 32 + c);
+              const float sc[4] = {v[c] + ee.x, v[c + 1] + ee.y, v[c + 2] + ee.z, v[c + 3] + ee.w};
+#pragma unroll
+              for (int q = 0; q < 4; ++q) {
+                // codes are visited in rising order: strict '<' keeps the lowest index on ties
+                if (sc[q] < best_s[m]) { best_s[m] = sc[q]; best_i[m] = j * kTileCodes + half * 32 + c + q; }
+              }
+            }
+          }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(bar_acc_empty + 8 * s);
+      }
+      const int64_t row0 = tile * kTileRows + warp * 32 + lane;
+#pragma unroll
+      for (int m = 0; m < kMmaPerTile; ++m) {
+        const int64_t row = row0 + m * kRowsPerMma;
+        if (row < n_rows) {
+          out_index[row] = best_i[m];
+          if (out_score) out_score[row] = best_s[m];
+        }
+      }
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 9) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+bool assign_tc_supported(const isi_rows_layout& lay, int64_t n_rows, int dim, int n_embed) {
+  (void)lay;
+  // small problems stay on the SIMT kernel: a 256-row tile per SM needs ~38k rows to fill
+  // the machine once, and the launch is latency-bound below a few thousand rows
+  return dim == kDim && n_embed <= kMaxCodes && n_rows >= 4096;
+}
+
+int launch_prepare_tc(const float* embed, int dim, int n_embed, const Prepared& p, cudaStream_t stream) {
+  if (dim != kDim) return ISI_OK;   // nothing to prepare: the SIMT kernel serves this shape
+  const int n_tiles = (n_embed + kTileCodes - 1) / kTileCodes;
+  const int total = n_tiles * kTileCodes * kDim;
+  int grid = (total + 255) / 256;
+  if (grid > 4 * kNumSms) grid = 4 * kNumSms;
+  vq_prepare_tc_kernel<<<grid, 256, 0, stream>>>(embed, n_embed, p);
+  ISI_LAUNCH_CHECK();
+  return ISI_OK;
+}
+
+int launch_assign_tc(const float* x, const isi_rows_layout& lay, int64_t n_rows, int dim, int n_embed,
+                     const Prepared& p, int64_t* out_index, float* out_score, cudaStream_t stream) {
+  if (dim != kDim || n_embed > kMaxCodes) return ISI_ERR_UNSUPPORTED;
+  cudaError_t e = cudaFuncSetAttribute(vq_assign_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Smem::total);
+  if (e != cudaSuccess) return (int)e;
+  const int64_t n_row_tiles = (n_rows + kTileRows - 1) / kTileRows;
+  const int grid = (int)(n_row_tiles < kNumSms ? n_row_tiles : kNumSms);
+  vq_assign_tc_kernel<<<grid, kThreads, Smem::total, stream>>>(
+      x, lay, n_rows, n_embed, reinterpret_cast<const char*>(p.b_hi), p.e2, out_index, out_score);
+  ISI_LAUNCH_CHECK();
+  return ISI_OK;
 }
 
 }  // namespace isi

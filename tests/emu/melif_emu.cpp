@@ -15,42 +15,52 @@ static void emulate(const float* audio, int64_t n_notes, int64_t n_samples, int 
                     const float* window, const float* twiddle, const int32_t* mel_start,
                     const int32_t* mel_count, const float* mel_weight, float* out) {
   using P = Plan<NFFT>;
-  constexpr int M = P::M, IPT = (M / 2) / NT, RPT = M / NT;
+  constexpr int M = P::M, RPT = M / NT, kGroups = NT / 64;
+  static_assert(NT == M / 2, "one polar item per thread");
   const cpx* tw = reinterpret_cast<const cpx*>(twiddle);
-  std::vector<cpx> zbuf((size_t)FB * M);
+  const int span = (FB - 1) * hop + NFFT;
+  const int dc = drop_dc ? 1 : 0;
+  std::vector<float> stage(span);
+  std::vector<cpx> zA((size_t)FB * P::kPitchA), zB((size_t)FB * P::kPitchB);
   for (int64_t n = 0; n < n_notes; ++n) {
     const float* note = audio + n * n_samples;
     float* out0 = out + n * 2 * M * n_frames;
     float* out1 = out0 + (int64_t)M * n_frames;
-    std::vector<BinState> sa((size_t)NT * IPT, BinState{0.f, 0.f}), sb = sa;
-    std::vector<RowState> rs((size_t)NT * RPT, RowState{0.f});
+    std::vector<BinState> sa(NT, BinState{1.f, 0.f, 0.f}), sb = sa, sc = sa;
+    std::vector<float> prev((size_t)NT * RPT, 0.f);
     for (int f0 = 0; f0 < n_frames; f0 += FB) {
       const int nf = (FB < n_frames - f0) ? FB : n_frames - f0;
       for (int tid = 0; tid < NT; ++tid)
+        stage_fill(tid, NT, stage.data(), span, note, n_samples, (int64_t)f0 * hop - pad_left);
+      for (int tid = 0; tid < NT; ++tid)
+        for (int fb = tid / 64; fb < nf; fb += kGroups)
+          fft_pass1<P>(tid & 63, stage.data() + fb * hop, window, tw, zA.data() + fb * P::kPitchA);
+      for (int tid = 0; tid < NT; ++tid)
+        for (int fb = tid / 64; fb < nf; fb += kGroups)
+          fft_pass2<P>(tid & 63, tw, zA.data() + fb * P::kPitchA);
+      for (int tid = 0; tid < NT; ++tid)
+        for (int fb = tid / 64; fb < nf; fb += kGroups)
+          fft_pass3<P>(tid & 63, zA.data() + fb * P::kPitchA, zB.data() + fb * P::kPitchB);
+      for (int tid = 0; tid < NT; ++tid)
         for (int fb = 0; fb < nf; ++fb)
-          pack_frame<P>(tid, NT, zbuf.data() + fb * M, note, n_samples,
-                        (int64_t)(f0 + fb) * hop - pad_left, window);
-      for (int tid = 0; tid < NT; ++tid)
-        for (int fb = tid / 64; fb < nf; fb += NT / 64) fft_pass1<P>(tid & 63, zbuf.data() + fb * M, tw);
-      for (int tid = 0; tid < NT; ++tid)
-        for (int fb = tid / 64; fb < nf; fb += NT / 64) fft_pass2<P>(tid & 63, zbuf.data() + fb * M, tw);
-      for (int tid = 0; tid < NT; ++tid)
-        for (int fb = tid / 64; fb < nf; fb += NT / 64) fft_pass3<P>(tid & 63, zbuf.data() + fb * M);
-      for (int tid = 0; tid < NT; ++tid)
-        for (int fb = 0; fb < nf; ++fb)
-          for (int i = 0; i < IPT; ++i)
-            polar_item<P>(tid + i * NT, zbuf.data() + fb * M, tw, f0 + fb == 0, use_mel != 0,
-                          drop_dc != 0, eps, sa[tid * IPT + i], sb[tid * IPT + i]);
+          polar_item<P>(tid, zB.data() + fb * P::kPitchB, tw[tid], f0 + fb == 0, use_mel != 0, eps,
+                        sa[tid], sb[tid], sc[tid]);
       for (int tid = 0; tid < NT; ++tid)
         for (int r = 0; r < RPT; ++r) {
           const int row = tid + r * NT;
-          int ms = 0, mc = 0;
-          const float* mw = nullptr;
-          if (use_mel) { ms = mel_start[row]; mc = mel_count[row]; mw = mel_weight + (int64_t)row * mel_width; }
+          float w[kMaxMelWidth] = {0};
+          int bin0 = row + dc, cnt = 0;
+          if (use_mel) {
+            bin0 = mel_start[row] + dc; cnt = mel_count[row];
+            for (int i = 0; i < mel_width && i < kMaxMelWidth; ++i) w[i] = mel_weight[(int64_t)row * mel_width + i];
+          }
           for (int fb = 0; fb < nf; ++fb) {
             float v0, v1;
-            emit_row<P>(row, zbuf.data() + fb * M, f0 + fb == 0, use_mel != 0, drop_dc != 0, eps, ms,
-                        mc, mw, rs[tid * RPT + r], v0, v1);
+            if (use_mel)
+              emit_mel(zB.data() + fb * P::kPitchB, bin0, cnt, w, f0 + fb == 0, eps,
+                       prev[tid * RPT + r], v0, v1);
+            else
+              emit_linear(zB.data() + fb * P::kPitchB, bin0, v0, v1);
             out0[(int64_t)row * n_frames + f0 + fb] = v0;
             out1[(int64_t)row * n_frames + f0 + fb] = v1;
           }
