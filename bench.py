@@ -337,7 +337,8 @@ def b200_arm(args):
                                "encode (bottom 16 / top 2, K=512, D=64) -> top+bottom codes",
                    "notes_per_step_per_gpu": B, "sharding": "notes sharded per rank, no collective",
                    "conv_encoder": "torch/cuDNN fp32 (TF32 convs as torch defaults), random init",
-                   "l2": "inputs exceed L2: 65.5 MB audio + 268 MB spectrogram per step at B=256",
+                   "l2": f"inputs exceed L2 (126 MB): {B * 0.256:.0f} MB audio + "
+                         f"{B * 1.0486:.0f} MB spectrogram per step",
                    "assign_algo": args.assign_algo},
         "e2e": {"value": e2e_value, "unit": "notes/s",
                 "h2d_bytes_per_step": host_audio.numel() * 4,
@@ -346,7 +347,7 @@ def b200_arm(args):
         "gpu_launches": launches,
         "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"],
                    "reasons": clk["reasons"], "samples": clk["samples"]},
-        "roofline": {"kernel": "melif_kernel<2048,8,512>", "bound": "hbm", "achieved": melif_gbs,
+        "roofline": {"kernel": "melif_kernel<2048,4,256>", "bound": "hbm", "achieved": melif_gbs,
                      "peak": hbm_peak, "unit": "GB/s", "frac": melif_gbs / hbm_peak,
                      "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
                      "ms_per_launch": melif_ms, "algorithmic_bytes_per_launch": MELIF_BYTES_PER_NOTE * B},
@@ -385,7 +386,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=256, help="notes per step per GPU")
+    ap.add_argument("--batch", type=int, default=296,
+                    help="notes per step per GPU (default 2 x 148 SMs: whole waves of note CTAs)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--assign-algo", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -4,14 +4,17 @@
 // GANsynth_pytorch; reference call sites utils/misc.py:10-29, extract_code.py:199-206,
 // train_vqvae.py:604-611).
 //
-// One CTA owns one note and walks its frames in batches of FB.  Per batch the audio span
-// (FB-1)*hop + n_fft samples is brought into shared memory by ONE bulk async copy
-// (cp.async.bulk, the 1-D TMA path, completion on an mbarrier) issued a whole batch ahead,
-// so HBM latency is hidden behind the previous batch's FFT.  Twiddles and the window sit in
-// shared memory, the mel band of each output row in registers; the complex spectrum,
-// magnitudes and phases never leave shared memory / registers.  The only HBM traffic is
-// the audio once (plus the frame overlap from L2) and the final [2, F, T'] tensor, written
-// FB consecutive time steps (one 32-byte sector at FB = 8) per row at a time.
+// One CTA owns a run of frames of one note (a whole note when the batch alone fills the
+// GPU, else a segment -- the only cross-frame state is the previous frame's spectrum, which
+// a segment recomputes with one look-back transform) and walks it in batches of FB frames.
+// Per batch the audio span (FB-1)*hop + n_fft is brought into shared memory by ONE bulk
+// async copy (cp.async.bulk, the 1-D TMA path, completion on an mbarrier) issued a whole
+// batch ahead, so HBM latency hides behind the previous batch's transform.  Twiddles and
+// the window sit in shared memory, the mel band of each output row in registers; the
+// complex spectrum, magnitudes and phase steps never leave shared memory / registers.
+// HBM traffic is the audio once (frame overlap is served from shared memory) and the final
+// [2, F, T'] tensor, FB consecutive time steps per row at a time.  Two CTAs share an SM so
+// one CTA's barrier waits are filled by the other's work.
 #include "common.cuh"
 #include "melif_core.cuh"
 
@@ -53,8 +56,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 
 struct MelifSmem {
-  // byte offsets into dynamic shared memory
-  int tw, win, stage, za, zb, bar, total;
+  int tw, win, stage, za, zb, bar, total;   // byte offsets into dynamic shared memory
 };
 
 template <int NFFT, int FB>
@@ -73,14 +75,15 @@ __host__ __device__ inline MelifSmem melif_smem_layout(int hop) {
 }
 
 template <int NFFT, int FB, int NT>
-__global__ void __launch_bounds__(NT, 1)
+__global__ void __launch_bounds__(NT, 2)
 melif_kernel(const float* __restrict__ audio, int64_t n_samples, isi_melif_params p,
-             float* __restrict__ out, int bulk_ok) {
+             float* __restrict__ out, int bulk_ok, int seg_frames, int n_segs) {
   using P = Plan<NFFT>;
   constexpr int M = P::M;
+  constexpr int IPT = (M / 2) / NT;           // polar work items per thread
   constexpr int RPT = M / NT;                 // output rows per thread
   constexpr int kGroups = NT / 64;            // frames transformed concurrently
-  static_assert(NT == M / 2, "one polar work item per thread");
+  static_assert(IPT >= 1 && (M / 2) % NT == 0 && NT % 64 == 0, "bad thread count");
   extern __shared__ __align__(128) unsigned char smem[];
   const MelifSmem L = melif_smem_layout<NFFT, FB>(p.hop);
   cpx* tw = reinterpret_cast<cpx*>(smem + L.tw);
@@ -91,13 +94,15 @@ melif_kernel(const float* __restrict__ audio, int64_t n_samples, isi_melif_param
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar);
 
   const int tid = threadIdx.x;
-  const float* note = audio + (int64_t)blockIdx.x * n_samples;
-  float* out0 = out + (int64_t)blockIdx.x * 2 * M * p.n_frames;
+  const int note_idx = blockIdx.x / n_segs, seg = blockIdx.x - note_idx * n_segs;
+  const int fs = seg * seg_frames;                          // first frame of this CTA
+  const int fe = min(p.n_frames, fs + seg_frames);          // one past its last frame
+  const float* note = audio + (int64_t)note_idx * n_samples;
+  float* out0 = out + (int64_t)note_idx * 2 * M * p.n_frames;
   float* out1 = out0 + (int64_t)M * p.n_frames;
   const bool use_mel = p.use_mel != 0;
   const int dc = p.drop_dc ? 1 : 0;
   const float eps = p.safelog_eps;
-  const int span = (FB - 1) * p.hop + NFFT;
 
   // ---- one-time setup: tables to shared memory, per-thread constants to registers ----
   for (int i = tid; i < NFFT; i += NT) {
@@ -108,14 +113,14 @@ melif_kernel(const float* __restrict__ audio, int64_t n_samples, isi_melif_param
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  const cpx w_item = reinterpret_cast<const cpx*>(p.twiddle)[tid];
-  int row_bin[RPT], row_cnt[RPT];
+  cpx w_item[IPT];
+#pragma unroll
+  for (int i = 0; i < IPT; ++i) w_item[i] = reinterpret_cast<const cpx*>(p.twiddle)[tid + i * NT];
+  int row_bin[RPT], row_cnt[RPT], row_cnt_warp[RPT];
   float row_w[RPT][kMaxMelWidth];
-  float row_prev[RPT];
 #pragma unroll
   for (int r = 0; r < RPT; ++r) {
     const int row = tid + r * NT;
-    row_prev[r] = 0.f;
     row_cnt[r] = 0;
     row_bin[r] = row + dc;
 #pragma unroll
@@ -127,16 +132,24 @@ melif_kernel(const float* __restrict__ audio, int64_t n_samples, isi_melif_param
       for (int i = 0; i < kMaxMelWidth; ++i)
         if (i < p.mel_width) row_w[r][i] = p.mel_weight[(int64_t)row * p.mel_width + i];
     }
+    row_cnt_warp[r] = __reduce_max_sync(0xffffffffu, row_cnt[r]);
   }
-  BinState sa{1.f, 0.f, 0.f}, sb{1.f, 0.f, 0.f}, sc{1.f, 0.f, 0.f};
+  BinState sa[IPT], sb[IPT], sc{1.f, 0.f};
+#pragma unroll
+  for (int i = 0; i < IPT; ++i) { sa[i] = BinState{1.f, 0.f}; sb[i] = BinState{1.f, 0.f}; }
   __syncthreads();
 
-  // stage the audio span of batch `b`: zero-fill what lies outside the note, one bulk copy
-  // for the rest (thread 0), completion signalled on `bar`
-  auto prefetch = [&](int b) {
-    const int64_t s0 = (int64_t)b * FB * p.hop - p.pad_left;
-    const int64_t lo = s0 < 0 ? -s0 : 0;                                   // first valid index
-    int64_t hi = n_samples - s0;                                           // one past last valid
+  // Stage the audio span of frames [frame, frame + nfr): zero-fill what lies outside the
+  // note, one bulk copy for the rest (thread 0), completion signalled on `bar`.
+  auto stage_span = [&](int frame, int nfr) {
+    const int span = (nfr - 1) * p.hop + NFFT;
+    const int64_t s0 = (int64_t)frame * p.hop - p.pad_left;
+    if (!bulk_ok) {
+      stage_fill(tid, NT, stage, span, note, n_samples, s0);
+      return;
+    }
+    const int64_t lo = s0 < 0 ? -s0 : 0;                      // first valid index
+    int64_t hi = n_samples - s0;                              // one past the last valid index
     hi = hi < 0 ? 0 : (hi > span ? span : hi);
     const int64_t vlo = lo < hi ? lo : hi;
     for (int i = tid; i < vlo; i += NT) stage[i] = 0.f;
@@ -152,35 +165,53 @@ melif_kernel(const float* __restrict__ audio, int64_t n_samples, isi_melif_param
       }
     }
   };
-
-  const int n_batches = (p.n_frames + FB - 1) / FB;
-  if (bulk_ok) prefetch(0);
-
-  for (int b = 0; b < n_batches; ++b) {
-    const int f0 = b * FB;
-    const int nf = min(FB, p.n_frames - f0);
-    if (bulk_ok) {
-      mbar_wait(bar, b & 1);
-      if (b == 0) __syncthreads();   // batch 0's zero-filled pad was written by other threads;
-                                     // later batches' pads are ordered by the syncs below
-    } else {
-      __syncthreads();
-      stage_fill(tid, NT, stage, span, note, n_samples, (int64_t)f0 * p.hop - p.pad_left);
-      __syncthreads();
-    }
-    // pass 1: window + pack + radix R1 (64 threads per frame)
+  uint32_t stage_phase = 0;
+  auto stage_wait = [&]() {
+    if (bulk_ok) { mbar_wait(bar, stage_phase & 1); ++stage_phase; }
+    __syncthreads();       // zero-filled pads / synchronous fills were written by other threads
+  };
+  auto transform = [&](int nf, int next_frame, int next_nfr) {
     for (int fb = tid / 64; fb < nf; fb += kGroups)
       fft_pass1<P>(tid & 63, stage + fb * p.hop, win, tw, zA + fb * P::kPitchA);
     __syncthreads();
-    if (bulk_ok && b + 1 < n_batches) prefetch(b + 1);
+    if (next_nfr > 0 && bulk_ok) stage_span(next_frame, next_nfr);   // the stage is free again
     for (int fb = tid / 64; fb < nf; fb += kGroups) fft_pass2<P>(tid & 63, tw, zA + fb * P::kPitchA);
     __syncthreads();
     for (int fb = tid / 64; fb < nf; fb += kGroups)
       fft_pass3<P>(tid & 63, zA + fb * P::kPitchA, zB + fb * P::kPitchB);
     __syncthreads();
-    // polar: frames in order, unwrap state in registers
-    for (int fb = 0; fb < nf; ++fb)
-      polar_item<P>(tid, zB + fb * P::kPitchB, w_item, f0 + fb == 0, use_mel, eps, sa, sb, sc);
+  };
+
+  const int n_batches = (fe - fs + FB - 1) / FB;
+  // ---- look-back: the spectrum of frame fs-1 seeds the phase-step state ----
+  if (fs > 0) {
+    stage_span(fs - 1, 1);
+    stage_wait();
+    transform(1, fs, min(FB, fe - fs));
+#pragma unroll
+    for (int i = 0; i < IPT; ++i)
+      polar_item<P>(tid + i * NT, zB, w_item[i], true, use_mel, eps, sa[i], sb[i], sc);
+    if (!bulk_ok) { __syncthreads(); stage_span(fs, min(FB, fe - fs)); }
+  } else {
+    stage_span(fs, min(FB, fe - fs));
+  }
+
+  for (int b = 0; b < n_batches; ++b) {
+    const int f0 = fs + b * FB;
+    const int nf = min(FB, fe - f0);
+    stage_wait();
+    const int next_nfr = (b + 1 < n_batches) ? min(FB, fe - (f0 + FB)) : 0;
+    transform(nf, f0 + FB, next_nfr);
+    // polar: frames in order, previous spectrum value in registers
+#pragma unroll
+    for (int fb = 0; fb < FB; ++fb) {
+      if (fb < nf) {
+#pragma unroll
+        for (int i = 0; i < IPT; ++i)
+          polar_item<P>(tid + i * NT, zB + fb * P::kPitchB, w_item[i], f0 + fb == 0, use_mel, eps,
+                        sa[i], sb[i], sc);
+      }
+    }
     __syncthreads();
     // emit: FB consecutive time steps per row
 #pragma unroll
@@ -192,8 +223,8 @@ melif_kernel(const float* __restrict__ audio, int64_t n_samples, isi_melif_param
         v0[fb] = 0.f; v1[fb] = 0.f;
         if (fb < nf) {
           if (use_mel)
-            emit_mel(zB + fb * P::kPitchB, row_bin[r], row_cnt[r], row_w[r], f0 + fb == 0, eps,
-                     row_prev[r], v0[fb], v1[fb]);
+            emit_mel(zB + fb * P::kPitchB, row_bin[r], row_cnt[r], row_cnt_warp[r], row_w[r],
+                     f0 + fb == 0, eps, v0[fb], v1[fb]);
           else
             emit_linear(zB + fb * P::kPitchB, row_bin[r], v0[fb], v1[fb]);
         }
@@ -214,6 +245,25 @@ melif_kernel(const float* __restrict__ audio, int64_t n_samples, isi_melif_param
           if (fb < nf) { d0[fb] = v0[fb]; d1[fb] = v1[fb]; }
       }
     }
+    if (!bulk_ok && b + 1 < n_batches) { __syncthreads(); stage_span(f0 + FB, next_nfr); }
+  }
+}
+
+// Frames per CTA: whole notes when the batch fills the GPU on its own, else the split that
+// maximises (wave efficiency) x (useful / useful + look-back work).
+static void choose_segments(int64_t n_notes, int n_frames, int fb, int* seg_frames, int* n_segs) {
+  const int frames_padded = (n_frames + fb - 1) / fb * fb;
+  const int max_segs = frames_padded / (4 * fb) > 1 ? frames_padded / (4 * fb) : 1;
+  const double slots = 2.0 * kNumSms;
+  double best = -1.0;
+  *seg_frames = frames_padded; *n_segs = 1;
+  for (int s = 1; s <= max_segs; ++s) {
+    const int sf = ((frames_padded + s - 1) / s + fb - 1) / fb * fb;
+    const int ns = (n_frames + sf - 1) / sf;
+    const double waves = (double)n_notes * ns / slots;
+    const double wave_eff = waves / (double)(int64_t)(waves + 0.999999);
+    const double eff = wave_eff * (ns == 1 ? 1.0 : (double)sf / (sf + 2.0));
+    if (eff > best + 1e-9) { best = eff; *seg_frames = sf; *n_segs = ns; }
   }
 }
 
@@ -228,20 +278,22 @@ static int launch_melif_t(const float* audio, int64_t n_notes, int64_t n_samples
   // the bulk copy needs 16-byte aligned global addresses and sizes
   const int bulk_ok = (n_samples % 4 == 0) && (p.hop % 4 == 0) && (p.pad_left % 4 == 0) &&
                       ((uintptr_t)audio % 16 == 0);
-  melif_kernel<NFFT, FB, NT><<<(unsigned)n_notes, NT, L.total, stream>>>(audio, n_samples, p, out,
-                                                                        bulk_ok);
+  int seg_frames, n_segs;
+  choose_segments(n_notes, p.n_frames, FB, &seg_frames, &n_segs);
+  if (n_notes * n_segs > 0x7fffffff) return ISI_ERR_SHAPE;
+  melif_kernel<NFFT, FB, NT><<<(unsigned)(n_notes * n_segs), NT, L.total, stream>>>(
+      audio, n_samples, p, out, bulk_ok, seg_frames, n_segs);
   ISI_LAUNCH_CHECK();
   return ISI_OK;
 }
 
 int launch_melif(const float* audio, int64_t n_notes, int64_t n_samples,
                  const isi_melif_params& p, float* out, cudaStream_t stream) {
-  if (n_notes > 0x7fffffff) return ISI_ERR_SHAPE;
   if (p.use_mel && p.mel_width > kMaxMelWidth) return ISI_ERR_UNSUPPORTED;
   switch (p.n_fft) {
-    case 2048: return launch_melif_t<2048, 8, 512>(audio, n_notes, n_samples, p, out, stream);
-    case 1024: return launch_melif_t<1024, 8, 256>(audio, n_notes, n_samples, p, out, stream);
-    case 512:  return launch_melif_t<512, 8, 128>(audio, n_notes, n_samples, p, out, stream);
+    case 2048: return launch_melif_t<2048, 4, 256>(audio, n_notes, n_samples, p, out, stream);
+    case 1024: return launch_melif_t<1024, 4, 128>(audio, n_notes, n_samples, p, out, stream);
+    case 512:  return launch_melif_t<512, 4, 64>(audio, n_notes, n_samples, p, out, stream);
     default:   return ISI_ERR_UNSUPPORTED;
   }
 }

@@ -10,10 +10,10 @@
 //           audio, radix R1 = M/64 over stride 64, twiddle, into zA (64-blocks padded by 4)
 //   pass 2  radix 16 over stride 4 inside each 64-block of zA, twiddle, in place
 //   pass 3  radix 4 on consecutive quadruples of zA, written in natural bin order to zB
-//   polar   untangle X[k], X[M-k] from Z[k], Z[M-k]; |X|, phase step = arg(X_t conj X_t-1);
-//           time-unwrapped phase carried in registers; (v0, v1) overwrite zB in place
-//   emit    banded mel projections of (|X|+eps)^2 and of the unwrapped phase (or a copy
-//           in linear mode), log and mel-IF, FB consecutive time steps per row
+//   polar   untangle X[k], X[M-k] from Z[k], Z[M-k]; |X|, phase step = arg(X_t conj X_t-1)
+//           (previous spectrum value carried in registers); (v0, v1) overwrite zB in place
+//   emit    banded mel projections of (|X|+eps)^2 and of the phase steps (or a copy in
+//           linear mode), log and wrapped mel-IF, FB consecutive time steps per row
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -41,16 +41,20 @@ constexpr float kInvTwoPi = 0.15915494309189533577f;
 constexpr float kInvPi = 0.31830988618379067154f;
 
 // ---- fast scalar math (device: MUFU-based; host emulation: libm) ----
-ISI_HD float fast_rcp(float x) {
+ISI_HD float fast_rcp(float x) {           // one MUFU.RCP, ~1 ulp
 #ifdef __CUDA_ARCH__
-  return __frcp_rn(x);
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 #else
   return 1.0f / x;
 #endif
 }
-ISI_HD float fast_rsqrt(float x) {
+ISI_HD float fast_rsqrt(float x) {         // one MUFU.RSQ, ~2 ulp
 #ifdef __CUDA_ARCH__
-  return rsqrtf(x);
+  float r;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 #else
   return 1.0f / sqrtf(x);
 #endif
@@ -68,7 +72,7 @@ ISI_HD float fast_log(float x) {
 ISI_HD float fast_atan2(float y, float x) {
   const float ax = fabsf(x), ay = fabsf(y);
   const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
-  const float a = (mx == 0.f) ? 0.f : mn * fast_rcp(mx);
+  const float a = (mx < 1.17549435e-38f) ? 0.f : mn * fast_rcp(mx);   // zero / denormal -> 0
   const float s = a * a;
   float p = -0.0040545654483139515f;
   p = fmaf(p, s, 0.021862952038645744f);
@@ -214,31 +218,28 @@ ISI_HD float wrap_step(float dd) {
   return fmaf(-kTwoPi, rintf(dd * kInvTwoPi), dd);
 }
 
-// running state of one spectrogram bin across frames: previous spectrum value (exact
-// zeros replaced by 1+0i, whose phase is also 0) and the time-unwrapped phase
-struct BinState { float pre, pim, unwrapped; };
+// State of one spectrogram bin across frames: the previous spectrum value (exact zeros
+// replaced by 1+0i, whose phase is also 0).  The wrapped phase advance of frame t is
+// arg(X_t conj X_{t-1}); nothing cumulative is carried, because the mel IF only needs
+// differences of the projected unwrapped phase, and the projection is linear:
+//   mel_phase_t - mel_phase_{t-1} = sum_k w_k (u_t[k] - u_{t-1}[k]) = sum_k w_k step_t[k].
+struct BinState { float pre, pim; };
 
 ISI_HD void polar_bin(cpx x, bool first_frame, bool use_mel, float eps, BinState& st, cpx& out) {
   const float m2 = fmaf(x.re, x.re, x.im * x.im);
-  const float mag = (m2 > 0.f) ? m2 * fast_rsqrt(m2) : 0.f;
+  const float mag = (m2 > 1.17549435e-38f) ? m2 * fast_rsqrt(m2) : 0.f;
   if (x.re == 0.f && x.im == 0.f) x.re = 1.f;
-  float step;
-  if (first_frame) {
-    step = fast_atan2(x.im, x.re);
-    st.unwrapped = step;
-  } else {
-    // arg(X_t conj X_{t-1}) is the wrapped phase advance
-    step = fast_atan2(x.im * st.pre - x.re * st.pim, x.re * st.pre + x.im * st.pim);
-    st.unwrapped += step;
-  }
+  const float step = first_frame
+      ? fast_atan2(x.im, x.re)
+      : fast_atan2(x.im * st.pre - x.re * st.pim, x.re * st.pre + x.im * st.pim);
   st.pre = x.re; st.pim = x.im;
-  if (use_mel) { const float a = mag + eps; out = cpx{a * a, st.unwrapped}; }
+  if (use_mel) { const float a = mag + eps; out = cpx{a * a, step}; }
   else         { out = cpx{fast_log(mag + eps), step * kInvPi}; }
 }
 
 // ---- polar: work item `it` (0..M/2-1) of one frame.  Item 0 owns bin M/2 and the two
 //      purely real bins 0 and M; item it>0 owns bins it and M-it.  zB[k] <- (v0, v1):
-//      mel mode (|X|+eps)^2 and unwrapped phase, linear mode log(|X|+eps) and IF. ----
+//      mel mode (|X|+eps)^2 and the phase step, linear mode log(|X|+eps) and IF. ----
 template <typename P>
 ISI_HD void polar_item(int it, cpx* zB, cpx w /* tw[it] */, bool first_frame, bool use_mel,
                        float eps, BinState& sa, BinState& sb, BinState& sc) {
@@ -267,7 +268,9 @@ ISI_HD void polar_item(int it, cpx* zB, cpx w /* tw[it] */, bool first_frame, bo
 }
 
 // ---- emit: one output row of one frame.  `bin0` is the FFT bin of the row (linear
-//      mode) or of the first band element (mel mode); mel weights live in registers. ----
+//      mode) or of the first band element (mel mode); mel weights live in registers,
+//      zero beyond `count`; `count_uniform` >= count is uniform across the warp so whole
+//      iterations are skipped without divergence. ----
 constexpr int kMaxMelWidth = 8;
 
 ISI_HD void emit_linear(const cpx* zB, int bin0, float& out0, float& out1) {
@@ -275,21 +278,19 @@ ISI_HD void emit_linear(const cpx* zB, int bin0, float& out0, float& out1) {
   out0 = v.re; out1 = v.im;
 }
 
-ISI_HD void emit_mel(const cpx* zB, int bin0, int count, const float* w, bool first_frame,
-                     float eps, float& prev, float& out0, float& out1) {
+ISI_HD void emit_mel(const cpx* zB, int bin0, int count, int count_uniform, const float* w,
+                     bool first_frame, float eps, float& out0, float& out1) {
   float m2 = 0.f, mp = 0.f;
 #pragma unroll
   for (int i = 0; i < kMaxMelWidth; ++i) {
-    if (i < count) {
-      const cpx v = zB[bin0 + i];
+    if (i < count_uniform) {
+      const cpx v = (i < count) ? zB[bin0 + i] : cpx{0.f, 0.f};
       m2 = fmaf(w[i], v.re, m2);
       mp = fmaf(w[i], v.im, mp);
     }
   }
   out0 = fast_log(m2 + eps);
-  const float step = first_frame ? mp : wrap_step(mp - prev);
-  prev = mp;
-  out1 = step * kInvPi;
+  out1 = (first_frame ? mp : wrap_step(mp)) * kInvPi;
 }
 
 }  // namespace melif

@@ -219,15 +219,22 @@ class QuantizedBottleneck(nn.Module):
             quantize = quantize.to(input.dtype)
         return quantize, scalars[0], ind.view(*input.shape[:-1]), scalars[1]
 
+    def reduce_ema_stats(self, stats: torch.Tensor) -> torch.Tensor:
+        """Sum the packed ``[counts (K) | embed_sum (K*D, code-major)]`` buffer over the
+        ranks of ``stats_process_group`` in place (one collective per quantiser per step;
+        NCCL on GPUs).  A no-op outside torch.distributed or with ``sync_ema_stats`` off."""
+        import torch.distributed as dist
+        if (self.sync_ema_stats and dist.is_available() and dist.is_initialized()
+                and dist.get_world_size(self.stats_process_group) > 1):
+            dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=self.stats_process_group)
+        return stats
+
     def _ema_update(self, stats: torch.Tensor) -> None:
         """bottleneck.py:79-92.  With torch.distributed initialised the packed
         ``[counts | embed_sum]`` buffer is summed over ranks first, so N ranks update like
         one process on the concatenated batch (the reference itself never
         reduces these and lets DDP broadcast rank 0's buffers instead)."""
-        import torch.distributed as dist
-        if (self.sync_ema_stats and dist.is_available() and dist.is_initialized()
-                and dist.get_world_size(self.stats_process_group) > 1):
-            dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=self.stats_process_group)
+        self.reduce_ema_stats(stats)
         for buf in (self.cluster_size, self.embed_avg, self.embed):
             if not buf.is_contiguous():
                 raise RuntimeError("codebook buffers must be contiguous")

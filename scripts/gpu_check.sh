@@ -1,0 +1,41 @@
+#!/bin/bash
+# Runs on the GPU box (via gpurun): parity tests, benches and an ncu capture.
+# Usage: bash scripts/gpu_check.sh <tag> [steps...]   steps: frontend simt tc quant bench ncu_melif ncu_assign launches
+cd "${GRAFT_REPO_ROOT:-.}"
+mkdir -p gpurun_out
+tag=$1; shift
+steps="$*"
+[ -z "$steps" ] && steps="frontend quant tc bench"
+for s in $steps; do
+  case $s in
+    frontend)
+      timeout 900 python -m pytest tests/test_gpu_frontend.py -q 2>&1 | tail -40 > gpurun_out/pytest_frontend_$tag.log
+      tail -3 gpurun_out/pytest_frontend_$tag.log ;;
+    simt)
+      timeout 600 python bench.py --steps 10 --warmup 3 --assign-algo simt --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_simt_$tag.json ;;
+    tc)
+      timeout 300 python -m pytest tests/test_gpu_quantizer_tc.py -x -q -s 2>&1 | tail -60 > gpurun_out/pytest_tc_$tag.log
+      tail -15 gpurun_out/pytest_tc_$tag.log ;;
+    quant)
+      timeout 900 python -m pytest tests/test_gpu_quantizer.py -q 2>&1 | tail -40 > gpurun_out/pytest_quant_$tag.log
+      tail -3 gpurun_out/pytest_quant_$tag.log ;;
+    bench)
+      timeout 900 python bench.py --steps 20 --warmup 3 2>&1 | tail -1 > gpurun_out/bench_$tag.json
+      cut -c1-400 gpurun_out/bench_$tag.json ;;
+    ncu_melif)
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:melif_kernel -s 3 -c 1 \
+        -o gpurun_out/melif_$tag python bench.py --steps 2 --warmup 3 --no-cpu-baseline --assign-algo simt > gpurun_out/ncu_melif_$tag.log 2>&1
+      tail -1 gpurun_out/ncu_melif_$tag.log | cut -c1-200 ;;
+    ncu_assign)
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:vq_assign_tc -s 2 -c 1 \
+        -o gpurun_out/assign_$tag python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_assign_$tag.log 2>&1
+      tail -1 gpurun_out/ncu_assign_$tag.log | cut -c1-200 ;;
+    launches)
+      timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 400 --csv \
+        --log-file gpurun_out/launches_$tag.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches_$tag.log 2>&1
+      tail -1 gpurun_out/ncu_launches_$tag.log | cut -c1-200 ;;
+    all_tests)
+      timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -40 > gpurun_out/pytest_all_$tag.log
+      tail -5 gpurun_out/pytest_all_$tag.log ;;
+  esac
+done

@@ -1,0 +1,64 @@
+"""Host-side logic that needs no GPU: shard arithmetic, layout detection, band tables."""
+import numpy as np
+import pytest
+import torch
+from hypothesis import given, settings, strategies as st
+
+from interactive_spectrogram_inpainting_b200 import _lib
+from interactive_spectrogram_inpainting_b200.utils import distributed as du
+from interactive_spectrogram_inpainting_b200.utils import spectrograms_helper as sh
+
+
+@settings(max_examples=200, deadline=None)
+@given(total=st.integers(0, 5000), world=st.integers(1, 16))
+def test_shards_partition_the_notes_exactly(total, world):
+    seen_strided, seen_contig = [], []
+    for rank in range(world):
+        idx = list(du.shard_indices(total, rank, world))
+        lo, hi = du.shard_range(total, rank, world)
+        assert len(idx) == hi - lo == du.shard_size(total, rank, world)
+        seen_strided += idx
+        seen_contig += list(range(lo, hi))
+    assert sorted(seen_strided) == list(range(total))      # no pad, no drop, no duplicate
+    assert seen_contig == list(range(total))
+
+
+@settings(max_examples=100, deadline=None)
+@given(b=st.integers(1, 4), h=st.integers(1, 6), w=st.integers(1, 6), d=st.integers(1, 9))
+def test_rows_layout_addresses_every_element(b, h, w, d):
+    base = torch.arange(b * d * h * w, dtype=torch.float32).view(b, d, h, w)
+    for view in (base.permute(0, 2, 3, 1), base.permute(0, 2, 3, 1).contiguous()):
+        lay = _lib.rows_layout(view)
+        assert lay is not None
+        flat = view.reshape(-1, d)
+        storage = view.contiguous().view(-1) if view.is_contiguous() else base.view(-1)
+        for row in range(flat.shape[0]):
+            bi, r = divmod(row, lay.rows_per_batch)
+            for col in range(d):
+                off = bi * lay.batch_stride + r * lay.row_stride + col * lay.col_stride
+                assert storage[off] == flat[row, col]
+
+
+def test_rows_layout_rejects_what_it_cannot_describe():
+    t = torch.zeros(4, 6, 8, 16)[:, ::2, ::3]
+    lay = _lib.rows_layout(t)
+    if lay is not None:          # if described, it must be exact
+        flat = t.reshape(-1, 16)
+        assert lay.rows_per_batch * (flat.shape[0] // lay.rows_per_batch) == flat.shape[0]
+
+
+@pytest.mark.parametrize("n_fft", [512, 1024, 2048])
+def test_band_table_rows_are_contiguous_and_narrow(n_fft):
+    starts, counts, weights = sh.mel_band_table(n_fft, 16000, 0.0, 8000.0, 700.0, 1.5)
+    assert weights.shape[1] <= 8 and (counts <= weights.shape[1]).all()
+    assert (starts + counts <= n_fft // 2).all() and (weights >= 0).all()
+    for j in range(n_fft // 2):
+        assert (weights[j, counts[j]:] == 0).all()
+
+
+def test_helper_metadata_matches_reference_call_sites():
+    h = sh.MelSpectrogramsHelper()
+    assert (h.fs_hz, h.n_fft, h.hop_length, h.window_length) == (16000, 2048, 512, 2048)
+    assert h.safelog_eps == 1e-6 and h.num_frames(64000) == 128 and h.n_freq == 1024
+    with pytest.raises(ValueError):
+        sh.SpectrogramsHelper(n_fft=1000)

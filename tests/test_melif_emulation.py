@@ -28,7 +28,7 @@ def emu(tmp_path_factory):
     return lib
 
 
-def _run(emu, helper, audio):
+def _run(emu, helper, audio, seg_frames=0):
     n_notes, n_samples = audio.shape
     frames = helper.num_frames(n_samples)
     out = np.zeros((n_notes, 2, helper.n_freq, frames), dtype=np.float32)
@@ -46,7 +46,7 @@ def _run(emu, helper, audio):
                            helper.n_fft, helper.hop_length, helper.pad_left, frames,
                            1 if helper.drop_bin == "dc" else 0, int(helper.use_mel_scale), width,
                            ctypes.c_float(helper.safelog_eps), ptr(win), ptr(tw), *mel_args,
-                           ptr(out))
+                           ptr(out), seg_frames)
     assert rc == 0
     return torch.from_numpy(out)
 
@@ -113,6 +113,16 @@ def test_emulated_kernel_other_sizes_and_ragged_lengths(emu, n_fft, hop, samples
     cfg = fo.FrontEndConfig(n_fft=n_fft, hop_length=hop, window_length=n_fft)
     assert got.shape[-1] == fo.frame_geometry(cfg, samples)[2]
     check_against_oracle(got, audio, cfg)
+
+
+def test_emulated_segments_equal_whole_note(emu):
+    """A note split into frame segments (each re-deriving the previous frame's spectrum with
+    a look-back transform) gives bit-identical output to the unsplit note."""
+    audio = synthetic.synthetic_notes(1)
+    helper = sh.MelSpectrogramsHelper()
+    whole = _run(emu, helper, audio)
+    for seg in (16, 44, 64):
+        assert torch.equal(_run(emu, helper, audio, seg_frames=seg), whole)
 
 
 def test_emulated_kernel_nyquist_knob(emu):
