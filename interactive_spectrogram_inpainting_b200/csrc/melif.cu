@@ -64,17 +64,17 @@ __host__ __device__ inline MelifSmem melif_smem_layout(int hop) {
   using P = Plan<NFFT>;
   MelifSmem s;
   int off = 0;
-  s.tw = off;    off += NFFT * 8;
+  s.tw = off;    off += (NFFT / 2) * 8;                     // W_M^e, e < M
   s.win = off;   off += NFFT * 4;
   s.stage = off; off += (((FB - 1) * hop + NFFT + 3) / 4) * 16;
-  s.za = off;    off += FB * P::kPitchA * 8;
+  s.za = off;    off += FB * P::kPitchA * 8;                // also zC[bin][FB] during polar/emit
   s.zb = off;    off += FB * P::kPitchB * 8;
   s.bar = off;   off += 16;
   s.total = off;
   return s;
 }
 
-template <int NFFT, int FB, int NT>
+template <int NFFT, int FB, int NT, bool MEL>
 __global__ void __launch_bounds__(NT, 2)
 melif_kernel(const float* __restrict__ audio, int64_t n_samples, isi_melif_params p,
              float* __restrict__ out, int bulk_ok, int seg_frames, int n_segs) {
@@ -84,12 +84,14 @@ melif_kernel(const float* __restrict__ audio, int64_t n_samples, isi_melif_param
   constexpr int RPT = M / NT;                 // output rows per thread
   constexpr int kGroups = NT / 64;            // frames transformed concurrently
   static_assert(IPT >= 1 && (M / 2) % NT == 0 && NT % 64 == 0, "bad thread count");
+  static_assert(FB * P::kPitchA >= (M + 1) * FB, "zC must fit in zA");
   extern __shared__ __align__(128) unsigned char smem[];
   const MelifSmem L = melif_smem_layout<NFFT, FB>(p.hop);
-  cpx* tw = reinterpret_cast<cpx*>(smem + L.tw);
+  cpx* twm = reinterpret_cast<cpx*>(smem + L.tw);
   float* win = reinterpret_cast<float*>(smem + L.win);
   float* stage = reinterpret_cast<float*>(smem + L.stage);
   cpx* zA = reinterpret_cast<cpx*>(smem + L.za);
+  cpx* zC = zA;
   cpx* zB = reinterpret_cast<cpx*>(smem + L.zb);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar);
 
@@ -100,39 +102,37 @@ melif_kernel(const float* __restrict__ audio, int64_t n_samples, isi_melif_param
   const float* note = audio + (int64_t)note_idx * n_samples;
   float* out0 = out + (int64_t)note_idx * 2 * M * p.n_frames;
   float* out1 = out0 + (int64_t)M * p.n_frames;
-  const bool use_mel = p.use_mel != 0;
   const int dc = p.drop_dc ? 1 : 0;
   const float eps = p.safelog_eps;
+  const bool frames_aligned8 = (p.hop % 2) == 0;
 
   // ---- one-time setup: tables to shared memory, per-thread constants to registers ----
-  for (int i = tid; i < NFFT; i += NT) {
-    tw[i] = reinterpret_cast<const cpx*>(p.twiddle)[i];
-    win[i] = p.window[i];
-  }
+  const cpx* tw_global = reinterpret_cast<const cpx*>(p.twiddle);     // W_N^j, j < N
+  for (int i = tid; i < M; i += NT) twm[i] = tw_global[2 * i];
+  for (int i = tid; i < NFFT; i += NT) win[i] = p.window[i];
   if (tid == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   cpx w_item[IPT];
 #pragma unroll
-  for (int i = 0; i < IPT; ++i) w_item[i] = reinterpret_cast<const cpx*>(p.twiddle)[tid + i * NT];
+  for (int i = 0; i < IPT; ++i) w_item[i] = tw_global[tid + i * NT];
   int row_bin[RPT], row_cnt[RPT], row_cnt_warp[RPT];
-  float row_w[RPT][kMaxMelWidth];
+  float row_w[RPT][MEL ? kMaxMelWidth : 1];
 #pragma unroll
   for (int r = 0; r < RPT; ++r) {
     const int row = tid + r * NT;
     row_cnt[r] = 0;
     row_bin[r] = row + dc;
-#pragma unroll
-    for (int i = 0; i < kMaxMelWidth; ++i) row_w[r][i] = 0.f;
-    if (use_mel) {
+    row_cnt_warp[r] = 0;
+    if (MEL) {
       row_bin[r] = p.mel_start[row] + dc;
       row_cnt[r] = p.mel_count[row];
 #pragma unroll
       for (int i = 0; i < kMaxMelWidth; ++i)
-        if (i < p.mel_width) row_w[r][i] = p.mel_weight[(int64_t)row * p.mel_width + i];
+        row_w[r][i] = (i < p.mel_width) ? p.mel_weight[(int64_t)row * p.mel_width + i] : 0.f;
+      row_cnt_warp[r] = __reduce_max_sync(0xffffffffu, row_cnt[r]);
     }
-    row_cnt_warp[r] = __reduce_max_sync(0xffffffffu, row_cnt[r]);
   }
   BinState sa[IPT], sb[IPT], sc{1.f, 0.f};
 #pragma unroll
@@ -165,87 +165,67 @@ melif_kernel(const float* __restrict__ audio, int64_t n_samples, isi_melif_param
       }
     }
   };
+
+  // Batch -1 is the look-back transform of frame fs-1: it only seeds the phase-step state.
+  const int n_batches = (fe - fs + FB - 1) / FB;
+  const int b_begin = fs > 0 ? -1 : 0;
+  stage_span(fs > 0 ? fs - 1 : fs, fs > 0 ? 1 : min(FB, fe - fs));
   uint32_t stage_phase = 0;
-  auto stage_wait = [&]() {
+
+  for (int b = b_begin; b < n_batches; ++b) {
+    const bool lookback = b < 0;
+    const int f0 = lookback ? fs - 1 : fs + b * FB;
+    const int nf = lookback ? 1 : min(FB, fe - f0);
+    const int next_f0 = fs + (b + 1) * FB;
+    const int next_nf = (b + 1 < n_batches) ? min(FB, fe - next_f0) : 0;
+
     if (bulk_ok) { mbar_wait(bar, stage_phase & 1); ++stage_phase; }
-    __syncthreads();       // zero-filled pads / synchronous fills were written by other threads
-  };
-  auto transform = [&](int nf, int next_frame, int next_nfr) {
+    __syncthreads();       // zero-filled pads / synchronous fills come from other threads;
+                           // also fences the previous batch's emit (zC) from this pass 1 (zA)
     for (int fb = tid / 64; fb < nf; fb += kGroups)
-      fft_pass1<P>(tid & 63, stage + fb * p.hop, win, tw, zA + fb * P::kPitchA);
+      fft_pass1<P>(tid & 63, stage + fb * p.hop, frames_aligned8, win, twm, zA + fb * P::kPitchA);
     __syncthreads();
-    if (next_nfr > 0 && bulk_ok) stage_span(next_frame, next_nfr);   // the stage is free again
-    for (int fb = tid / 64; fb < nf; fb += kGroups) fft_pass2<P>(tid & 63, tw, zA + fb * P::kPitchA);
+    if (next_nf > 0 && bulk_ok) stage_span(next_f0, next_nf);          // the stage is free again
+    for (int fb = tid / 64; fb < nf; fb += kGroups) fft_pass2<P>(tid & 63, twm, zA + fb * P::kPitchA);
     __syncthreads();
     for (int fb = tid / 64; fb < nf; fb += kGroups)
       fft_pass3<P>(tid & 63, zA + fb * P::kPitchA, zB + fb * P::kPitchB);
     __syncthreads();
-  };
-
-  const int n_batches = (fe - fs + FB - 1) / FB;
-  // ---- look-back: the spectrum of frame fs-1 seeds the phase-step state ----
-  if (fs > 0) {
-    stage_span(fs - 1, 1);
-    stage_wait();
-    transform(1, fs, min(FB, fe - fs));
+    // polar: frames in order, previous spectrum value in registers; zB -> zC (= zA storage)
+#pragma unroll 1
+    for (int fb = 0; fb < nf; ++fb) {
 #pragma unroll
-    for (int i = 0; i < IPT; ++i)
-      polar_item<P>(tid + i * NT, zB, w_item[i], true, use_mel, eps, sa[i], sb[i], sc);
-    if (!bulk_ok) { __syncthreads(); stage_span(fs, min(FB, fe - fs)); }
-  } else {
-    stage_span(fs, min(FB, fe - fs));
-  }
-
-  for (int b = 0; b < n_batches; ++b) {
-    const int f0 = fs + b * FB;
-    const int nf = min(FB, fe - f0);
-    stage_wait();
-    const int next_nfr = (b + 1 < n_batches) ? min(FB, fe - (f0 + FB)) : 0;
-    transform(nf, f0 + FB, next_nfr);
-    // polar: frames in order, previous spectrum value in registers
-#pragma unroll
-    for (int fb = 0; fb < FB; ++fb) {
-      if (fb < nf) {
-#pragma unroll
-        for (int i = 0; i < IPT; ++i)
-          polar_item<P>(tid + i * NT, zB + fb * P::kPitchB, w_item[i], f0 + fb == 0, use_mel, eps,
-                        sa[i], sb[i], sc);
-      }
+      for (int i = 0; i < IPT; ++i)
+        polar_item<P, FB, MEL>(tid + i * NT, zB + fb * P::kPitchB, zC, fb, w_item[i],
+                               lookback || (f0 + fb == 0), eps, sa[i], sb[i], sc);
     }
-    __syncthreads();
-    // emit: FB consecutive time steps per row
+    if (!lookback) {
+      __syncthreads();
+      // emit: all FB time steps of a row at once
 #pragma unroll
-    for (int r = 0; r < RPT; ++r) {
-      const int row = tid + r * NT;
-      float v0[FB], v1[FB];
+      for (int r = 0; r < RPT; ++r) {
+        const int row = tid + r * NT;
+        float v0[FB], v1[FB];
+        if (MEL)
+          emit_mel<FB>(zC, row_bin[r], row_cnt[r], row_cnt_warp[r], row_w[r], f0 == 0, eps, v0, v1);
+        else
+          emit_linear<FB>(zC, row_bin[r], v0, v1);
+        float* d0 = out0 + (int64_t)row * p.n_frames + f0;
+        float* d1 = out1 + (int64_t)row * p.n_frames + f0;
+        if (nf == FB && (FB % 4 == 0) && (p.n_frames % 4 == 0)) {
 #pragma unroll
-      for (int fb = 0; fb < FB; ++fb) {
-        v0[fb] = 0.f; v1[fb] = 0.f;
-        if (fb < nf) {
-          if (use_mel)
-            emit_mel(zB + fb * P::kPitchB, row_bin[r], row_cnt[r], row_cnt_warp[r], row_w[r],
-                     f0 + fb == 0, eps, v0[fb], v1[fb]);
-          else
-            emit_linear(zB + fb * P::kPitchB, row_bin[r], v0[fb], v1[fb]);
+          for (int q = 0; q < FB / 4; ++q) {
+            reinterpret_cast<float4*>(d0)[q] = make_float4(v0[4 * q], v0[4 * q + 1], v0[4 * q + 2], v0[4 * q + 3]);
+            reinterpret_cast<float4*>(d1)[q] = make_float4(v1[4 * q], v1[4 * q + 1], v1[4 * q + 2], v1[4 * q + 3]);
+          }
+        } else {
+#pragma unroll
+          for (int fb = 0; fb < FB; ++fb)
+            if (fb < nf) { d0[fb] = v0[fb]; d1[fb] = v1[fb]; }
         }
       }
-      float* d0 = out0 + (int64_t)row * p.n_frames + f0;
-      float* d1 = out1 + (int64_t)row * p.n_frames + f0;
-      if (nf == FB && (FB % 4 == 0) && (p.n_frames % 4 == 0)) {
-#pragma unroll
-        for (int q = 0; q < FB / 4; ++q) {
-          __stcs(reinterpret_cast<float4*>(d0) + q,
-                 make_float4(v0[4 * q], v0[4 * q + 1], v0[4 * q + 2], v0[4 * q + 3]));
-          __stcs(reinterpret_cast<float4*>(d1) + q,
-                 make_float4(v1[4 * q], v1[4 * q + 1], v1[4 * q + 2], v1[4 * q + 3]));
-        }
-      } else {
-#pragma unroll
-        for (int fb = 0; fb < FB; ++fb)
-          if (fb < nf) { d0[fb] = v0[fb]; d1[fb] = v1[fb]; }
-      }
     }
-    if (!bulk_ok && b + 1 < n_batches) { __syncthreads(); stage_span(f0 + FB, next_nfr); }
+    if (!bulk_ok && next_nf > 0) { __syncthreads(); stage_span(next_f0, next_nf); }
   }
 }
 
@@ -267,12 +247,12 @@ static void choose_segments(int64_t n_notes, int n_frames, int fb, int* seg_fram
   }
 }
 
-template <int NFFT, int FB, int NT>
+template <int NFFT, int FB, int NT, bool MEL>
 static int launch_melif_t(const float* audio, int64_t n_notes, int64_t n_samples,
                           const isi_melif_params& p, float* out, cudaStream_t stream) {
   const MelifSmem L = melif_smem_layout<NFFT, FB>(p.hop);
   if (L.total > 227 * 1024) return ISI_ERR_UNSUPPORTED;
-  cudaError_t e = cudaFuncSetAttribute(melif_kernel<NFFT, FB, NT>,
+  cudaError_t e = cudaFuncSetAttribute(melif_kernel<NFFT, FB, NT, MEL>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
   if (e != cudaSuccess) return (int)e;
   // the bulk copy needs 16-byte aligned global addresses and sizes
@@ -281,7 +261,7 @@ static int launch_melif_t(const float* audio, int64_t n_notes, int64_t n_samples
   int seg_frames, n_segs;
   choose_segments(n_notes, p.n_frames, FB, &seg_frames, &n_segs);
   if (n_notes * n_segs > 0x7fffffff) return ISI_ERR_SHAPE;
-  melif_kernel<NFFT, FB, NT><<<(unsigned)(n_notes * n_segs), NT, L.total, stream>>>(
+  melif_kernel<NFFT, FB, NT, MEL><<<(unsigned)(n_notes * n_segs), NT, L.total, stream>>>(
       audio, n_samples, p, out, bulk_ok, seg_frames, n_segs);
   ISI_LAUNCH_CHECK();
   return ISI_OK;
@@ -290,12 +270,17 @@ static int launch_melif_t(const float* audio, int64_t n_notes, int64_t n_samples
 int launch_melif(const float* audio, int64_t n_notes, int64_t n_samples,
                  const isi_melif_params& p, float* out, cudaStream_t stream) {
   if (p.use_mel && p.mel_width > kMaxMelWidth) return ISI_ERR_UNSUPPORTED;
+#define ISI_MELIF_CASE(N, FB, NT)                                                            \
+  case N:                                                                                  \
+    return p.use_mel ? launch_melif_t<N, FB, NT, true>(audio, n_notes, n_samples, p, out, stream) \
+                     : launch_melif_t<N, FB, NT, false>(audio, n_notes, n_samples, p, out, stream);
   switch (p.n_fft) {
-    case 2048: return launch_melif_t<2048, 4, 256>(audio, n_notes, n_samples, p, out, stream);
-    case 1024: return launch_melif_t<1024, 4, 128>(audio, n_notes, n_samples, p, out, stream);
-    case 512:  return launch_melif_t<512, 4, 64>(audio, n_notes, n_samples, p, out, stream);
-    default:   return ISI_ERR_UNSUPPORTED;
+    ISI_MELIF_CASE(2048, 4, 256)
+    ISI_MELIF_CASE(1024, 4, 128)
+    ISI_MELIF_CASE(512, 4, 64)
+    default: return ISI_ERR_UNSUPPORTED;
   }
+#undef ISI_MELIF_CASE
 }
 
 }  // namespace isi

@@ -11,9 +11,10 @@
 //   pass 2  radix 16 over stride 4 inside each 64-block of zA, twiddle, in place
 //   pass 3  radix 4 on consecutive quadruples of zA, written in natural bin order to zB
 //   polar   untangle X[k], X[M-k] from Z[k], Z[M-k]; |X|, phase step = arg(X_t conj X_t-1)
-//           (previous spectrum value carried in registers); (v0, v1) overwrite zB in place
+//           (previous spectrum value carried in registers); (v0, v1) go to zC[bin][frame],
+//           which reuses zA's storage
 //   emit    banded mel projections of (|X|+eps)^2 and of the phase steps (or a copy in
-//           linear mode), log and wrapped mel-IF, FB consecutive time steps per row
+//           linear mode) for all FB frames of a row at once, log and wrapped mel-IF
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -59,9 +60,11 @@ ISI_HD float fast_rsqrt(float x) {         // one MUFU.RSQ, ~2 ulp
   return 1.0f / sqrtf(x);
 #endif
 }
-ISI_HD float fast_log(float x) {
+ISI_HD float fast_log(float x) {           // one MUFU.LG2 + one multiply
 #ifdef __CUDA_ARCH__
-  return __logf(x);
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r * 0.69314718055994530942f;
 #else
   return logf(x);
 #endif
@@ -160,27 +163,38 @@ ISI_HD void stage_fill(int t, int nt, float* stage, int span, const float* audio
   }
 }
 
-// twiddle table: tw[j] = exp(-2 pi i j / N), j in [0, N)
+// twiddle table in shared memory: twm[e] = exp(-2 pi i e / M), e in [0, M)
 // ---- pass 1 (thread j of 64): window, pack, radix R1 over stride 64 ----
 template <typename P>
-ISI_HD void fft_pass1(int j, const float* frame /* stage + fb*hop */, const float* win,
-                      const cpx* tw, cpx* zA) {
+ISI_HD void fft_pass1(int j, const float* frame /* stage + fb*hop */, bool frame_aligned8,
+                      const float* win, const cpx* twm, cpx* zA) {
   cpx v[P::R1];
+  if (frame_aligned8) {
 #pragma unroll
-  for (int r = 0; r < P::R1; ++r) {
-    const int m = j + 64 * r;
-    v[r] = cpx{frame[2 * m] * win[2 * m], frame[2 * m + 1] * win[2 * m + 1]};
+    for (int r = 0; r < P::R1; ++r) {
+      const int m = j + 64 * r;
+      const cpx a = reinterpret_cast<const cpx*>(frame)[m];
+      const cpx w = reinterpret_cast<const cpx*>(win)[m];
+      v[r] = cpx{a.re * w.re, a.im * w.im};
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < P::R1; ++r) {
+      const int m = j + 64 * r;
+      const cpx w = reinterpret_cast<const cpx*>(win)[m];
+      v[r] = cpx{frame[2 * m] * w.re, frame[2 * m + 1] * w.im};
+    }
   }
   dft_small<P::R1>(v);
 #pragma unroll
-  for (int p = 1; p < P::R1; ++p) v[p] = cmul(v[p], tw[2 * j * p]);   // W_M^(j p) = W_N^(2 j p)
+  for (int p = 1; p < P::R1; ++p) v[p] = cmul(v[p], twm[j * p]);               // W_M^(j p)
 #pragma unroll
   for (int p = 0; p < P::R1; ++p) zA[j + 68 * p] = v[p];
 }
 
 // ---- pass 2: inside each (padded) 64-block, radix 16 over stride 4 ----
 template <typename P>
-ISI_HD void fft_pass2(int t, const cpx* tw, cpx* zA) {
+ISI_HD void fft_pass2(int t, const cpx* twm, cpx* zA) {
   for (int item = t; item < 4 * P::R1; item += P::kFftThreads) {
     const int b = item >> 2, j = item & 3;
     cpx* blk = zA + 68 * b;
@@ -190,7 +204,7 @@ ISI_HD void fft_pass2(int t, const cpx* tw, cpx* zA) {
     dft16(v);
     if (j != 0) {
 #pragma unroll
-      for (int p = 1; p < 16; ++p) v[p] = cmul(v[p], tw[(P::N / 64) * j * p]);   // W_64^(j p)
+      for (int p = 1; p < 16; ++p) v[p] = cmul(v[p], twm[P::R1 * j * p]);      // W_64^(j p)
     }
 #pragma unroll
     for (int p = 0; p < 16; ++p) blk[j + 4 * p] = v[p];
@@ -225,7 +239,8 @@ ISI_HD float wrap_step(float dd) {
 //   mel_phase_t - mel_phase_{t-1} = sum_k w_k (u_t[k] - u_{t-1}[k]) = sum_k w_k step_t[k].
 struct BinState { float pre, pim; };
 
-ISI_HD void polar_bin(cpx x, bool first_frame, bool use_mel, float eps, BinState& st, cpx& out) {
+template <bool MEL>
+ISI_HD cpx polar_bin(cpx x, bool first_frame, float eps, BinState& st) {
   const float m2 = fmaf(x.re, x.re, x.im * x.im);
   const float mag = (m2 > 1.17549435e-38f) ? m2 * fast_rsqrt(m2) : 0.f;
   if (x.re == 0.f && x.im == 0.f) x.re = 1.f;
@@ -233,64 +248,71 @@ ISI_HD void polar_bin(cpx x, bool first_frame, bool use_mel, float eps, BinState
       ? fast_atan2(x.im, x.re)
       : fast_atan2(x.im * st.pre - x.re * st.pim, x.re * st.pre + x.im * st.pim);
   st.pre = x.re; st.pim = x.im;
-  if (use_mel) { const float a = mag + eps; out = cpx{a * a, step}; }
-  else         { out = cpx{fast_log(mag + eps), step * kInvPi}; }
+  if (MEL) { const float a = mag + eps; return cpx{a * a, step}; }
+  return cpx{fast_log(mag + eps), step * kInvPi};
 }
 
-// ---- polar: work item `it` (0..M/2-1) of one frame.  Item 0 owns bin M/2 and the two
-//      purely real bins 0 and M; item it>0 owns bins it and M-it.  zB[k] <- (v0, v1):
+// ---- polar: work item `it` (0..M/2-1) of frame slot `fb`.  Item 0 owns bin M/2 and the
+//      two purely real bins 0 and M; item it>0 owns bins it and M-it.  Reads the natural
+//      order spectrum zB (one frame), writes (v0, v1) to zC[bin][fb] (FB frames per bin):
 //      mel mode (|X|+eps)^2 and the phase step, linear mode log(|X|+eps) and IF. ----
-template <typename P>
-ISI_HD void polar_item(int it, cpx* zB, cpx w /* tw[it] */, bool first_frame, bool use_mel,
-                       float eps, BinState& sa, BinState& sb, BinState& sc) {
+template <typename P, int FB, bool MEL>
+ISI_HD void polar_item(int it, const cpx* zB, cpx* zC, int fb, cpx w /* W_N^it */,
+                       bool first_frame, float eps, BinState& sa, BinState& sb, BinState& sc) {
   constexpr int M = P::M;
   if (it == 0) {
     const cpx z0 = zB[0], zh = zB[M / 2];
-    cpx o;
-    polar_bin(cpx{zh.re, -zh.im}, first_frame, use_mel, eps, sa, o);          // X[M/2]
-    zB[M / 2] = o;
-    polar_bin(cpx{z0.re + z0.im, 0.f}, first_frame, use_mel, eps, sb, o);     // X[0]
-    zB[0] = o;
-    polar_bin(cpx{z0.re - z0.im, 0.f}, first_frame, use_mel, eps, sc, o);     // X[M]
-    zB[M] = o;
+    zC[(M / 2) * FB + fb] = polar_bin<MEL>(cpx{zh.re, -zh.im}, first_frame, eps, sa);      // X[M/2]
+    zC[fb] = polar_bin<MEL>(cpx{z0.re + z0.im, 0.f}, first_frame, eps, sb);                // X[0]
+    zC[M * FB + fb] = polar_bin<MEL>(cpx{z0.re - z0.im, 0.f}, first_frame, eps, sc);       // X[M]
   } else {
     const cpx a = zB[it], b = zB[M - it];
     const cpx e = cpx{0.5f * (a.re + b.re), 0.5f * (a.im - b.im)};            // (A + conj B)/2
     const cpx d = cpx{0.5f * (a.re - b.re), 0.5f * (a.im + b.im)};            // (A - conj B)/2
     const cpx p = cmul(w, mul_neg_i(d));                                      // W_N^k (-i) d
     const cpx m = csub(e, p);
-    cpx o;
-    polar_bin(cadd(e, p), first_frame, use_mel, eps, sa, o);
-    zB[it] = o;
-    polar_bin(cpx{m.re, -m.im}, first_frame, use_mel, eps, sb, o);
-    zB[M - it] = o;
+    zC[it * FB + fb] = polar_bin<MEL>(cadd(e, p), first_frame, eps, sa);
+    zC[(M - it) * FB + fb] = polar_bin<MEL>(cpx{m.re, -m.im}, first_frame, eps, sb);
   }
 }
 
-// ---- emit: one output row of one frame.  `bin0` is the FFT bin of the row (linear
-//      mode) or of the first band element (mel mode); mel weights live in registers,
-//      zero beyond `count`; `count_uniform` >= count is uniform across the warp so whole
-//      iterations are skipped without divergence. ----
+// ---- emit: one output row, all FB frames of the batch at once, from zC[bin][fb].
+//      `bin0` is the FFT bin of the row (linear mode) or of the first band element (mel
+//      mode); mel weights live in registers, zero beyond `count`; `count_uniform` >= count
+//      is uniform across the warp so whole taps are skipped without divergence. ----
 constexpr int kMaxMelWidth = 8;
 
-ISI_HD void emit_linear(const cpx* zB, int bin0, float& out0, float& out1) {
-  const cpx v = zB[bin0];
-  out0 = v.re; out1 = v.im;
+template <int FB>
+ISI_HD void emit_linear(const cpx* zC, int bin0, float* out0, float* out1) {
+#pragma unroll
+  for (int fb = 0; fb < FB; ++fb) { const cpx v = zC[bin0 * FB + fb]; out0[fb] = v.re; out1[fb] = v.im; }
 }
 
-ISI_HD void emit_mel(const cpx* zB, int bin0, int count, int count_uniform, const float* w,
-                     bool first_frame, float eps, float& out0, float& out1) {
-  float m2 = 0.f, mp = 0.f;
+template <int FB>
+ISI_HD void emit_mel(const cpx* zC, int bin0, int count, int count_uniform, const float* w,
+                     bool first_is_frame0, float eps, float* out0, float* out1) {
+  float m2[FB], mp[FB];
+#pragma unroll
+  for (int fb = 0; fb < FB; ++fb) { m2[fb] = 0.f; mp[fb] = 0.f; }
 #pragma unroll
   for (int i = 0; i < kMaxMelWidth; ++i) {
     if (i < count_uniform) {
-      const cpx v = (i < count) ? zB[bin0 + i] : cpx{0.f, 0.f};
-      m2 = fmaf(w[i], v.re, m2);
-      mp = fmaf(w[i], v.im, mp);
+      if (i < count) {
+        const cpx* q = zC + (bin0 + i) * FB;
+#pragma unroll
+        for (int fb = 0; fb < FB; ++fb) {
+          const cpx v = q[fb];
+          m2[fb] = fmaf(w[i], v.re, m2[fb]);
+          mp[fb] = fmaf(w[i], v.im, mp[fb]);
+        }
+      }
     }
   }
-  out0 = fast_log(m2 + eps);
-  out1 = (first_frame ? mp : wrap_step(mp)) * kInvPi;
+#pragma unroll
+  for (int fb = 0; fb < FB; ++fb) {
+    out0[fb] = fast_log(m2[fb] + eps);
+    out1[fb] = ((fb == 0 && first_is_frame0) ? mp[fb] : wrap_step(mp[fb])) * kInvPi;
+  }
 }
 
 }  // namespace melif

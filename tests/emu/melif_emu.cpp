@@ -11,7 +11,7 @@
 
 using namespace isi::melif;
 
-template <int NFFT, int FB, int NT>
+template <int NFFT, int FB, int NT, bool MEL>
 static void emulate(const float* audio, int64_t n_notes, int64_t n_samples, int hop, int pad_left,
                     int n_frames, int drop_dc, int use_mel, int mel_width, float eps,
                     const float* window, const float* twiddle, const int32_t* mel_start,
@@ -19,9 +19,13 @@ static void emulate(const float* audio, int64_t n_notes, int64_t n_samples, int 
   using P = Plan<NFFT>;
   constexpr int M = P::M, IPT = (M / 2) / NT, RPT = M / NT, kGroups = NT / 64;
   const cpx* tw = reinterpret_cast<const cpx*>(twiddle);
+  std::vector<cpx> twm(M);
+  for (int i = 0; i < M; ++i) twm[i] = tw[2 * i];
+  const bool aligned8 = (hop % 2) == 0;
   const int dc = drop_dc ? 1 : 0;
   std::vector<float> stage((FB - 1) * hop + NFFT);
   std::vector<cpx> zA((size_t)FB * P::kPitchA), zB((size_t)FB * P::kPitchB);
+  cpx* zC = zA.data();
   const int n_segs = (n_frames + seg_frames - 1) / seg_frames;
 
   auto transform = [&](const float* note, int frame, int nf) {
@@ -30,10 +34,10 @@ static void emulate(const float* audio, int64_t n_notes, int64_t n_samples, int 
       stage_fill(tid, NT, stage.data(), span, note, n_samples, (int64_t)frame * hop - pad_left);
     for (int tid = 0; tid < NT; ++tid)
       for (int fb = tid / 64; fb < nf; fb += kGroups)
-        fft_pass1<P>(tid & 63, stage.data() + fb * hop, window, tw, zA.data() + fb * P::kPitchA);
+        fft_pass1<P>(tid & 63, stage.data() + fb * hop, aligned8, window, twm.data(), zA.data() + fb * P::kPitchA);
     for (int tid = 0; tid < NT; ++tid)
       for (int fb = tid / 64; fb < nf; fb += kGroups)
-        fft_pass2<P>(tid & 63, tw, zA.data() + fb * P::kPitchA);
+        fft_pass2<P>(tid & 63, twm.data(), zA.data() + fb * P::kPitchA);
     for (int tid = 0; tid < NT; ++tid)
       for (int fb = tid / 64; fb < nf; fb += kGroups)
         fft_pass3<P>(tid & 63, zA.data() + fb * P::kPitchA, zB.data() + fb * P::kPitchB);
@@ -50,8 +54,8 @@ static void emulate(const float* audio, int64_t n_notes, int64_t n_samples, int 
         transform(note, fs - 1, 1);
         for (int tid = 0; tid < NT; ++tid)
           for (int i = 0; i < IPT; ++i)
-            polar_item<P>(tid + i * NT, zB.data(), tw[tid + i * NT], true, use_mel != 0, eps,
-                          sa[tid * IPT + i], sb[tid * IPT + i], sc[tid]);
+            polar_item<P, FB, MEL>(tid + i * NT, zB.data(), zC, 0, tw[tid + i * NT], true, eps,
+                                   sa[tid * IPT + i], sb[tid * IPT + i], sc[tid]);
       }
       for (int f0 = fs; f0 < fe; f0 += FB) {
         const int nf = std::min(FB, fe - f0);
@@ -59,8 +63,8 @@ static void emulate(const float* audio, int64_t n_notes, int64_t n_samples, int 
         for (int tid = 0; tid < NT; ++tid)
           for (int fb = 0; fb < nf; ++fb)
             for (int i = 0; i < IPT; ++i)
-              polar_item<P>(tid + i * NT, zB.data() + fb * P::kPitchB, tw[tid + i * NT], f0 + fb == 0,
-                            use_mel != 0, eps, sa[tid * IPT + i], sb[tid * IPT + i], sc[tid]);
+              polar_item<P, FB, MEL>(tid + i * NT, zB.data() + fb * P::kPitchB, zC, fb, tw[tid + i * NT],
+                                     f0 + fb == 0, eps, sa[tid * IPT + i], sb[tid * IPT + i], sc[tid]);
         for (int tid = 0; tid < NT; ++tid)
           for (int r = 0; r < RPT; ++r) {
             const int row = tid + r * NT;
@@ -70,14 +74,12 @@ static void emulate(const float* audio, int64_t n_notes, int64_t n_samples, int 
               bin0 = mel_start[row] + dc; cnt = mel_count[row];
               for (int i = 0; i < mel_width && i < kMaxMelWidth; ++i) w[i] = mel_weight[(int64_t)row * mel_width + i];
             }
+            float v0[FB], v1[FB];
+            if (MEL) emit_mel<FB>(zC, bin0, cnt, kMaxMelWidth, w, f0 == 0, eps, v0, v1);
+            else     emit_linear<FB>(zC, bin0, v0, v1);
             for (int fb = 0; fb < nf; ++fb) {
-              float v0, v1;
-              if (use_mel)
-                emit_mel(zB.data() + fb * P::kPitchB, bin0, cnt, kMaxMelWidth, w, f0 + fb == 0, eps, v0, v1);
-              else
-                emit_linear(zB.data() + fb * P::kPitchB, bin0, v0, v1);
-              out0[(int64_t)row * n_frames + f0 + fb] = v0;
-              out1[(int64_t)row * n_frames + f0 + fb] = v1;
+              out0[(int64_t)row * n_frames + f0 + fb] = v0[fb];
+              out1[(int64_t)row * n_frames + f0 + fb] = v1[fb];
             }
           }
       }
@@ -92,10 +94,11 @@ extern "C" int melif_emulate(const float* audio, int64_t n_notes, int64_t n_samp
 #define ARGS audio, n_notes, n_samples, hop, pad_left, n_frames, drop_dc, use_mel, mel_width, eps, \
              window, twiddle, mel_start, mel_count, mel_weight, out, seg_frames
   if (seg_frames <= 0) seg_frames = (n_frames + 3) / 4 * 4;
+#define CASE(N, FB, NT) case N: if (use_mel) emulate<N, FB, NT, true>(ARGS); else emulate<N, FB, NT, false>(ARGS); return 0;
   switch (n_fft) {
-    case 2048: emulate<2048, 4, 256>(ARGS); return 0;
-    case 1024: emulate<1024, 4, 128>(ARGS); return 0;
-    case 512:  emulate<512, 4, 64>(ARGS); return 0;
+    CASE(2048, 4, 256)
+    CASE(1024, 4, 128)
+    CASE(512, 4, 64)
     default: return -3;
   }
 }
