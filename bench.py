@@ -105,6 +105,66 @@ class ClockSampler:
         return out
 
 
+class NvmlClockSampler:
+    """SM clock, max clock and throttle reasons sampled every ~10 ms from NVML on a thread;
+    only samples taken between ``start()`` and ``stop()`` (the timed region) are summarised.
+    Falls back to the nvidia-smi sampler when pynvml is unavailable."""
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
+               "sw_power_cap": 0x4}
+
+    def __init__(self, index: int):
+        import threading
+        self.samples, self.lock = [], threading.Lock()
+        self.active, self.done = False, False
+        self.thread, self.handle, self.nvml = None, None, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML indexes physical devices; honour CUDA_VISIBLE_DEVICES if it remaps them
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.nvml = None
+
+    def _run(self):
+        n = self.nvml
+        while not self.done:
+            if self.active:
+                try:
+                    sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+                    mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+                    try:
+                        rs = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+                    except Exception:
+                        rs = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+                    with self.lock:
+                        self.samples.append((sm, mx, rs))
+                except Exception:
+                    pass
+            time.sleep(0.01)
+
+    def start(self):
+        self.active = True
+
+    def stop(self):
+        self.active = False
+
+    def summary(self):
+        self.done = True
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        with self.lock:
+            s = list(self.samples)
+        if s:
+            reasons = sorted(k for k, bit in self.REASONS.items() if any(r & bit for _, _, r in s))
+            out.update(sm_mhz=statistics.median(x[0] for x in s), sm_max_mhz=max(x[1] for x in s),
+                       reasons=reasons, samples=len(s))
+        return out
+
+
 def make_audio(batch: int, seed_offset: int = 0) -> torch.Tensor:
     from interactive_spectrogram_inpainting_b200.utils import synthetic
     base = synthetic.synthetic_notes(min(batch, 64), seed=synthetic.AUDIO_SEED + seed_offset)
@@ -198,8 +258,12 @@ def b200_arm(args):
 
     B, K, W = args.batch, args.steps, max(args.warmup, 3)
     torch.manual_seed(0)
-    helper = MelSpectrogramsHelper().to(dev)
+    cl = bool(args.channels_last)
+    helper = MelSpectrogramsHelper(channels_last=cl).to(dev)
     model = VQVAE(**MODEL_KW).to(dev).eval()
+    if cl:      # same values, NHWC storage end to end: no cuDNN layout-conversion kernels
+        model = model.to(memory_format=torch.channels_last)
+    clocks = NvmlClockSampler(local)
     model.quantize_t.assign_algo = model.quantize_b.assign_algo = args.assign_algo
     host_audio = make_audio(B, seed_offset=rank).pin_memory()
     audio = host_audio.to(dev)
@@ -232,13 +296,14 @@ def b200_arm(args):
         step(audio)
     barrier()
     launches0 = _lib.total_launches()
-    with ClockSampler(local) as clocks:
-        t0, t1 = ev(), ev()
-        t0.record()
-        for _ in range(K):
-            step(audio, record=True)
-        t1.record()
-        barrier()
+    clocks.start()
+    t0, t1 = ev(), ev()
+    t0.record()
+    for _ in range(K):
+        step(audio, record=True)
+    t1.record()
+    barrier()
+    clocks.stop()
     launches = _lib.total_launches() - launches0
     ms_total = max_over_ranks(t0.elapsed_time(t1))
     value = world * B * K / (ms_total * 1e-3)
@@ -336,7 +401,8 @@ def b200_arm(args):
         "config": {"workload": "extract_code cfg2: 4 s/16 kHz notes -> mel-IF -> VQ-VAE-2 "
                                "encode (bottom 16 / top 2, K=512, D=64) -> top+bottom codes",
                    "notes_per_step_per_gpu": B, "sharding": "notes sharded per rank, no collective",
-                   "conv_encoder": "torch/cuDNN fp32 (TF32 convs as torch defaults), random init",
+                   "conv_encoder": "torch/cuDNN fp32 (TF32 convs as torch defaults), random init, "
+                                   + ("channels_last storage" if cl else "NCHW storage"),
                    "l2": f"inputs exceed L2 (126 MB): {B * 0.256:.0f} MB audio + "
                          f"{B * 1.0486:.0f} MB spectrogram per step",
                    "assign_algo": args.assign_algo},
@@ -384,13 +450,15 @@ def b200_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=296,
                     help="notes per step per GPU (default 2 x 148 SMs: whole waves of note CTAs)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--assign-algo", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--channels-last", type=int, default=1,
+                    help="1: spectrogram + conv stack in torch.channels_last storage (default)")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

@@ -182,13 +182,17 @@ typedef struct isi_melif_params {
   const int32_t* mel_start; /* [n_fft/2] first linear bin of each mel band      */
   const int32_t* mel_count; /* [n_fft/2] band length (0..mel_width)             */
   const float* mel_weight;  /* [n_fft/2, mel_width] band weights                */
+  int32_t channels_last;    /* 0: out is [B,2,F,T'] planes (the reference layout);   */
+                            /* 1: the same logical tensor in torch channels_last     */
+                            /*    storage [B,F,T',2] (what the cuDNN convs consume)  */
 } isi_melif_params;
 
 /*
  * audio [n_notes, n_samples] FP32 (contiguous) -> out [n_notes, 2, n_fft/2,
  * n_frames] FP32: channel 0 log-magnitude, channel 1 instantaneous frequency,
  * frequency-major / time-contiguous like the reference tensors
- * (Inference.ipynb:71, flask_server.py:891-896).
+ * (Inference.ipynb:71, flask_server.py:891-896), or channel-interleaved storage of the
+ * same logical tensor when h_params->channels_last is set.
  */
 ISI_API int isi_melif_forward(const float* audio, int64_t n_notes, int64_t n_samples,
                       const isi_melif_params* h_params, float* out,

@@ -33,7 +33,7 @@ class MelifParams(ctypes.Structure):
                 ("mel_width", ctypes.c_int32), ("safelog_eps", ctypes.c_float),
                 ("window", ctypes.c_void_p), ("twiddle", ctypes.c_void_p),
                 ("mel_start", ctypes.c_void_p), ("mel_count", ctypes.c_void_p),
-                ("mel_weight", ctypes.c_void_p)]
+                ("mel_weight", ctypes.c_void_p), ("channels_last", ctypes.c_int32)]
 
 
 EXPORTS = {

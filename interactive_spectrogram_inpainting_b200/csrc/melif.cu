@@ -182,17 +182,20 @@ melif_kernel(const float* __restrict__ audio, int64_t n_samples, isi_melif_param
     if (bulk_ok) { mbar_wait(bar, stage_phase & 1); ++stage_phase; }
     __syncthreads();       // zero-filled pads / synchronous fills come from other threads;
                            // also fences the previous batch's emit (zC) from this pass 1 (zA)
+    // The three FFT passes of a frame only involve the 64 threads of its group: they meet
+    // on a named barrier of their own instead of stalling the whole CTA.
+    const uint32_t group_bar = 1 + (tid >> 6);
     for (int fb = tid / 64; fb < nf; fb += kGroups)
       fft_pass1<P>(tid & 63, stage + fb * p.hop, frames_aligned8, win, twm, zA + fb * P::kPitchA);
-    __syncthreads();
-    if (next_nf > 0 && bulk_ok) stage_span(next_f0, next_nf);          // the stage is free again
+    asm volatile("bar.sync %0, 64;" ::"r"(group_bar) : "memory");
     for (int fb = tid / 64; fb < nf; fb += kGroups) fft_pass2<P>(tid & 63, twm, zA + fb * P::kPitchA);
-    __syncthreads();
+    asm volatile("bar.sync %0, 64;" ::"r"(group_bar) : "memory");
     for (int fb = tid / 64; fb < nf; fb += kGroups)
       fft_pass3<P>(tid & 63, zA + fb * P::kPitchA, zB + fb * P::kPitchB);
     __syncthreads();
+    if (next_nf > 0 && bulk_ok) stage_span(next_f0, next_nf);   // every group is done with the stage
     // polar: frames in order, previous spectrum value in registers; zB -> zC (= zA storage)
-#pragma unroll 1
+#pragma unroll 2
     for (int fb = 0; fb < nf; ++fb) {
 #pragma unroll
       for (int i = 0; i < IPT; ++i)
@@ -210,6 +213,20 @@ melif_kernel(const float* __restrict__ audio, int64_t n_samples, isi_melif_param
           emit_mel<FB>(zC, row_bin[r], row_cnt[r], row_cnt_warp[r], row_w[r], f0 == 0, eps, v0, v1);
         else
           emit_linear<FB>(zC, row_bin[r], v0, v1);
+        if (p.channels_last) {
+          // [B, F, T', 2]: the FB time steps of both channels are one contiguous run
+          float* d = out + (((int64_t)note_idx * M + row) * p.n_frames + f0) * 2;
+          if (nf == FB && (FB % 2 == 0) && (p.n_frames % 2 == 0)) {
+#pragma unroll
+            for (int q = 0; q < FB / 2; ++q)
+              reinterpret_cast<float4*>(d)[q] = make_float4(v0[2 * q], v1[2 * q], v0[2 * q + 1], v1[2 * q + 1]);
+          } else {
+#pragma unroll
+            for (int fb = 0; fb < FB; ++fb)
+              if (fb < nf) { d[2 * fb] = v0[fb]; d[2 * fb + 1] = v1[fb]; }
+          }
+          continue;
+        }
         float* d0 = out0 + (int64_t)row * p.n_frames + f0;
         float* d1 = out1 + (int64_t)row * p.n_frames + f0;
         if (nf == FB && (FB % 4 == 0) && (p.n_frames % 4 == 0)) {

@@ -91,7 +91,8 @@ class SpectrogramsHelper(nn.Module):
     def __init__(self, fs_hz: int = 16000, n_fft: int = 2048, hop_length: int = 512,
                  window_length: int = 2048, safelog_eps: float = 1e-6, *,
                  pad_left: Optional[int] = None, n_frames: Optional[int] = None,
-                 drop_bin: str = "dc", window_periodic: bool = True):
+                 drop_bin: str = "dc", window_periodic: bool = True,
+                 channels_last: bool = False):
         super().__init__()
         if n_fft not in SUPPORTED_N_FFT:
             raise ValueError(f"n_fft must be one of {SUPPORTED_N_FFT}, got {n_fft}")
@@ -107,6 +108,9 @@ class SpectrogramsHelper(nn.Module):
         self.pad_left = n_fft - hop_length if pad_left is None else pad_left
         self.fixed_n_frames = n_frames
         self.drop_bin = drop_bin
+        # True: to_spectrogram returns the same [B,2,F,T'] tensor in torch.channels_last
+        # storage, which is what the cuDNN conv encoder wants (no layout-conversion kernels)
+        self.channels_last = channels_last
 
         w = torch.hann_window(window_length, periodic=window_periodic, dtype=torch.float64)
         if window_length < n_fft:
@@ -135,6 +139,7 @@ class SpectrogramsHelper(nn.Module):
         p.safelog_eps = self.safelog_eps
         p.window, p.twiddle = self.window.data_ptr(), self.twiddle.data_ptr()
         p.mel_start = p.mel_count = p.mel_weight = None
+        p.channels_last = 1 if self.channels_last else 0
         return p
 
     def to_spectrogram(self, audio: torch.Tensor) -> torch.Tensor:
@@ -155,7 +160,9 @@ class SpectrogramsHelper(nn.Module):
         frames = self.num_frames(n_samples)
         if self.hop_length * (frames - 1) + self.n_fft - n_samples - self.pad_left < 0:
             raise ValueError("n_frames too small for the audio length")
-        out = torch.empty(n_notes, 2, self.n_freq, frames, dtype=torch.float32, device=a.device)
+        out = torch.empty(n_notes, 2, self.n_freq, frames, dtype=torch.float32, device=a.device,
+                          memory_format=(torch.channels_last if self.channels_last
+                                         else torch.contiguous_format))
         params = self._params(frames)
         _lib.invoke("isi_melif_forward", a.data_ptr(), n_notes, n_samples, params,
                                                  out.data_ptr(), _lib.stream_ptr(a.device))

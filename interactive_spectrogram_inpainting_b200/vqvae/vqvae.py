@@ -163,9 +163,22 @@ class VQVAE(nn.Module):
                 perplexity_t, perplexity_b)
 
     def encode_codes(self, input: torch.Tensor):
-        """Top and bottom code maps only -- what ``extract_code.py`` stores."""
-        out = self.encode(input)
-        return out[3], out[4]
+        """Top and bottom code maps only -- what ``extract_code.py`` stores.  Same codes as
+        ``encode``; the bottom quantiser only searches (its lookup, commitment term and
+        perplexity feed nothing here)."""
+        if self.training or not hasattr(self.quantize_b, "assign"):
+            out = self.encode(input)
+            return out[3], out[4]
+        enc_b = self.enc_b(input)
+        enc_t = self.enc_t(enc_b)
+        quant_t, _, id_t, _ = self.quantize_t(self.quantize_conv_t(enc_t).permute(0, 2, 3, 1))
+        dec_t = self.dec_t(quant_t.permute(0, 3, 1, 2))
+        if self.adapt_quantized_durations:
+            n = min(dec_t.shape[-1], enc_b.shape[-1])
+            dec_t, enc_b = dec_t[..., :n], enc_b[..., :n]
+        id_b = self.quantize_b.assign(
+            self.quantize_conv_b(torch.cat([dec_t, enc_b], 1)).permute(0, 2, 3, 1))
+        return id_t, id_b
 
     # -- vqvae.py:280-295 --
     def decode(self, quant_t: torch.Tensor, quant_b: torch.Tensor):

@@ -63,3 +63,23 @@ def test_full_batch_size_property():
     spec = helper.to_spectrogram(audio)
     for i in (0, 100, 255):
         assert torch.equal(helper.to_spectrogram(audio[i:i + 1])[0], spec[i])
+
+
+def test_channels_last_storage_holds_the_same_tensor():
+    audio = synthetic.synthetic_notes(3).to(DEV)
+    plain = MelSpectrogramsHelper().to(DEV).to_spectrogram(audio)
+    nhwc = MelSpectrogramsHelper(channels_last=True).to(DEV).to_spectrogram(audio)
+    assert nhwc.shape == plain.shape and nhwc.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(nhwc, plain)
+    lin = SpectrogramsHelper(channels_last=True).to(DEV).to_spectrogram(audio[:, :9001])
+    assert torch.equal(lin, SpectrogramsHelper().to(DEV).to_spectrogram(audio[:, :9001]))
+
+
+def test_small_batches_are_split_into_frame_segments_identically():
+    """B=1 runs as several frame segments per note (look-back transform at each seam);
+    B=300 runs whole notes: the two must agree bit for bit."""
+    helper = MelSpectrogramsHelper().to(DEV)
+    audio = synthetic.synthetic_notes(300).to(DEV)
+    whole = helper.to_spectrogram(audio)
+    for i in (0, 7, 299):
+        assert torch.equal(helper.to_spectrogram(audio[i:i + 1])[0], whole[i])
