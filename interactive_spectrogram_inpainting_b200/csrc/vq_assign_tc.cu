@@ -8,11 +8,12 @@
 // Persistent CTAs, one per SM, each owning tiles of 256 rows (two M=128 accumulators).
 // Warp roles:
 //   warps 0-3  epilogue   tcgen05.ld the 128 x 64 accumulators, add |e|^2, running argmin
-//   warps 4-7  x loader   coalesced global reads of the row tile in the caller's layout,
-//                         hi/lo split, st.shared into the SWIZZLE_128B K-major UMMA layout
-//   warp  8    B producer streams pre-split, pre-swizzled 64-code operand tiles of the
+//   warps 4-11 x loader   coalesced global reads of the NEXT row tile into registers (in the
+//                         caller's layout) while the MMAs run; then hi/lo split and
+//                         st.shared into the SWIZZLE_128B K-major UMMA layout
+//   warp  12   B producer streams pre-split, pre-swizzled 64-code operand tiles of the
 //                         codebook through a 2-stage ring with cp.async.bulk + mbarrier
-//   warp  9    MMA issuer one elected lane issues the tcgen05.mma chain; owns TMEM
+//   warp  13   MMA issuer one elected lane issues the tcgen05.mma chain; owns TMEM
 // The accumulators live in TMEM (2 stages x 2 row tiles x 64 columns), so the argmin of
 // tile j overlaps the MMAs of tile j+1.
 #include "common.cuh"
@@ -34,7 +35,13 @@ constexpr int kBStageBytes = 2 * kBBytesPart;                   // 32 KB
 constexpr int kBStages = 2;
 constexpr int kAccStages = 2;
 constexpr int kTmemCols = kAccStages * kMmaPerTile * kTileCodes;  // 256
-constexpr int kThreads = 320;
+constexpr int kFirstLoaderWarp = 4;                  // warps 0-3: epilogue (TMEM lane quarters)
+constexpr int kLoaderWarps = 8;
+constexpr int kLoaderThreads = kLoaderWarps * 32;                                  // 256
+constexpr int kChunksPerThread = kTileRows * (kDim / 4) / kLoaderThreads;          // 16
+constexpr int kProducerWarp = kFirstLoaderWarp + kLoaderWarps;                     // 12
+constexpr int kMmaWarp = kProducerWarp + 1;                                        // 13
+constexpr int kThreads = (kMmaWarp + 1) * 32;                                      // 448
 constexpr int kMaxCodes = 4096;                      // |e|^2 table held in shared memory
 
 // instruction descriptor: D=F32, A=B=TF32, both K-major, N=64, M=128
@@ -103,21 +110,19 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                : "memory");
 }
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
-  uint32_t r[32];
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, float* v) {
+  // 64 consecutive accumulator columns of this thread's TMEM lane; the wait sits in the
+  // same asm statement so no use of the registers can be scheduled ahead of it
+  uint32_t r[64];
   asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
-        "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]),
-        "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]),
-        "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]), "=r"(r[32]), "=r"(r[33]), "=r"(r[34]), "=r"(r[35]), "=r"(r[36]), "=r"(r[37]), "=r"(r[38]), "=r"(r[39]), "=r"(r[40]), "=r"(r[41]), "=r"(r[42]), "=r"(r[43]), "=r"(r[44]), "=r"(r[45]), "=r"(r[46]), "=r"(r[47]), "=r"(r[48]), "=r"(r[49]), "=r"(r[50]), "=r"(r[51]), "=r"(r[52]), "=r"(r[53]), "=r"(r[54]), "=r"(r[55]), "=r"(r[56]), "=r"(r[57]), "=r"(r[58]), "=r"(r[59]), "=r"(r[60]), "=r"(r[61]), "=r"(r[62]), "=r"(r[63])
+      : "r"(taddr)
+      : "memory");
 #pragma unroll
-  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+  for (int i = 0; i < 64; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 // byte offset of element (row r, feature d) inside one (rows x 64) K-major SW128 operand
@@ -182,11 +187,11 @@ vq_assign_tc_kernel(const float* __restrict__ x, isi_rows_layout lay, int64_t n_
       mbar_init(bar_acc_full + 8 * i, 1);
       mbar_init(bar_acc_empty + 8 * i, 128);
     }
-    mbar_init(bar_a_full, 128);
+    mbar_init(bar_a_full, kLoaderThreads);
     mbar_init(bar_a_empty, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 9) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)),
                  "n"(kTmemCols));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -197,16 +202,22 @@ vq_assign_tc_kernel(const float* __restrict__ x, isi_rows_layout lay, int64_t n_
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp >= 4 && warp < 8) {
+  if (warp >= kFirstLoaderWarp && warp < kFirstLoaderWarp + kLoaderWarps) {
     // ===================== x loader / splitter =====================
-    const int t = threadIdx.x - 128;                      // 0..127
+    // Each thread owns kChunksPerThread 16-byte chunks (4 consecutive features of one row).
+    // The chunks of the NEXT tile are fetched into registers while the tensor cores still
+    // work on the current one; when the MMAs release the operand buffer only the hi/lo
+    // split and the swizzled st.shared remain on the critical path.
+    const int t = threadIdx.x - kFirstLoaderWarp * 32;    // 0 .. kLoaderThreads-1
     const bool rows_contiguous = (lay.row_stride == 1 && lay.col_stride != 1);
-    uint32_t it = 0;
-    for (int64_t tile = blockIdx.x; tile < n_row_tiles; tile += gridDim.x, ++it) {
-      mbar_wait(bar_a_empty, (it & 1) ^ 1);               // MMAs of the previous tile are done
+    const bool vec_ok = (lay.col_stride == 1) && ((lay.row_stride & 3) == 0) &&
+                        ((lay.batch_stride & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+    float4 buf[kChunksPerThread];
+    auto fetch = [&](int64_t tile) {
       const int64_t row0 = tile * kTileRows;
-      // 256 rows x 16 chunks (float4 of 4 consecutive features)
-      for (int e = t; e < kTileRows * (kDim / 4); e += 128) {
+#pragma unroll
+      for (int i = 0; i < kChunksPerThread; ++i) {
+        const int e = t + i * kLoaderThreads;
         int r, c;
         if (rows_contiguous) { r = e % kTileRows; c = e / kTileRows; }
         else                 { c = e % (kDim / 4); r = e / (kDim / 4); }
@@ -214,16 +225,30 @@ vq_assign_tc_kernel(const float* __restrict__ x, isi_rows_layout lay, int64_t n_
         const int64_t row = row0 + r;
         if (row < n_rows) {
           const float* src = x + row_offset(lay, row) + (int64_t)(4 * c) * lay.col_stride;
-          if (lay.col_stride == 1 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
-            v = *reinterpret_cast<const float4*>(src);
+          if (vec_ok) {
+            v = __ldg(reinterpret_cast<const float4*>(src));
           } else {
-            v.x = src[0]; v.y = src[lay.col_stride]; v.z = src[2 * lay.col_stride];
-            v.w = src[3 * lay.col_stride];
+            v.x = __ldg(src); v.y = __ldg(src + lay.col_stride); v.z = __ldg(src + 2 * lay.col_stride);
+            v.w = __ldg(src + 3 * lay.col_stride);
           }
         }
-        float4 hi = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
-        float4 lo = make_float4(to_tf32(v.x - hi.x), to_tf32(v.y - hi.y), to_tf32(v.z - hi.z),
-                                to_tf32(v.w - hi.w));
+        buf[i] = v;
+      }
+    };
+    uint32_t it = 0;
+    if ((int64_t)blockIdx.x < n_row_tiles) fetch(blockIdx.x);
+    for (int64_t tile = blockIdx.x; tile < n_row_tiles; tile += gridDim.x, ++it) {
+      mbar_wait(bar_a_empty, (it & 1) ^ 1);               // MMAs of the previous tile are done
+#pragma unroll
+      for (int i = 0; i < kChunksPerThread; ++i) {
+        const int e = t + i * kLoaderThreads;
+        int r, c;
+        if (rows_contiguous) { r = e % kTileRows; c = e / kTileRows; }
+        else                 { c = e % (kDim / 4); r = e / (kDim / 4); }
+        const float4 v = buf[i];
+        const float4 hi = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+        const float4 lo = make_float4(to_tf32(v.x - hi.x), to_tf32(v.y - hi.y), to_tf32(v.z - hi.z),
+                                      to_tf32(v.w - hi.w));
         const int m = r >> 7, rr = r & 127;
         const uint32_t off = Smem::a + (uint32_t)(m * 2) * kABytesPart + operand_offset(kRowsPerMma, rr, 4 * c);
         *reinterpret_cast<float4*>(smem + off) = hi;
@@ -231,8 +256,9 @@ vq_assign_tc_kernel(const float* __restrict__ x, isi_rows_layout lay, int64_t n_
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy
       mbar_arrive(bar_a_full);
+      if (tile + gridDim.x < n_row_tiles) fetch(tile + gridDim.x);
     }
-  } else if (warp == 8) {
+  } else if (warp == kProducerWarp) {
     // ===================== B producer =====================
     if (lane == 0) {
       uint32_t step = 0;
@@ -246,7 +272,7 @@ vq_assign_tc_kernel(const float* __restrict__ x, isi_rows_layout lay, int64_t n_
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       uint32_t step = 0, it = 0;
@@ -303,19 +329,16 @@ vq_assign_tc_kernel(const float* __restrict__ x, isi_rows_layout lay, int64_t n_
         const float* e2t = e2s + j * kTileCodes;
 #pragma unroll
         for (int m = 0; m < kMmaPerTile; ++m) {
+          float v[kTileCodes];
+          tmem_ld64(tmem_base + lane_field + (uint32_t)((s * kMmaPerTile + m) * kTileCodes), v);
 #pragma unroll
-          for (int half = 0; half < 2; ++half) {
-            float v[32];
-            tmem_ld32(tmem_base + lane_field + (uint32_t)((s * kMmaPerTile + m) * kTileCodes + half * 32), v);
+          for (int c = 0; c < kTileCodes; c += 4) {
+            const float4 ee = *reinterpret_cast<const float4*>(e2t + c);
+            const float sc[4] = {v[c] + ee.x, v[c + 1] + ee.y, v[c + 2] + ee.z, v[c + 3] + ee.w};
 #pragma unroll
-            for (int c = 0; c < 32; c += 4) {
-              const float4 ee = *reinterpret_cast<const float4*>(e2t + half * 32 + c);
-              const float sc[4] = {v[c] + ee.x, v[c + 1] + ee.y, v[c + 2] + ee.z, v[c + 3] + ee.w};
-#pragma unroll
-              for (int q = 0; q < 4; ++q) {
-                // codes are visited in rising order: strict '<' keeps the lowest index on ties
-                if (sc[q] < best_s[m]) { best_s[m] = sc[q]; best_i[m] = j * kTileCodes + half * 32 + c + q; }
-              }
+            for (int q = 0; q < 4; ++q) {
+              // codes are visited in rising order: strict '<' keeps the lowest index on ties
+              if (sc[q] < best_s[m]) { best_s[m] = sc[q]; best_i[m] = j * kTileCodes + c + q; }
             }
           }
         }
@@ -336,7 +359,7 @@ vq_assign_tc_kernel(const float* __restrict__ x, isi_rows_layout lay, int64_t n_
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 9) {
+  if (warp == kMmaWarp) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
   }
 }

@@ -62,7 +62,7 @@ def check_against_oracle(got, audio, cfg, max_excluded=0.5):
       * log-magnitude: <= 1e-4 x max-abs at >= 99.9 % of positions, never worse than 0.05;
       * IF on well-conditioned positions (FP64 mask: bin within 80 dB of its frame peak,
         step not within 1e-3 rad of the wrap; 60-90 % of positions on the synthetic notes): <= 1e-4 x max-abs
-        at >= 99.97 %, never worse than 5e-4;
+        at >= 99.95 %, never worse than 5e-4;
       * IF everywhere: <= 1e-3 at >= 99.97 %, wrap flips (error ~2) at <= 5e-5.
     Returns the excluded (ill-conditioned) fraction."""
     want = fo.to_spectrogram(audio.double(), cfg)
@@ -74,7 +74,7 @@ def check_against_oracle(got, audio, cfg, max_excluded=0.5):
     err1 = (got[:, 1].double() - want[:, 1]).abs()
     tol1 = 1e-4 * want[:, 1].abs().max().clamp_min(1.0)
     assert err1[stable].max() <= 5 * tol1, err1[stable].max()
-    assert (err1[stable] > tol1).double().mean() < 3e-4
+    assert (err1[stable] > tol1).double().mean() < 5e-4
     everywhere = err1.clone()
     if not cfg.use_mel_scale:
         # the purely real bin (DC or Nyquist) has phase exactly 0 or pi: every step sits on
