@@ -258,6 +258,7 @@ def b200_arm(args):
 
     B, K, W = args.batch, args.steps, max(args.warmup, 3)
     torch.manual_seed(0)
+    torch.backends.cudnn.benchmark = bool(args.cudnn_benchmark)   # conv algorithm autotuning
     cl = bool(args.channels_last)
     helper = MelSpectrogramsHelper(channels_last=cl).to(dev)
     model = VQVAE(**MODEL_KW).to(dev).eval()
@@ -271,18 +272,9 @@ def b200_arm(args):
                   torch.empty(B, 64, 8, dtype=torch.int64).pin_memory())
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
-    melif_events, assign_events = [], []
-
-    def step(src, record=False):
+    def step(src):
         with torch.no_grad():
-            if record:
-                a, b = ev(), ev()
-                a.record()
-            spec = helper.to_spectrogram(src)
-            if record:
-                b.record()
-                melif_events.append((a, b))
-            return model.encode_codes(spec)
+            return model.encode_codes(helper.to_spectrogram(src))
 
     def max_over_ranks(ms):
         if world == 1:
@@ -299,31 +291,39 @@ def b200_arm(args):
     clocks.start()
     t0, t1 = ev(), ev()
     t0.record()
+    _lib.event_log = []            # every C-ABI call of the timed region gets CUDA events
     for _ in range(K):
-        step(audio, record=True)
+        step(audio)
     t1.record()
     barrier()
     clocks.stop()
+    step_events, _lib.event_log = _lib.event_log, None
     launches = _lib.total_launches() - launches0
     ms_total = max_over_ranks(t0.elapsed_time(t1))
     value = world * B * K / (ms_total * 1e-3)
-    melif_ms = statistics.mean(a.elapsed_time(b) for a, b in melif_events)
+    per_call = {}
+    for name, a, b in step_events:
+        per_call.setdefault(name, []).append(a.elapsed_time(b))
+    melif_ms = statistics.mean(per_call["isi_melif_forward"])
+    kernel_ms_per_step = {k: sum(v) / K for k, v in per_call.items()}
 
     # ---- e2e: pinned host audio in, code maps out, copies inside the timed region ----
-    def e2e_step():
-        dev_audio = host_audio.to(dev, non_blocking=True)
-        id_t, id_b = step(dev_audio)
-        host_codes[0].copy_(id_t, non_blocking=True)
-        host_codes[1].copy_(id_b, non_blocking=True)
-    for _ in range(W):
-        e2e_step()
+    # Through the public extraction API (extract.py): the H2D copy of batch i+1 overlaps the
+    # compute of batch i on a side stream, code maps come back per batch, rows are assembled.
+    from interactive_spectrogram_inpainting_b200 import extract
+    names = [f"note_{i:07d}" for i in range(B)]
+
+    def e2e_run(n_batches):
+        loader = extract.SpectrogramBatches([(host_audio, names)] * n_batches, helper, dev)
+        return extract.extract_codes(loader, model)
+    e2e_run(W)
     barrier()
     t0, t1 = ev(), ev()
     t0.record()
-    for _ in range(K):
-        e2e_step()
+    rows = e2e_run(K)
     t1.record()
     barrier()
+    assert len(rows) == B * K and rows[0].top.shape == (32, 4) and rows[0].bottom.shape == (64, 8)
     e2e_ms = max_over_ranks(t0.elapsed_time(t1))
     e2e_value = world * B * K / (e2e_ms * 1e-3)
 
@@ -367,6 +367,24 @@ def b200_arm(args):
         torch.cuda.synchronize()
         assign_ms = t0.elapsed_time(t1) / 10
 
+        # lookup + commitment + EMA statistics, and the EMA update, on the same rows (HBM-bound)
+        qmod.train()
+        qmod.sync_ema_stats = False
+        for _ in range(2):
+            qmod(qx)
+        torch.cuda.synchronize()
+        _lib.event_log = []
+        for _ in range(5):
+            qmod(qx)
+        torch.cuda.synchronize()
+        train_events, _lib.event_log = _lib.event_log, None
+        tms = {}
+        for name, a, b in train_events:
+            tms.setdefault(name, []).append(a.elapsed_time(b))
+        gather_ms = statistics.mean(tms["isi_vq_gather_stats"])
+        ema_ms = statistics.mean(tms["isi_vq_ema_update"])
+        gather_bytes = qn * (4 * DIM * 2 + 8) + 4 * N_EMBED * (DIM + 1)
+
         # TF32 dense peak of this box, measured like MEASURED_PEAKS.json measured BF16
         torch.backends.cuda.matmul.allow_tf32 = True
         ma = torch.randn(8192, 8192, device=dev)
@@ -409,20 +427,32 @@ def b200_arm(args):
         "e2e": {"value": e2e_value, "unit": "notes/s",
                 "h2d_bytes_per_step": host_audio.numel() * 4,
                 "d2h_bytes_per_step": (host_codes[0].numel() + host_codes[1].numel()) * 8,
+                "api": "extract.extract_codes(extract.SpectrogramBatches(pinned host audio))",
                 "ms_per_step": e2e_ms / K},
         "gpu_launches": launches,
         "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"],
                    "reasons": clk["reasons"], "samples": clk["samples"]},
         "roofline": {"kernel": "melif_kernel<2048,4,256>", "bound": "hbm", "achieved": melif_gbs,
                      "peak": hbm_peak, "unit": "GB/s", "frac": melif_gbs / hbm_peak,
-                     "traffic": None, "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
+                     # dram__bytes_read+write of one launch from the committed ncu capture
+                     # (profiles/r01_melif_v4b_r01e_ncu_summary.csv: 76.2 + 259.6 MB at 296 notes,
+                     # channels_last output), scaled to this batch
+                     "traffic": (76.168704e6 + 259.628288e6) / 296 * B if cl else None,
+                     "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
                      "ms_per_launch": melif_ms, "algorithmic_bytes_per_launch": MELIF_BYTES_PER_NOTE * B},
         "rooflines_other": [
             {"kernel": f"vq_assign ({args.assign_algo})", "bound": "tensor",
              "achieved": assign_tflops, "peak": tf32_tflops / 3.0, "unit": "TFLOP/s",
              "frac": assign_tflops / (tf32_tflops / 3.0), "ms_per_launch": assign_ms,
              "rows": qn, "note": "2*N*K*D algorithmic FLOP over the 3xTF32 roofline = TF32 dense "
-                                 f"cuBLAS peak measured on this box ({tf32_tflops:.0f} TFLOP/s) / 3"}],
+                                 f"cuBLAS peak measured on this box ({tf32_tflops:.0f} TFLOP/s) / 3"},
+            {"kernel": "vq_gather_stats (training: lookup + (q-x)^2 + EMA sums)", "bound": "hbm",
+             "achieved": gather_bytes / (gather_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+             "frac": gather_bytes / (gather_ms * 1e-3) / 1e9 / hbm_peak, "ms_per_launch": gather_ms,
+             "rows": qn, "note": "N*(4D read + 4D write + 8) + 4K(D+1) algorithmic bytes"},
+            {"kernel": "vq_ema_update (2 kernels)", "bound": "latency", "ms_per_launch": ema_ms,
+             "note": "K*D = 32768 elements; launch-latency bound"}],
+        "kernel_ms_per_step": kernel_ms_per_step,
         "hot_path_only": {"value": world * B * K / (hot_ms * 1e-3), "unit": "notes/s",
                           "ms_per_step": hot_ms / K,
                           "what": "front end + top/bottom quantiser kernels, conv features precomputed"},
@@ -457,6 +487,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--assign-algo", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cudnn-benchmark", type=int, default=1)
     ap.add_argument("--channels-last", type=int, default=1,
                     help="1: spectrogram + conv stack in torch.channels_last storage (default)")
     args = ap.parse_args()

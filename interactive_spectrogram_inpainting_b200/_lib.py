@@ -156,9 +156,20 @@ KERNELS_PER_CALL = {
 launch_counts = {name: 0 for name in KERNELS_PER_CALL}
 
 
+event_log = None     # set to a list to have every call bracketed by CUDA events (bench.py)
+
+
 def invoke(name: str, *args) -> None:
     """Call entry point ``name``, raise on a non-zero status, count its kernel launches."""
-    check(getattr(load(), name)(*args), name)
+    log = event_log
+    if log is not None:
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        check(getattr(load(), name)(*args), name)
+        stop.record()
+        log.append((name, start, stop))
+    else:
+        check(getattr(load(), name)(*args), name)
     launch_counts[name] += KERNELS_PER_CALL[name]
 
 

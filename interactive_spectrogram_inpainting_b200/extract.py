@@ -27,13 +27,37 @@ class SpectrogramBatches:
     ``source`` yields ``(audio [b, T] float tensor on any device, names)``."""
 
     def __init__(self, source: Iterable[Tuple[torch.Tensor, Sequence[str]]], spectrograms_helper,
-                 device: torch.device, transform: Optional[Callable] = None):
+                 device: torch.device, transform: Optional[Callable] = None, prefetch: bool = True):
         self.source, self.helper, self.device, self.transform = source, spectrograms_helper, device, transform
+        self.prefetch = prefetch
+
+    def _upload(self, item, stream):
+        audio, names = item
+        with torch.cuda.stream(stream):
+            dev_audio = audio.to(self.device, non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(stream)
+        return dev_audio, names, ready
 
     def __iter__(self) -> Iterator[Tuple[torch.Tensor, Sequence[str]]]:
-        for audio, names in self.source:
-            audio = audio.to(self.device, non_blocking=True)
-            spec = self.helper.to_spectrogram(audio)
+        """With ``prefetch`` the host->device copy of batch i+1 (pinned source memory) runs
+        on a side stream while batch i is transformed and encoded."""
+        main = torch.cuda.current_stream(self.device)
+        side = torch.cuda.Stream(self.device) if self.prefetch else main
+        it = iter(self.source)
+        pending = None
+        for item in it:
+            pending = self._upload(item, side)
+            break
+        while pending is not None:
+            dev_audio, names, ready = pending
+            pending = None
+            for item in it:
+                pending = self._upload(item, side)
+                break
+            main.wait_event(ready)
+            dev_audio.record_stream(main)
+            spec = self.helper.to_spectrogram(dev_audio)
             if self.transform is not None:
                 spec = self.transform(spec)
             yield spec, names
