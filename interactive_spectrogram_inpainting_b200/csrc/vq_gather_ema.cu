@@ -154,6 +154,79 @@ vq_gather_stats_kernel(const float* __restrict__ x, isi_rows_layout xl,
   }
 }
 
+// ---------------------------------------------------------------------------
+// Row-major fast path (the layout of channels_last activations and of [N, D] tensors):
+// LPR = D/4 lanes hold one row as float4s, so every global access is a 16-byte vector and a
+// warp moves 512 B per instruction.  Each lane group owns kRowsPerGroup CONSECUTIVE rows and
+// keeps the running sum of the current run of equal codes in registers: one vector reduction
+// (red.global.add.v4.f32) per run reaches memory, not one per row.  Neighbouring
+// spectrogram positions often share a code, and a collapsed codebook (all rows -> one code)
+// degrades to one reduction per group instead of serialising a million atomics on one line.
+// ---------------------------------------------------------------------------
+template <int LPR>   // lanes per row = D / 4
+__global__ void __launch_bounds__(256)
+vq_gather_rowmajor_kernel(const float* __restrict__ x, int64_t x_row_stride,
+                          const int64_t* __restrict__ index, int64_t n_rows, int n_embed,
+                          const float* __restrict__ et, float* __restrict__ out_q,
+                          int64_t q_row_stride, float* __restrict__ stats, int counts_only,
+                          double* __restrict__ partials, int32_t* __restrict__ status_flag) {
+  constexpr int D = LPR * 4;
+  constexpr int kGroups = 256 / LPR;
+  constexpr int kRows = kGatherRows / kGroups;          // consecutive rows per lane group
+  static_assert(kGatherRows % kGroups == 0, "tile must split evenly over the lane groups");
+  __shared__ double warp_part[8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int group = tid / LPR, gl = tid % LPR;          // lane group, lane within the group
+  const int64_t row0 = (int64_t)blockIdx.x * kGatherRows + (int64_t)group * kRows;
+
+  float4 run = make_float4(0.f, 0.f, 0.f, 0.f);
+  int run_code = -1, run_len = 0;
+  float sq = 0.f;
+  auto flush = [&]() {
+    if (run_code >= 0 && stats) {
+      if (gl == 0) atomicAdd(&stats[run_code], (float)run_len);
+      if (!counts_only)
+        atomicAdd(reinterpret_cast<float4*>(stats + n_embed + (int64_t)run_code * D) + gl, run);
+    }
+  };
+#pragma unroll 4
+  for (int i = 0; i < kRows; ++i) {
+    const int64_t row = row0 + i;
+    if (row >= n_rows) break;
+    const int64_t v = __ldg(index + row);
+    const bool ok = (v >= 0 && v < n_embed);
+    if (!ok && gl == 0 && status_flag) atomicExch(status_flag, 1);
+    const int c = ok ? (int)v : -1;
+    float4 q = ok ? __ldg(reinterpret_cast<const float4*>(et + (int64_t)c * D) + gl)
+                  : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (x) {
+      const float4 xv = __ldg(reinterpret_cast<const float4*>(x + row * x_row_stride) + gl);
+      const float4 t = make_float4(q.x - xv.x, q.y - xv.y, q.z - xv.z, q.w - xv.w);
+      sq = fmaf(t.x, t.x, sq); sq = fmaf(t.y, t.y, sq); sq = fmaf(t.z, t.z, sq); sq = fmaf(t.w, t.w, sq);
+      q = make_float4(xv.x + t.x, xv.y + t.y, xv.z + t.z, xv.w + t.w);   // bottleneck.py:95
+      if (stats && !counts_only) {
+        if (c != run_code) { flush(); run = make_float4(0.f, 0.f, 0.f, 0.f); run_code = c; run_len = 0; }
+        run.x += xv.x; run.y += xv.y; run.z += xv.z; run.w += xv.w;
+        ++run_len;
+      }
+    }
+    if (stats && (counts_only || !x)) {
+      if (c != run_code) { flush(); run_code = c; run_len = 0; }
+      ++run_len;
+    }
+    if (out_q) reinterpret_cast<float4*>(out_q + row * q_row_stride)[gl] = q;
+  }
+  flush();
+  sq = warp_sum(sq);
+  if (lane == 0) warp_part[warp] = (double)sq;
+  __syncthreads();
+  if (tid == 0) {
+    double s = 0.0;
+    for (int w = 0; w < 8; ++w) s += warp_part[w];
+    partials[blockIdx.x] = s;
+  }
+}
+
 // diff = sum(partials) / (N*D) ; perplexity from the usage histogram
 __global__ void __launch_bounds__(256)
 vq_finish_kernel(const double* __restrict__ partials, int64_t n_partials, int64_t n_rows, int dim,
@@ -288,6 +361,30 @@ int launch_gather_stats(const float* x, const isi_rows_layout& xl, const int64_t
                         int32_t* status_flag, cudaStream_t stream) {
   int64_t grid = (n_rows + kGatherRows - 1) / kGatherRows;
   if (grid > 0x7fffffff) return ISI_ERR_SHAPE;
+  double* partials = (double*)workspace;
+  // row-major fast path: uniform row stride, 16-byte aligned float4 rows on both sides
+  auto uniform = [&](const isi_rows_layout& l) {
+    return l.col_stride == 1 && (l.row_stride & 3) == 0 &&
+           (l.rows_per_batch >= n_rows || l.batch_stride == l.rows_per_batch * l.row_stride);
+  };
+  const bool fast = (dim == 16 || dim == 32 || dim == 64 || dim == 128) &&
+                    (!x || (uniform(xl) && ((uintptr_t)x & 15) == 0)) &&
+                    (!out_q || (uniform(ql) && ((uintptr_t)out_q & 15) == 0)) &&
+                    (!stats || counts_only || ((n_embed & 3) == 0 && ((uintptr_t)stats & 15) == 0));
+  if (fast) {
+#define ISI_GATHER_CASE(LPR)                                                                   \
+    case LPR * 4:                                                                              \
+      vq_gather_rowmajor_kernel<LPR><<<(unsigned)grid, 256, 0, stream>>>(                      \
+          x, xl.row_stride, index, n_rows, n_embed, p.et, out_q, ql.row_stride, stats,         \
+          counts_only, partials, status_flag);                                                 \
+      break;
+    switch (dim) {
+      ISI_GATHER_CASE(4) ISI_GATHER_CASE(8) ISI_GATHER_CASE(16) ISI_GATHER_CASE(32)
+    }
+#undef ISI_GATHER_CASE
+    ISI_LAUNCH_CHECK();
+    return ISI_OK;
+  }
   size_t smem = (size_t)kGatherRows * (dim + 1) * 4 + kGatherRows * 4;
   if (smem > 200 * 1024) return ISI_ERR_UNSUPPORTED;
   if (smem > 48 * 1024) {
@@ -295,7 +392,6 @@ int launch_gather_stats(const float* x, const isi_rows_layout& xl, const int64_t
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
   }
-  double* partials = (double*)workspace;
   vq_gather_stats_kernel<<<(unsigned)grid, kGatherThreads, smem, stream>>>(
       x, xl, index, n_rows, dim, n_embed, p.et, out_q, ql, stats, counts_only, partials,
       status_flag);

@@ -170,3 +170,40 @@ def test_full_size_properties_cfg2_batch():
     assert torch.equal(ind2, ind) and diff2.item() < 1e-12
     assert torch.bincount(ind.view(-1), minlength=n_embed).sum().item() == x.shape[0]
     assert 1.0 <= perp.item() <= n_embed
+
+
+@pytest.mark.parametrize("dim,n_embed", [(64, 512), (128, 256), (32, 100), (16, 64)])
+def test_row_major_and_nchw_layouts_agree_in_training(dim, n_embed):
+    """The same rows through the row-major fast path (contiguous [B,H,W,D]) and through the
+    tile kernel (permuted NCHW view): identical indices/outputs, EMA buffers within FP32
+    summation-order noise, and both within 1e-5 of the oracle."""
+    embed = synthetic.synthetic_codebook(dim, n_embed)
+    x = synthetic.synthetic_features(6 * 24 * 10, embed, 99).view(6, 24, 10, dim)
+    nhwc = x.to(DEV)
+    nchw_view = x.permute(0, 3, 1, 2).contiguous().to(DEV).permute(0, 2, 3, 1)
+    assert nhwc.is_contiguous() and not nchw_view.is_contiguous()
+    ma, mb = make(dim, n_embed, embed, "simt").train(), make(dim, n_embed, embed, "simt").train()
+    qa, da, ia, pa = ma(nhwc)
+    qb, db, ib, pb = mb(nchw_view)
+    assert torch.equal(ia, ib) and torch.equal(qa, qb)
+    assert abs(da.item() - db.item()) <= 1e-6 * abs(da.item()) and pa.item() == pb.item()
+    st = qo.CodebookState(embed.clone(), torch.zeros(n_embed), embed.clone())
+    qo.ema_update(st, x.reshape(-1, dim), ia.cpu().reshape(-1), 0.99, 1e-5)
+    for m in (ma, mb):
+        for got, want in ((m.cluster_size, st.cluster_size), (m.embed_avg, st.embed_avg),
+                          (m.embed, st.embed)):
+            assert (got.cpu() - want).abs().max() <= 1e-5 * want.abs().max()
+
+
+def test_collapsed_codebook_usage_is_still_exact():
+    """Every row picks the same code (the run-length aggregation's extreme case)."""
+    dim, n_embed = 64, 512
+    embed = synthetic.synthetic_codebook(dim, n_embed)
+    x = (embed[:, 7][None, :] + 1e-3 * torch.randn(20000, dim)).contiguous()
+    m = make(dim, n_embed, embed, "auto").train()
+    _, _, ind, perp = m(x.to(DEV))
+    assert (ind == 7).all() and abs(perp.item() - 1.0) < 1e-5
+    want_cs = torch.zeros(n_embed); want_cs[7] = 0.01 * 20000
+    assert torch.allclose(m.cluster_size.cpu(), want_cs, rtol=1e-6)
+    want_avg7 = 0.99 * embed[:, 7] + 0.01 * x.sum(0)
+    assert (m.embed_avg.cpu()[:, 7] - want_avg7).abs().max() <= 1e-4 * want_avg7.abs().max()
