@@ -227,6 +227,122 @@ vq_gather_rowmajor_kernel(const float* __restrict__ x, int64_t x_row_stride,
   }
 }
 
+// ---------------------------------------------------------------------------
+// Training statistics with CTA-private accumulators (row-major input, K*D*4 <= ~140 KB):
+// the segmented reduction proper.  Persistent CTAs each keep a full [K, D] accumulator in
+// shared memory; inside a CTA every code is OWNED by one warp (code % 16), so rows are
+// added with plain ld/add/st -- no atomics, no conflicts -- and runs of equal codes are
+// first summed in registers.  Global memory sees one vector reduction per (CTA, used code)
+// at the very end: 148 x 128 KB at most, instead of 256 B of atomics per row.
+// ---------------------------------------------------------------------------
+constexpr int kStatsThreads = 512;
+constexpr int kStatsWarps = kStatsThreads / 32;
+
+template <int D>
+__global__ void __launch_bounds__(kStatsThreads, 1)
+vq_gather_stats_smem_kernel(const float* __restrict__ x, int64_t x_row_stride,
+                            const int64_t* __restrict__ index, int64_t n_rows, int n_embed,
+                            const float* __restrict__ et, float* __restrict__ out_q,
+                            int64_t q_row_stride, float* __restrict__ stats,
+                            double* __restrict__ partials, int32_t* __restrict__ status_flag,
+                            int64_t n_tiles) {
+  constexpr int VPL = D / 32;                       // accumulator floats per lane
+  constexpr int C4 = D / 4;                         // float4 chunks per row
+  extern __shared__ __align__(16) float smem[];
+  float* acc = smem;                                // [K][D]
+  float* cnt = acc + (size_t)n_embed * D;           // [K]
+  float* xs = cnt + ((n_embed + 3) & ~3);           // [kGatherRows][D]
+  int* codes = reinterpret_cast<int*>(xs + kGatherRows * D);   // [kGatherRows]
+  __shared__ double warp_part[kStatsWarps];
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < n_embed * D + ((n_embed + 3) & ~3); i += kStatsThreads) smem[i] = 0.f;
+  __syncthreads();
+
+  float run[VPL];
+  int run_code = -1, run_len = 0;
+  auto flush_run = [&]() {
+    if (run_code >= 0) {
+      float* a = acc + (size_t)run_code * D + lane * VPL;
+#pragma unroll
+      for (int v = 0; v < VPL; ++v) a[v] += run[v];
+      if (lane == 0) cnt[run_code] += (float)run_len;
+    }
+  };
+
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int64_t row0 = tile * kGatherRows;
+    const int rows_here = (int)min((int64_t)kGatherRows, n_rows - row0);
+    if (tid < kGatherRows) {
+      int c = -1;
+      if (tid < rows_here) {
+        const int64_t v = __ldg(index + row0 + tid);
+        if (v >= 0 && v < n_embed) c = (int)v;
+        else if (status_flag) atomicExch(status_flag, 1);
+      }
+      codes[tid] = c;
+    }
+    __syncthreads();
+    // lookup, commitment term, output; the x tile stays in shared memory for the statistics
+    float sq = 0.f;
+    for (int e = tid; e < kGatherRows * C4; e += kStatsThreads) {
+      const int r = e / C4, j = e % C4;
+      if (r < rows_here) {
+        const int c = codes[r];
+        const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (row0 + r) * x_row_stride) + j);
+        float4 q = c >= 0 ? __ldg(reinterpret_cast<const float4*>(et + (int64_t)c * D) + j)
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+        const float4 t = make_float4(q.x - xv.x, q.y - xv.y, q.z - xv.z, q.w - xv.w);
+        sq = fmaf(t.x, t.x, sq); sq = fmaf(t.y, t.y, sq); sq = fmaf(t.z, t.z, sq); sq = fmaf(t.w, t.w, sq);
+        q = make_float4(xv.x + t.x, xv.y + t.y, xv.z + t.z, xv.w + t.w);     // bottleneck.py:95
+        if (out_q) reinterpret_cast<float4*>(out_q + (row0 + r) * q_row_stride)[j] = q;
+        reinterpret_cast<float4*>(xs + r * D)[j] = xv;
+      }
+    }
+    sq = warp_sum(sq);
+    if (lane == 0) warp_part[warp] = (double)sq;
+    __syncthreads();
+    if (tid == 0) {
+      double s = 0.0;
+      for (int w = 0; w < kStatsWarps; ++w) s += warp_part[w];
+      partials[tile] = s;
+    }
+    // statistics: this warp adds the rows whose code it owns
+#pragma unroll 1
+    for (int g = 0; g < kGatherRows / 32; ++g) {
+      const int c_l = codes[g * 32 + lane];
+      unsigned todo = __ballot_sync(0xffffffffu, c_l >= 0 && (c_l % kStatsWarps) == warp);
+      while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int c = __shfl_sync(0xffffffffu, c_l, src);
+        if (c != run_code) {
+          flush_run();
+          run_code = c; run_len = 0;
+#pragma unroll
+          for (int v = 0; v < VPL; ++v) run[v] = 0.f;
+        }
+        const float* xr = xs + (g * 32 + src) * D + lane * VPL;
+#pragma unroll
+        for (int v = 0; v < VPL; ++v) run[v] += xr[v];
+        ++run_len;
+      }
+    }
+    __syncthreads();          // the tile buffers are reused by the next iteration
+  }
+  flush_run();
+  __syncthreads();
+  // one vector reduction per used code of this CTA
+  for (int k = warp; k < n_embed; k += kStatsWarps) {
+    const float n = cnt[k];
+    if (n > 0.f) {
+      if (lane == 0) atomicAdd(&stats[k], n);
+      if (lane < C4) atomicAdd(reinterpret_cast<float4*>(stats + n_embed + (int64_t)k * D) + lane,
+                               reinterpret_cast<const float4*>(acc + (size_t)k * D)[lane]);
+    }
+  }
+}
+
 // diff = sum(partials) / (N*D) ; perplexity from the usage histogram
 __global__ void __launch_bounds__(256)
 vq_finish_kernel(const double* __restrict__ partials, int64_t n_partials, int64_t n_rows, int dim,
@@ -371,8 +487,31 @@ int launch_gather_stats(const float* x, const isi_rows_layout& xl, const int64_t
                     (!x || (uniform(xl) && ((uintptr_t)x & 15) == 0)) &&
                     (!out_q || (uniform(ql) && ((uintptr_t)out_q & 15) == 0)) &&
                     (!stats || counts_only || ((n_embed & 3) == 0 && ((uintptr_t)stats & 15) == 0));
+  // training statistics: CTA-private shared-memory accumulators when the codebook fits
+  const size_t stats_smem = ((size_t)n_embed * dim + ((n_embed + 3) & ~3) + (size_t)kGatherRows * dim) * 4 +
+                            kGatherRows * 4;
+  if (fast && x && stats && !counts_only && (dim == 32 || dim == 64 || dim == 128) &&
+      stats_smem <= 200 * 1024) {
+    const int64_t want = (grid + 3) / 4;
+    const unsigned ctas = (unsigned)(want < kNumSms ? (want < 1 ? 1 : want) : kNumSms);
+#define ISI_STATS_CASE(DD)                                                                      \
+    case DD: {                                                                                  \
+      cudaError_t e = cudaFuncSetAttribute(vq_gather_stats_smem_kernel<DD>,                     \
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                                           (int)stats_smem);                                    \
+      if (e != cudaSuccess) return (int)e;                                                      \
+      vq_gather_stats_smem_kernel<DD><<<ctas, kStatsThreads, stats_smem, stream>>>(             \
+          x, xl.row_stride, index, n_rows, n_embed, p.et, out_q, ql.row_stride, stats,          \
+          partials, status_flag, grid);                                                         \
+      break;                                                                                    \
+    }
+    switch (dim) { ISI_STATS_CASE(32) ISI_STATS_CASE(64) ISI_STATS_CASE(128) }
+#undef ISI_STATS_CASE
+    ISI_LAUNCH_CHECK();
+    return ISI_OK;
+  }
   if (fast) {
-#define ISI_GATHER_CASE(LPR)                                                                   \
+#define ISI_GATHER_CASE(LPR)                                                                  \
     case LPR * 4:                                                                              \
       vq_gather_rowmajor_kernel<LPR><<<(unsigned)grid, 256, 0, stream>>>(                      \
           x, xl.row_stride, index, n_rows, n_embed, p.et, out_q, ql.row_stride, stats,         \
