@@ -237,27 +237,84 @@ vq_gather_rowmajor_kernel(const float* __restrict__ x, int64_t x_row_stride,
 // ---------------------------------------------------------------------------
 constexpr int kStatsThreads = 512;
 constexpr int kStatsWarps = kStatsThreads / 32;
+constexpr int kHalfRows = kGatherRows / 2;          // pipeline granule: half a 128-row tile
 
-template <int D>
+__device__ __forceinline__ uint32_t st_s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void st_mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "W_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra D_%=;\n\t"
+      "bra W_%=;\n\t"
+      "D_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+
+// The rows must be fully contiguous ([N, D] with row stride D): every 64-row granule is then
+// ONE cp.async.bulk into a ring of shared-memory stages, several granules ahead of the
+// consumers, which keeps enough bytes in flight to stream at HBM rate from one CTA per SM.
+template <int D, int STAGES>
 __global__ void __launch_bounds__(kStatsThreads, 1)
-vq_gather_stats_smem_kernel(const float* __restrict__ x, int64_t x_row_stride,
-                            const int64_t* __restrict__ index, int64_t n_rows, int n_embed,
-                            const float* __restrict__ et, float* __restrict__ out_q,
-                            int64_t q_row_stride, float* __restrict__ stats,
-                            double* __restrict__ partials, int32_t* __restrict__ status_flag,
-                            int64_t n_tiles) {
+vq_gather_stats_smem_kernel(const float* __restrict__ x, const int64_t* __restrict__ index,
+                            int64_t n_rows, int n_embed, const float* __restrict__ et,
+                            float* __restrict__ out_q, int64_t q_row_stride,
+                            float* __restrict__ stats, double* __restrict__ partials,
+                            int32_t* __restrict__ status_flag, int64_t n_tiles) {
   constexpr int VPL = D / 32;                       // accumulator floats per lane
   constexpr int C4 = D / 4;                         // float4 chunks per row
-  extern __shared__ __align__(16) float smem[];
+  extern __shared__ __align__(128) float smem[];
   float* acc = smem;                                // [K][D]
   float* cnt = acc + (size_t)n_embed * D;           // [K]
-  float* xs = cnt + ((n_embed + 3) & ~3);           // [kGatherRows][D]
-  int* codes = reinterpret_cast<int*>(xs + kGatherRows * D);   // [kGatherRows]
+  float* xs = cnt + ((n_embed + 31) & ~31);         // [STAGES][kHalfRows][D]
+  int* codes = reinterpret_cast<int*>(xs + STAGES * kHalfRows * D);   // [STAGES][kHalfRows]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(codes + STAGES * kHalfRows);
   __shared__ double warp_part[kStatsWarps];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < n_embed * D + ((n_embed + 3) & ~3); i += kStatsThreads) smem[i] = 0.f;
+  for (int i = tid; i < n_embed * D + ((n_embed + 31) & ~31); i += kStatsThreads) smem[i] = 0.f;
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; ++s)
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(st_s32(bars + s)));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
+
+  const int64_t my_tiles = (int64_t)blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t total = 2 * my_tiles;               // granules this CTA walks
+  auto granule_row0 = [&](int64_t g) {
+    return ((int64_t)blockIdx.x + (g >> 1) * gridDim.x) * kGatherRows + (g & 1) * kHalfRows;
+  };
+  auto issue = [&](int64_t g) {                     // thread 0 only
+    const int s = (int)(g % STAGES);
+    const int64_t row0 = granule_row0(g);
+    int64_t rows = n_rows - row0;
+    rows = rows < 0 ? 0 : (rows > kHalfRows ? kHalfRows : rows);
+    const uint32_t bar = st_s32(bars + s);
+    if (rows > 0) {
+      const uint32_t bytes = (uint32_t)rows * D * 4u;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+              "r"(st_s32(xs + (size_t)s * kHalfRows * D)),
+          "l"(x + row0 * D), "r"(bytes), "r"(bar) : "memory");
+    } else {
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+    }
+  };
+  auto load_code = [&](int64_t g) {                 // threads < kHalfRows
+    const int64_t row = granule_row0(g) + tid;
+    int c = -1;
+    if (row < n_rows) {
+      const int64_t v = __ldg(index + row);
+      if (v >= 0 && v < n_embed) c = (int)v;
+      else if (status_flag) atomicExch(status_flag, 1);
+    }
+    return c;
+  };
+
+  if (tid == 0)
+    for (int64_t g = 0; g < total && g < STAGES; ++g) issue(g);
+  int next_code = (tid < kHalfRows && total > 0) ? load_code(0) : -1;
 
   float run[VPL];
   int run_code = -1, run_len = 0;
@@ -269,48 +326,43 @@ vq_gather_stats_smem_kernel(const float* __restrict__ x, int64_t x_row_stride,
       if (lane == 0) cnt[run_code] += (float)run_len;
     }
   };
+  double tile_sq = 0.0;                             // thread 0: commitment sum of the open tile
 
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int64_t row0 = tile * kGatherRows;
-    const int rows_here = (int)min((int64_t)kGatherRows, n_rows - row0);
-    if (tid < kGatherRows) {
-      int c = -1;
-      if (tid < rows_here) {
-        const int64_t v = __ldg(index + row0 + tid);
-        if (v >= 0 && v < n_embed) c = (int)v;
-        else if (status_flag) atomicExch(status_flag, 1);
-      }
-      codes[tid] = c;
+  for (int64_t g = 0; g < total; ++g) {
+    const int s = (int)(g % STAGES);
+    const float* xt = xs + (size_t)s * kHalfRows * D;
+    int* ct = codes + s * kHalfRows;
+    const int64_t row0 = granule_row0(g);
+    int64_t rows64 = n_rows - row0;
+    const int rows_here = (int)(rows64 < 0 ? 0 : (rows64 > kHalfRows ? kHalfRows : rows64));
+    if (tid < kHalfRows) {
+      ct[tid] = next_code;
+      if (g + 1 < total) next_code = load_code(g + 1);       // overlaps this granule's work
     }
+    st_mbar_wait(st_s32(bars + s), (uint32_t)((g / STAGES) & 1));
     __syncthreads();
-    // lookup, commitment term, output; the x tile stays in shared memory for the statistics
+    // lookup, commitment term, output
     float sq = 0.f;
-    for (int e = tid; e < kGatherRows * C4; e += kStatsThreads) {
+#pragma unroll 2
+    for (int e = tid; e < kHalfRows * C4; e += kStatsThreads) {
       const int r = e / C4, j = e % C4;
       if (r < rows_here) {
-        const int c = codes[r];
-        const float4 xv = __ldg(reinterpret_cast<const float4*>(x + (row0 + r) * x_row_stride) + j);
+        const int c = ct[r];
+        const float4 xv = reinterpret_cast<const float4*>(xt + r * D)[j];
         float4 q = c >= 0 ? __ldg(reinterpret_cast<const float4*>(et + (int64_t)c * D) + j)
                           : make_float4(0.f, 0.f, 0.f, 0.f);
         const float4 t = make_float4(q.x - xv.x, q.y - xv.y, q.z - xv.z, q.w - xv.w);
         sq = fmaf(t.x, t.x, sq); sq = fmaf(t.y, t.y, sq); sq = fmaf(t.z, t.z, sq); sq = fmaf(t.w, t.w, sq);
         q = make_float4(xv.x + t.x, xv.y + t.y, xv.z + t.z, xv.w + t.w);     // bottleneck.py:95
         if (out_q) reinterpret_cast<float4*>(out_q + (row0 + r) * q_row_stride)[j] = q;
-        reinterpret_cast<float4*>(xs + r * D)[j] = xv;
       }
     }
     sq = warp_sum(sq);
     if (lane == 0) warp_part[warp] = (double)sq;
-    __syncthreads();
-    if (tid == 0) {
-      double s = 0.0;
-      for (int w = 0; w < kStatsWarps; ++w) s += warp_part[w];
-      partials[tile] = s;
-    }
     // statistics: this warp adds the rows whose code it owns
 #pragma unroll 1
-    for (int g = 0; g < kGatherRows / 32; ++g) {
-      const int c_l = codes[g * 32 + lane];
+    for (int grp = 0; grp < kHalfRows / 32; ++grp) {
+      const int c_l = ct[grp * 32 + lane];
       unsigned todo = __ballot_sync(0xffffffffu, c_l >= 0 && (c_l % kStatsWarps) == warp);
       while (todo) {
         const int src = __ffs(todo) - 1;
@@ -322,13 +374,23 @@ vq_gather_stats_smem_kernel(const float* __restrict__ x, int64_t x_row_stride,
 #pragma unroll
           for (int v = 0; v < VPL; ++v) run[v] = 0.f;
         }
-        const float* xr = xs + (g * 32 + src) * D + lane * VPL;
+        const float* xr = xt + (grp * 32 + src) * D + lane * VPL;
 #pragma unroll
         for (int v = 0; v < VPL; ++v) run[v] += xr[v];
         ++run_len;
       }
     }
-    __syncthreads();          // the tile buffers are reused by the next iteration
+    __syncthreads();          // every warp is done with this stage
+    if (tid == 0) {
+      double sum = 0.0;
+      for (int w = 0; w < kStatsWarps; ++w) sum += warp_part[w];
+      if (g & 1) partials[blockIdx.x + (g >> 1) * gridDim.x] = tile_sq + sum;
+      else tile_sq = sum;
+      if (g + STAGES < total) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        issue(g + STAGES);
+      }
+    }
   }
   flush_run();
   __syncthreads();
@@ -487,25 +549,27 @@ int launch_gather_stats(const float* x, const isi_rows_layout& xl, const int64_t
                     (!x || (uniform(xl) && ((uintptr_t)x & 15) == 0)) &&
                     (!out_q || (uniform(ql) && ((uintptr_t)out_q & 15) == 0)) &&
                     (!stats || counts_only || ((n_embed & 3) == 0 && ((uintptr_t)stats & 15) == 0));
-  // training statistics: CTA-private shared-memory accumulators when the codebook fits
-  const size_t stats_smem = ((size_t)n_embed * dim + ((n_embed + 3) & ~3) + (size_t)kGatherRows * dim) * 4 +
-                            kGatherRows * 4;
+  // training statistics: CTA-private shared-memory accumulators when the codebook fits and the
+  // rows are fully contiguous (one bulk copy per 64-row granule)
+  const int stages = dim <= 64 ? 4 : 2;
+  const size_t stats_smem = ((size_t)n_embed * dim + ((n_embed + 31) & ~31) +
+                             (size_t)stages * kHalfRows * dim) * 4 + stages * kHalfRows * 4 + 64;
   if (fast && x && stats && !counts_only && (dim == 32 || dim == 64 || dim == 128) &&
-      stats_smem <= 200 * 1024) {
+      xl.row_stride == dim && stats_smem <= 220 * 1024) {
     const int64_t want = (grid + 3) / 4;
     const unsigned ctas = (unsigned)(want < kNumSms ? (want < 1 ? 1 : want) : kNumSms);
-#define ISI_STATS_CASE(DD)                                                                      \
+#define ISI_STATS_CASE(DD, ST)                                                                  \
     case DD: {                                                                                  \
-      cudaError_t e = cudaFuncSetAttribute(vq_gather_stats_smem_kernel<DD>,                     \
+      cudaError_t e = cudaFuncSetAttribute(vq_gather_stats_smem_kernel<DD, ST>,                 \
                                            cudaFuncAttributeMaxDynamicSharedMemorySize,         \
                                            (int)stats_smem);                                    \
       if (e != cudaSuccess) return (int)e;                                                      \
-      vq_gather_stats_smem_kernel<DD><<<ctas, kStatsThreads, stats_smem, stream>>>(             \
-          x, xl.row_stride, index, n_rows, n_embed, p.et, out_q, ql.row_stride, stats,          \
-          partials, status_flag, grid);                                                         \
+      vq_gather_stats_smem_kernel<DD, ST><<<ctas, kStatsThreads, stats_smem, stream>>>(         \
+          x, index, n_rows, n_embed, p.et, out_q, ql.row_stride, stats, partials, status_flag,  \
+          grid);                                                                                \
       break;                                                                                    \
     }
-    switch (dim) { ISI_STATS_CASE(32) ISI_STATS_CASE(64) ISI_STATS_CASE(128) }
+    switch (dim) { ISI_STATS_CASE(32, 4) ISI_STATS_CASE(64, 4) ISI_STATS_CASE(128, 2) }
 #undef ISI_STATS_CASE
     ISI_LAUNCH_CHECK();
     return ISI_OK;
