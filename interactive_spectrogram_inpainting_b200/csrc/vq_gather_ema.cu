@@ -362,11 +362,17 @@ vq_gather_stats_smem_kernel(const float* __restrict__ x, const int64_t* __restri
     // statistics: this warp adds the rows whose code it owns
 #pragma unroll 1
     for (int grp = 0; grp < kHalfRows / 32; ++grp) {
+      // Rows of this 32-row group that share an owned code are grouped with match.any and
+      // summed in registers, so a popular code costs one accumulator update per group
+      // however its rows are interleaved with others.
       const int c_l = ct[grp * 32 + lane];
-      unsigned todo = __ballot_sync(0xffffffffu, c_l >= 0 && (c_l % kStatsWarps) == warp);
-      while (todo) {
-        const int src = __ffs(todo) - 1;
-        todo &= todo - 1;
+      const bool owned = c_l >= 0 && (c_l % kStatsWarps) == warp;
+      const unsigned peers = __match_any_sync(0xffffffffu, owned ? c_l : -1 - lane);
+      unsigned leaders = __ballot_sync(0xffffffffu, owned && lane == __ffs(peers) - 1);
+      while (leaders) {
+        const int src = __ffs(leaders) - 1;
+        leaders &= leaders - 1;
+        const unsigned members = __shfl_sync(0xffffffffu, peers, src);
         const int c = __shfl_sync(0xffffffffu, c_l, src);
         if (c != run_code) {
           flush_run();
@@ -374,10 +380,12 @@ vq_gather_stats_smem_kernel(const float* __restrict__ x, const int64_t* __restri
 #pragma unroll
           for (int v = 0; v < VPL; ++v) run[v] = 0.f;
         }
-        const float* xr = xt + (grp * 32 + src) * D + lane * VPL;
+        for (unsigned m = members; m; m &= m - 1) {
+          const float* xr = xt + (grp * 32 + __ffs(m) - 1) * D + lane * VPL;
 #pragma unroll
-        for (int v = 0; v < VPL; ++v) run[v] += xr[v];
-        ++run_len;
+          for (int v = 0; v < VPL; ++v) run[v] += xr[v];
+        }
+        run_len += __popc(members);
       }
     }
     __syncthreads();          // every warp is done with this stage

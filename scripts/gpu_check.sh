@@ -34,6 +34,10 @@ for s in $steps; do
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 400 --csv \
         --log-file gpurun_out/launches_$tag.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches_$tag.log 2>&1
       tail -1 gpurun_out/ncu_launches_$tag.log | cut -c1-200 ;;
+    ncu_stats)
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:vq_gather_stats_smem -s 3 -c 1 \
+        -o gpurun_out/stats_$tag python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_stats_$tag.log 2>&1
+      tail -1 gpurun_out/ncu_stats_$tag.log | cut -c1-200 ;;
     probe)
       timeout 120 ./tools/umma_probe.bin 2>&1 | tee gpurun_out/umma_probe_$tag.log ;;
     all_tests)
