@@ -24,9 +24,7 @@ import json
 import os
 import pathlib
 import statistics
-import subprocess
 import sys
-import tempfile
 import time
 
 ROOT = pathlib.Path(__file__).resolve().parent
@@ -52,63 +50,9 @@ def measured_peaks():
     return 6650.0, "fallback", {}
 
 
-class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 100 ms during the timed region."""
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
-
-    def __init__(self, index: int):
-        self.index, self.proc, self.path = index, None, None
-
-    def __enter__(self):
-        try:
-            fd, self.path = tempfile.mkstemp(suffix=".csv")
-            os.close(fd)
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100", "-i", str(self.index)],
-                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
-        except Exception:
-            self.proc = None
-        return self
-
-    def __exit__(self, *exc):
-        if self.proc is not None:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=5)
-            except Exception:
-                self.proc.kill()
-
-    def summary(self):
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if not self.path or not os.path.exists(self.path):
-            return out
-        sm, mx, reasons = [], [], set()
-        for line in open(self.path):
-            f = [s.strip() for s in line.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                sm.append(float(f[0])); mx.append(float(f[1]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
-                                "sw_power_cap"), f[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        os.unlink(self.path)
-        if sm:
-            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons),
-                       samples=len(sm))
-        return out
-
-
 class NvmlClockSampler:
     """SM clock, max clock and throttle reasons sampled every ~10 ms from NVML on a thread;
-    only samples taken between ``start()`` and ``stop()`` (the timed region) are summarised.
-    Falls back to the nvidia-smi sampler when pynvml is unavailable."""
+    only samples taken between ``start()`` and ``stop()`` (the timed region) are summarised."""
     REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20,
                "sw_power_cap": 0x4}
 

@@ -38,6 +38,11 @@ for s in $steps; do
       timeout 600 ncu --set full --clock-control none --import-source on -k regex:vq_gather_stats_smem -s 3 -c 1 \
         -o gpurun_out/stats_$tag python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_stats_$tag.log 2>&1
       tail -1 gpurun_out/ncu_stats_$tag.log | cut -c1-200 ;;
+    multi)
+      n=${NGPUS:-2}
+      timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 20 --warmup 3 2>&1 | tail -2 > gpurun_out/bench_multi${n}_$tag.json
+      cut -c1-300 gpurun_out/bench_multi${n}_$tag.json
+      timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus $n --steps 3 --warmup 1 2>&1 | tail -1 | cut -c1-200 ;;
     probe)
       timeout 120 ./tools/umma_probe.bin 2>&1 | tee gpurun_out/umma_probe_$tag.log ;;
     all_tests)
