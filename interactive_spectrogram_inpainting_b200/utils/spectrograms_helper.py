@@ -170,6 +170,49 @@ class SpectrogramsHelper(nn.Module):
 
     forward = to_spectrogram
 
+    # ------------------------------------------------------------------
+    # Inverse and file helpers: plain torch (SURVEY.md 8f N4 -- callers of the hot path:
+    # flask_server.py:596,648,1016, sample.py:526,599, train_vqvae.py:392-394).
+    # ------------------------------------------------------------------
+    def _linear_to_audio(self, spec: torch.Tensor) -> torch.Tensor:
+        """``[B, 2, F, T']`` linear log-magnitude + IF -> ``[B, samples]`` (GANSynth
+        ``specgrams_to_stfts`` + inverse STFT, padding removed)."""
+        logmag, ifreq = spec[:, 0].float(), spec[:, 1].float()
+        mag = torch.exp(logmag)
+        phase = torch.cumsum(ifreq * math.pi, dim=-1)
+        stft = torch.polar(mag, phase)
+        zero = torch.zeros_like(stft[:, :1])
+        stft = torch.cat([zero, stft], 1) if self.drop_bin == "dc" else torch.cat([stft, zero], 1)
+        frames = stft.shape[-1]
+        total = self.hop_length * (frames - 1) + self.n_fft
+        window = self.window.to(stft.device)
+        # overlap-add by hand: torch.istft insists on center=True framing
+        cols = torch.fft.irfft(stft, n=self.n_fft, dim=1) * window[None, :, None]
+        audio = torch.nn.functional.fold(cols, (1, total), (1, self.n_fft), stride=(1, self.hop_length))
+        norm = torch.nn.functional.fold((window ** 2)[None, :, None].expand(1, -1, frames).contiguous(),
+                                        (1, total), (1, self.n_fft), stride=(1, self.hop_length))
+        audio = (audio / norm.clamp_min(1e-8))[:, 0, 0]
+        pad_right = self.n_fft - self.hop_length
+        return audio[:, self.pad_left:total - pad_right]
+
+    def to_audio(self, spec: torch.Tensor) -> torch.Tensor:
+        return self._linear_to_audio(spec)
+
+    def from_wavfile(self, path, duration_n: Optional[int] = None) -> torch.Tensor:
+        """Load a wav file (mono mix, resampled to ``fs_hz``, cropped / zero-padded to
+        ``duration_n`` samples) and return its ``[1, 2, F, T']`` spectrogram on the helper's
+        device (call shape of flask_server.py:648, sample.py:526)."""
+        import torchaudio
+        wav, fs = torchaudio.load(str(path))
+        wav = wav.mean(0, keepdim=True)
+        if fs != self.fs_hz:
+            wav = torchaudio.functional.resample(wav, fs, self.fs_hz)
+        if duration_n is not None:
+            wav = wav[:, :duration_n]
+            if wav.shape[1] < duration_n:
+                wav = torch.nn.functional.pad(wav, (0, duration_n - wav.shape[1]))
+        return self.to_spectrogram(wav.to(self.window.device))
+
 
 class MelSpectrogramsHelper(SpectrogramsHelper):
     """Mel-scaled variant: log of the mel-projected squared magnitude and the IF of the
@@ -194,6 +237,22 @@ class MelSpectrogramsHelper(SpectrogramsHelper):
         self.register_buffer("mel_count", torch.from_numpy(counts), persistent=False)
         self.register_buffer("mel_weight", torch.from_numpy(weights).float().contiguous(),
                              persistent=False)
+
+    def to_audio(self, spec: torch.Tensor) -> torch.Tensor:
+        """GANSynth ``melspecgrams_to_specgrams`` (pseudo-inverse filterbank: transpose
+        normalised by the row sums of M M^T) followed by the linear inverse."""
+        logmelmag2, mel_if = spec[:, 0].float(), spec[:, 1].float()
+        m = torch.from_numpy(dense_mel_matrix(self.mel_start.cpu().numpy(), self.mel_count.cpu().numpy(),
+                                              self.mel_weight.double().cpu().numpy())).to(spec.device)
+        gram_rows = (m @ m.t()).sum(0)
+        scale = torch.where(gram_rows.abs() > 1e-8, 1.0 / gram_rows, gram_rows)
+        mel_to_lin = (m.t() * scale[None, :]).float()                  # [mel, linear]
+        mag2 = torch.einsum("bmt,ml->blt", torch.exp(logmelmag2), mel_to_lin)
+        logmag = 0.5 * torch.log(mag2.clamp_min(0) + self.safelog_eps)
+        mel_phase = torch.cumsum(mel_if * math.pi, dim=-1)
+        phase = torch.einsum("bmt,ml->blt", mel_phase, mel_to_lin)
+        ifreq = torch.cat([phase[..., :1], phase[..., 1:] - phase[..., :-1]], -1) / math.pi
+        return self._linear_to_audio(torch.stack([logmag, ifreq], 1))
 
     def _params(self, n_frames: int) -> "_lib.MelifParams":
         p = super()._params(n_frames)

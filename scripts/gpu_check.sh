@@ -43,6 +43,8 @@ for s in $steps; do
       timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 20 --warmup 3 2>&1 | tail -2 > gpurun_out/bench_multi${n}_$tag.json
       cut -c1-300 gpurun_out/bench_multi${n}_$tag.json
       timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus $n --steps 3 --warmup 1 2>&1 | tail -1 | cut -c1-200 ;;
+    multi_test)
+      timeout 600 python -m pytest tests/test_gpu_multi.py -q 2>&1 | tail -5 ;;
     probe)
       timeout 120 ./tools/umma_probe.bin 2>&1 | tee gpurun_out/umma_probe_$tag.log ;;
     all_tests)

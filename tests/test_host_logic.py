@@ -62,3 +62,26 @@ def test_helper_metadata_matches_reference_call_sites():
     assert h.safelog_eps == 1e-6 and h.num_frames(64000) == 128 and h.n_freq == 1024
     with pytest.raises(ValueError):
         sh.SpectrogramsHelper(n_fft=1000)
+
+
+def test_to_audio_inverts_the_linear_front_end_on_cpu():
+    """``to_audio`` is plain torch: check it against the oracle's forward transform."""
+    from interactive_spectrogram_inpainting_b200.utils import synthetic
+    from oracle import frontend_oracle as fo
+    audio = synthetic.synthetic_notes(2)
+    spec = fo.to_spectrogram(audio.double(), fo.FrontEndConfig(use_mel_scale=False)).float()
+    rebuilt = sh.SpectrogramsHelper().to_audio(spec)
+    assert rebuilt.shape == audio.shape
+    err = (rebuilt - audio)[:, 2048:-2048].abs().max()
+    assert err < 2e-3, err          # exp(log(|X| + eps)) keeps the 1e-6 offset; edges excluded
+
+
+def test_mel_to_audio_runs_and_is_close_in_level():
+    from interactive_spectrogram_inpainting_b200.utils import synthetic
+    from oracle import frontend_oracle as fo
+    audio = synthetic.synthetic_notes(1)
+    spec = fo.to_spectrogram(audio, fo.FrontEndConfig())
+    rebuilt = sh.MelSpectrogramsHelper().to_audio(spec)
+    assert rebuilt.shape == audio.shape and torch.isfinite(rebuilt).all()
+    ratio = rebuilt.pow(2).mean().sqrt() / audio.pow(2).mean().sqrt()
+    assert 0.3 < ratio < 3.0, ratio   # the mel pseudo-inverse is lossy; level must survive
