@@ -426,8 +426,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--batch", type=int, default=296,
-                    help="notes per step per GPU (default 2 x 148 SMs: whole waves of note CTAs)")
+    ap.add_argument("--batch", type=int, default=444,
+                    help="notes per step per GPU (default 3 x 148 SMs: one whole wave of note CTAs)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--assign-algo", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -13,8 +13,9 @@
 // the window sit in shared memory, the mel band of each output row in registers; the
 // complex spectrum, magnitudes and phase steps never leave shared memory / registers.
 // HBM traffic is the audio once (frame overlap is served from shared memory) and the final
-// [2, F, T'] tensor, FB consecutive time steps per row at a time.  Two CTAs share an SM so
-// one CTA's barrier waits are filled by the other's work.
+// [2, F, T'] tensor, FB consecutive time steps per row at a time.  The whole working set is one
+// FB-frame buffer (65 KB with tables and stage at n_fft 2048), so three CTAs share an SM and
+// fill each other's barrier and latency stalls.
 #include "common.cuh"
 #include "melif_core.cuh"
 
@@ -56,7 +57,7 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 }
 
 struct MelifSmem {
-  int tw, win, stage, za, zb, bar, total;   // byte offsets into dynamic shared memory
+  int tw, win, stage, za, bar, total;   // byte offsets into dynamic shared memory
 };
 
 template <int NFFT, int FB>
@@ -67,15 +68,14 @@ __host__ __device__ inline MelifSmem melif_smem_layout(int hop) {
   s.tw = off;    off += (NFFT / 2) * 8;                     // W_M^e, e < M
   s.win = off;   off += NFFT * 4;
   s.stage = off; off += (((FB - 1) * hop + NFFT + 3) / 4) * 16;
-  s.za = off;    off += FB * P::kPitchA * 8;                // also zC[bin][FB] during polar/emit
-  s.zb = off;    off += FB * P::kPitchB * 8;
+  s.za = off;    off += FB * P::kPitchA * 8;                // FFT workspace, spectrum, polar values
   s.bar = off;   off += 16;
   s.total = off;
   return s;
 }
 
 template <int NFFT, int FB, int NT, bool MEL>
-__global__ void __launch_bounds__(NT, 2)
+__global__ void __launch_bounds__(NT, 3)
 melif_kernel(const float* __restrict__ audio, int64_t n_samples, isi_melif_params p,
              float* __restrict__ out, int bulk_ok, int seg_frames, int n_segs) {
   using P = Plan<NFFT>;
@@ -84,15 +84,13 @@ melif_kernel(const float* __restrict__ audio, int64_t n_samples, isi_melif_param
   constexpr int RPT = M / NT;                 // output rows per thread
   constexpr int kGroups = NT / 64;            // frames transformed concurrently
   static_assert(IPT >= 1 && (M / 2) % NT == 0 && NT % 64 == 0, "bad thread count");
-  static_assert(FB * P::kPitchA >= (M + 1) * FB, "zC must fit in zA");
+  static_assert(P::kPitchA >= M + 1, "a frame region must hold bins 0..M");
   extern __shared__ __align__(128) unsigned char smem[];
   const MelifSmem L = melif_smem_layout<NFFT, FB>(p.hop);
   cpx* twm = reinterpret_cast<cpx*>(smem + L.tw);
   float* win = reinterpret_cast<float*>(smem + L.win);
   float* stage = reinterpret_cast<float*>(smem + L.stage);
   cpx* zA = reinterpret_cast<cpx*>(smem + L.za);
-  cpx* zC = zA;
-  cpx* zB = reinterpret_cast<cpx*>(smem + L.zb);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar);
 
   const int tid = threadIdx.x;
@@ -181,7 +179,7 @@ melif_kernel(const float* __restrict__ audio, int64_t n_samples, isi_melif_param
 
     if (bulk_ok) { mbar_wait(bar, stage_phase & 1); ++stage_phase; }
     __syncthreads();       // zero-filled pads / synchronous fills come from other threads;
-                           // also fences the previous batch's emit (zC) from this pass 1 (zA)
+                           // also fences the previous batch's emit from this pass 1
     // The three FFT passes of a frame only involve the 64 threads of its group: they meet
     // on a named barrier of their own instead of stalling the whole CTA.
     const uint32_t group_bar = 1 + (tid >> 6);
@@ -190,17 +188,21 @@ melif_kernel(const float* __restrict__ audio, int64_t n_samples, isi_melif_param
     asm volatile("bar.sync %0, 64;" ::"r"(group_bar) : "memory");
     for (int fb = tid / 64; fb < nf; fb += kGroups) fft_pass2<P>(tid & 63, twm, zA + fb * P::kPitchA);
     asm volatile("bar.sync %0, 64;" ::"r"(group_bar) : "memory");
-    for (int fb = tid / 64; fb < nf; fb += kGroups)
-      fft_pass3<P>(tid & 63, zA + fb * P::kPitchA, zB + fb * P::kPitchB);
+    for (int fb = tid / 64; fb < nf; fb += kGroups) {
+      Pass3Regs<P> regs;
+      fft_pass3_load<P>(tid & 63, zA + fb * P::kPitchA, regs);
+      asm volatile("bar.sync %0, 64;" ::"r"(group_bar) : "memory");
+      fft_pass3_store<P>(tid & 63, regs, zA + fb * P::kPitchA);
+    }
     __syncthreads();
     if (next_nf > 0 && bulk_ok) stage_span(next_f0, next_nf);   // every group is done with the stage
-    // polar: frames in order, previous spectrum value in registers; zB -> zC (= zA storage)
+    // polar: frames in order, previous spectrum value in registers, in place
 #pragma unroll 2
     for (int fb = 0; fb < nf; ++fb) {
 #pragma unroll
       for (int i = 0; i < IPT; ++i)
-        polar_item<P, FB, MEL>(tid + i * NT, zB + fb * P::kPitchB, zC, fb, w_item[i],
-                               lookback || (f0 + fb == 0), eps, sa[i], sb[i], sc);
+        polar_item<P, MEL>(tid + i * NT, zA + fb * P::kPitchA, w_item[i],
+                           lookback || (f0 + fb == 0), eps, sa[i], sb[i], sc);
     }
     if (!lookback) {
       __syncthreads();
@@ -210,9 +212,9 @@ melif_kernel(const float* __restrict__ audio, int64_t n_samples, isi_melif_param
         const int row = tid + r * NT;
         float v0[FB], v1[FB];
         if (MEL)
-          emit_mel<FB>(zC, row_bin[r], row_cnt[r], row_cnt_warp[r], row_w[r], f0 == 0, eps, v0, v1);
+          emit_mel<FB>(zA, P::kPitchA, row_bin[r], row_cnt[r], row_cnt_warp[r], row_w[r], f0 == 0, eps, v0, v1);
         else
-          emit_linear<FB>(zC, row_bin[r], v0, v1);
+          emit_linear<FB>(zA, P::kPitchA, row_bin[r], v0, v1);
         if (p.channels_last) {
           // [B, F, T', 2]: the FB time steps of both channels are one contiguous run
           float* d = out + (((int64_t)note_idx * M + row) * p.n_frames + f0) * 2;
@@ -251,7 +253,7 @@ melif_kernel(const float* __restrict__ audio, int64_t n_samples, isi_melif_param
 static void choose_segments(int64_t n_notes, int n_frames, int fb, int* seg_frames, int* n_segs) {
   const int frames_padded = (n_frames + fb - 1) / fb * fb;
   const int max_segs = frames_padded / (4 * fb) > 1 ? frames_padded / (4 * fb) : 1;
-  const double slots = 2.0 * kNumSms;
+  const double slots = 3.0 * kNumSms;   // __launch_bounds__(NT, 3)
   double best = -1.0;
   *seg_frames = frames_padded; *n_segs = 1;
   for (int s = 1; s <= max_segs; ++s) {

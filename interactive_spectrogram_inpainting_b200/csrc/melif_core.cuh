@@ -9,12 +9,13 @@
 //   pass 1  window + pack z[m] = w[2m] a[2m] + i w[2m+1] a[2m+1] straight from the staged
 //           audio, radix R1 = M/64 over stride 64, twiddle, into zA (64-blocks padded by 4)
 //   pass 2  radix 16 over stride 4 inside each 64-block of zA, twiddle, in place
-//   pass 3  radix 4 on consecutive quadruples of zA, written in natural bin order to zB
+//   pass 3  radix 4 on consecutive quadruples of zA, rewritten in place in natural bin order
 //   polar   untangle X[k], X[M-k] from Z[k], Z[M-k]; |X|, phase step = arg(X_t conj X_t-1)
-//           (previous spectrum value carried in registers); (v0, v1) go to zC[bin][frame],
-//           which reuses zA's storage
+//           (previous spectrum value carried in registers); (v0, v1) overwrite Z in place
 //   emit    banded mel projections of (|X|+eps)^2 and of the phase steps (or a copy in
 //           linear mode) for all FB frames of a row at once, log and wrapped mel-IF
+// One buffer of FB frames is the kernel's whole working set (65 KB at n_fft 2048 with the
+// tables and the audio stage), which is what lets three CTAs share an SM.
 #pragma once
 #include <math.h>
 #include <stdint.h>
@@ -149,7 +150,6 @@ struct Plan {
   static constexpr int R1 = M / 64;         // first radix: 16 (2048), 8 (1024), 4 (512)
   static constexpr int kFftThreads = 64;    // threads cooperating on one frame's FFT
   static constexpr int kPitchA = M + 4 * R1;  // zA: every 64-block padded by 4 (pass-2 banks)
-  static constexpr int kPitchB = M + 2;       // zB: bins 0..M in natural order
   static_assert(R1 == 16 || R1 == 8 || R1 == 4, "n_fft must be 2048, 1024 or 512");
 };
 
@@ -211,18 +211,35 @@ ISI_HD void fft_pass2(int t, const cpx* twm, cpx* zA) {
   }
 }
 
-// ---- pass 3: radix 4 on quadruple (p1, p2) of zA -> bins p1 + R1 p2 + 16 R1 p3 of zB.
-//      Lanes run along p1 so the natural-order stores are contiguous. ----
+// ---- pass 3: radix 4 on the quadruples (p1, p2) of zA, rewritten IN PLACE in natural bin
+//      order (bin p1 + R1 p2 + 16 R1 p3).  Load + butterfly and store are two calls with the
+//      frame group's barrier between them, because the natural-order slots overlap other
+//      threads' quadruples.  Lanes run along p1, so the stores are contiguous. ----
 template <typename P>
-ISI_HD void fft_pass3(int t, const cpx* zA, cpx* zB) {
+struct Pass3Regs { cpx q[P::R1 / 4][4]; };
+
+template <typename P>
+ISI_HD void fft_pass3_load(int t, const cpx* zA, Pass3Regs<P>& r) {
   constexpr int kStep = P::kFftThreads / P::R1;          // p2 values covered per sweep
   const int p1 = t % P::R1;
-  for (int p2 = t / P::R1; p2 < 16; p2 += kStep) {
+#pragma unroll
+  for (int i = 0; i < P::R1 / 4; ++i) {
+    const int p2 = t / P::R1 + kStep * i;
     const cpx* q = zA + 68 * p1 + 4 * p2;
-    cpx a0 = q[0], a1 = q[1], a2 = q[2], a3 = q[3];
-    dft4(a0, a1, a2, a3);
-    cpx* o = zB + p1 + P::R1 * p2;
-    o[0] = a0; o[16 * P::R1] = a1; o[32 * P::R1] = a2; o[48 * P::R1] = a3;
+    r.q[i][0] = q[0]; r.q[i][1] = q[1]; r.q[i][2] = q[2]; r.q[i][3] = q[3];
+    dft4(r.q[i][0], r.q[i][1], r.q[i][2], r.q[i][3]);
+  }
+}
+
+template <typename P>
+ISI_HD void fft_pass3_store(int t, const Pass3Regs<P>& r, cpx* z) {
+  constexpr int kStep = P::kFftThreads / P::R1;
+  const int p1 = t % P::R1;
+#pragma unroll
+  for (int i = 0; i < P::R1 / 4; ++i) {
+    const int p2 = t / P::R1 + kStep * i;
+    cpx* o = z + p1 + P::R1 * p2;
+    o[0] = r.q[i][0]; o[16 * P::R1] = r.q[i][1]; o[32 * P::R1] = r.q[i][2]; o[48 * P::R1] = r.q[i][3];
   }
 }
 
@@ -252,44 +269,45 @@ ISI_HD cpx polar_bin(cpx x, bool first_frame, float eps, BinState& st) {
   return cpx{fast_log(mag + eps), step * kInvPi};
 }
 
-// ---- polar: work item `it` (0..M/2-1) of frame slot `fb`.  Item 0 owns bin M/2 and the
-//      two purely real bins 0 and M; item it>0 owns bins it and M-it.  Reads the natural
-//      order spectrum zB (one frame), writes (v0, v1) to zC[bin][fb] (FB frames per bin):
-//      mel mode (|X|+eps)^2 and the phase step, linear mode log(|X|+eps) and IF. ----
-template <typename P, int FB, bool MEL>
-ISI_HD void polar_item(int it, const cpx* zB, cpx* zC, int fb, cpx w /* W_N^it */,
-                       bool first_frame, float eps, BinState& sa, BinState& sb, BinState& sc) {
+// ---- polar: work item `it` (0..M/2-1) of one frame, in place on its natural-order
+//      spectrum z[0..M].  Item 0 owns bin M/2 and the two purely real bins 0 and M; item it>0
+//      owns bins it and M-it.  z[k] <- (v0, v1): mel mode (|X|+eps)^2 and the phase step,
+//      linear mode log(|X|+eps) and IF. ----
+template <typename P, bool MEL>
+ISI_HD void polar_item(int it, cpx* z, cpx w /* W_N^it */, bool first_frame, float eps,
+                       BinState& sa, BinState& sb, BinState& sc) {
   constexpr int M = P::M;
   if (it == 0) {
-    const cpx z0 = zB[0], zh = zB[M / 2];
-    zC[(M / 2) * FB + fb] = polar_bin<MEL>(cpx{zh.re, -zh.im}, first_frame, eps, sa);      // X[M/2]
-    zC[fb] = polar_bin<MEL>(cpx{z0.re + z0.im, 0.f}, first_frame, eps, sb);                // X[0]
-    zC[M * FB + fb] = polar_bin<MEL>(cpx{z0.re - z0.im, 0.f}, first_frame, eps, sc);       // X[M]
+    const cpx z0 = z[0], zh = z[M / 2];
+    z[M / 2] = polar_bin<MEL>(cpx{zh.re, -zh.im}, first_frame, eps, sa);      // X[M/2]
+    z[0] = polar_bin<MEL>(cpx{z0.re + z0.im, 0.f}, first_frame, eps, sb);     // X[0]
+    z[M] = polar_bin<MEL>(cpx{z0.re - z0.im, 0.f}, first_frame, eps, sc);     // X[M]
   } else {
-    const cpx a = zB[it], b = zB[M - it];
+    const cpx a = z[it], b = z[M - it];
     const cpx e = cpx{0.5f * (a.re + b.re), 0.5f * (a.im - b.im)};            // (A + conj B)/2
     const cpx d = cpx{0.5f * (a.re - b.re), 0.5f * (a.im + b.im)};            // (A - conj B)/2
     const cpx p = cmul(w, mul_neg_i(d));                                      // W_N^k (-i) d
     const cpx m = csub(e, p);
-    zC[it * FB + fb] = polar_bin<MEL>(cadd(e, p), first_frame, eps, sa);
-    zC[(M - it) * FB + fb] = polar_bin<MEL>(cpx{m.re, -m.im}, first_frame, eps, sb);
+    z[it] = polar_bin<MEL>(cadd(e, p), first_frame, eps, sa);
+    z[M - it] = polar_bin<MEL>(cpx{m.re, -m.im}, first_frame, eps, sb);
   }
 }
 
-// ---- emit: one output row, all FB frames of the batch at once, from zC[bin][fb].
-//      `bin0` is the FFT bin of the row (linear mode) or of the first band element (mel
-//      mode); mel weights live in registers, zero beyond `count`; `count_uniform` >= count
-//      is uniform across the warp so whole taps are skipped without divergence. ----
+// ---- emit: one output row, all FB frames of the batch at once; frame fb's values sit at
+//      z[fb * pitch + bin].  `bin0` is the FFT bin of the row (linear mode) or of the first
+//      band element (mel mode); mel weights live in registers, zero beyond `count`;
+//      `count_uniform` >= count is uniform across the warp so whole taps are skipped without
+//      divergence. ----
 constexpr int kMaxMelWidth = 8;
 
 template <int FB>
-ISI_HD void emit_linear(const cpx* zC, int bin0, float* out0, float* out1) {
+ISI_HD void emit_linear(const cpx* z, int pitch, int bin0, float* out0, float* out1) {
 #pragma unroll
-  for (int fb = 0; fb < FB; ++fb) { const cpx v = zC[bin0 * FB + fb]; out0[fb] = v.re; out1[fb] = v.im; }
+  for (int fb = 0; fb < FB; ++fb) { const cpx v = z[fb * pitch + bin0]; out0[fb] = v.re; out1[fb] = v.im; }
 }
 
 template <int FB>
-ISI_HD void emit_mel(const cpx* zC, int bin0, int count, int count_uniform, const float* w,
+ISI_HD void emit_mel(const cpx* z, int pitch, int bin0, int count, int count_uniform, const float* w,
                      bool first_is_frame0, float eps, float* out0, float* out1) {
   float m2[FB], mp[FB];
 #pragma unroll
@@ -298,10 +316,9 @@ ISI_HD void emit_mel(const cpx* zC, int bin0, int count, int count_uniform, cons
   for (int i = 0; i < kMaxMelWidth; ++i) {
     if (i < count_uniform) {
       if (i < count) {
-        const cpx* q = zC + (bin0 + i) * FB;
 #pragma unroll
         for (int fb = 0; fb < FB; ++fb) {
-          const cpx v = q[fb];
+          const cpx v = z[fb * pitch + bin0 + i];
           m2[fb] = fmaf(w[i], v.re, m2[fb]);
           mp[fb] = fmaf(w[i], v.im, mp[fb]);
         }

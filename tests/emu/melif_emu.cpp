@@ -24,8 +24,7 @@ static void emulate(const float* audio, int64_t n_notes, int64_t n_samples, int 
   const bool aligned8 = (hop % 2) == 0;
   const int dc = drop_dc ? 1 : 0;
   std::vector<float> stage((FB - 1) * hop + NFFT);
-  std::vector<cpx> zA((size_t)FB * P::kPitchA), zB((size_t)FB * P::kPitchB);
-  cpx* zC = zA.data();
+  std::vector<cpx> zA((size_t)FB * P::kPitchA);
   const int n_segs = (n_frames + seg_frames - 1) / seg_frames;
 
   auto transform = [&](const float* note, int frame, int nf) {
@@ -38,9 +37,13 @@ static void emulate(const float* audio, int64_t n_notes, int64_t n_samples, int 
     for (int tid = 0; tid < NT; ++tid)
       for (int fb = tid / 64; fb < nf; fb += kGroups)
         fft_pass2<P>(tid & 63, twm.data(), zA.data() + fb * P::kPitchA);
+    std::vector<Pass3Regs<P>> regs((size_t)NT * FB);
     for (int tid = 0; tid < NT; ++tid)
       for (int fb = tid / 64; fb < nf; fb += kGroups)
-        fft_pass3<P>(tid & 63, zA.data() + fb * P::kPitchA, zB.data() + fb * P::kPitchB);
+        fft_pass3_load<P>(tid & 63, zA.data() + fb * P::kPitchA, regs[tid * FB + fb]);
+    for (int tid = 0; tid < NT; ++tid)
+      for (int fb = tid / 64; fb < nf; fb += kGroups)
+        fft_pass3_store<P>(tid & 63, regs[tid * FB + fb], zA.data() + fb * P::kPitchA);
   };
 
   for (int64_t n = 0; n < n_notes; ++n)
@@ -54,8 +57,8 @@ static void emulate(const float* audio, int64_t n_notes, int64_t n_samples, int 
         transform(note, fs - 1, 1);
         for (int tid = 0; tid < NT; ++tid)
           for (int i = 0; i < IPT; ++i)
-            polar_item<P, FB, MEL>(tid + i * NT, zB.data(), zC, 0, tw[tid + i * NT], true, eps,
-                                   sa[tid * IPT + i], sb[tid * IPT + i], sc[tid]);
+            polar_item<P, MEL>(tid + i * NT, zA.data(), tw[tid + i * NT], true, eps,
+                               sa[tid * IPT + i], sb[tid * IPT + i], sc[tid]);
       }
       for (int f0 = fs; f0 < fe; f0 += FB) {
         const int nf = std::min(FB, fe - f0);
@@ -63,8 +66,8 @@ static void emulate(const float* audio, int64_t n_notes, int64_t n_samples, int 
         for (int tid = 0; tid < NT; ++tid)
           for (int fb = 0; fb < nf; ++fb)
             for (int i = 0; i < IPT; ++i)
-              polar_item<P, FB, MEL>(tid + i * NT, zB.data() + fb * P::kPitchB, zC, fb, tw[tid + i * NT],
-                                     f0 + fb == 0, eps, sa[tid * IPT + i], sb[tid * IPT + i], sc[tid]);
+              polar_item<P, MEL>(tid + i * NT, zA.data() + fb * P::kPitchA, tw[tid + i * NT],
+                                 f0 + fb == 0, eps, sa[tid * IPT + i], sb[tid * IPT + i], sc[tid]);
         for (int tid = 0; tid < NT; ++tid)
           for (int r = 0; r < RPT; ++r) {
             const int row = tid + r * NT;
@@ -75,8 +78,8 @@ static void emulate(const float* audio, int64_t n_notes, int64_t n_samples, int 
               for (int i = 0; i < mel_width && i < kMaxMelWidth; ++i) w[i] = mel_weight[(int64_t)row * mel_width + i];
             }
             float v0[FB], v1[FB];
-            if (MEL) emit_mel<FB>(zC, bin0, cnt, kMaxMelWidth, w, f0 == 0, eps, v0, v1);
-            else     emit_linear<FB>(zC, bin0, v0, v1);
+            if (MEL) emit_mel<FB>(zA.data(), P::kPitchA, bin0, cnt, kMaxMelWidth, w, f0 == 0, eps, v0, v1);
+            else     emit_linear<FB>(zA.data(), P::kPitchA, bin0, v0, v1);
             for (int fb = 0; fb < nf; ++fb) {
               out0[(int64_t)row * n_frames + f0 + fb] = v0[fb];
               out1[(int64_t)row * n_frames + f0 + fb] = v1[fb];
