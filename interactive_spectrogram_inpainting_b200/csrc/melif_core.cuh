@@ -7,7 +7,7 @@
 //
 // Transform plan for an n_fft-point real frame (M = n_fft/2 complex points):
 //   pass 1  window + pack z[m] = w[2m] a[2m] + i w[2m+1] a[2m+1] straight from the staged
-//           audio, radix R1 = M/64 over stride 64, twiddle, into zA (64-blocks padded by 4)
+//           audio, radix R1 = M/64 over stride 64, twiddle, into zA (64-blocks at pitch 65)
 //   pass 2  radix 16 over stride 4 inside each 64-block of zA, twiddle, in place
 //   pass 3  radix 4 on consecutive quadruples of zA, rewritten in place in natural bin order
 //   polar   untangle X[k], X[M-k] from Z[k], Z[M-k]; |X|, phase step = arg(X_t conj X_t-1)
@@ -149,7 +149,9 @@ struct Plan {
   static constexpr int M = NFFT / 2;        // complex points; bins 0..M
   static constexpr int R1 = M / 64;         // first radix: 16 (2048), 8 (1024), 4 (512)
   static constexpr int kFftThreads = 64;    // threads cooperating on one frame's FFT
-  static constexpr int kPitchA = M + 4 * R1;  // zA: every 64-block padded by 4 (pass-2 banks)
+  static constexpr int kBlockPitch = 65;      // 64-blocks one element apart: lanes that walk the
+                                              // blocks (passes 2 and 3) hit 16 distinct bank pairs
+  static constexpr int kPitchA = kBlockPitch * R1 + 1;   // >= M + 1: also holds bins 0..M
   static_assert(R1 == 16 || R1 == 8 || R1 == 4, "n_fft must be 2048, 1024 or 512");
 };
 
@@ -189,15 +191,15 @@ ISI_HD void fft_pass1(int j, const float* frame /* stage + fb*hop */, bool frame
 #pragma unroll
   for (int p = 1; p < P::R1; ++p) v[p] = cmul(v[p], twm[j * p]);               // W_M^(j p)
 #pragma unroll
-  for (int p = 0; p < P::R1; ++p) zA[j + 68 * p] = v[p];
+  for (int p = 0; p < P::R1; ++p) zA[j + P::kBlockPitch * p] = v[p];
 }
 
-// ---- pass 2: inside each (padded) 64-block, radix 16 over stride 4 ----
+// ---- pass 2: inside each 64-block, radix 16 over stride 4 ----
 template <typename P>
 ISI_HD void fft_pass2(int t, const cpx* twm, cpx* zA) {
   for (int item = t; item < 4 * P::R1; item += P::kFftThreads) {
-    const int b = item >> 2, j = item & 3;
-    cpx* blk = zA + 68 * b;
+    const int b = item % P::R1, j = item / P::R1;       // lanes along b: bank = b (pitch 65)
+    cpx* blk = zA + P::kBlockPitch * b;
     cpx v[16];
 #pragma unroll
     for (int r = 0; r < 16; ++r) v[r] = blk[j + 4 * r];
@@ -225,7 +227,7 @@ ISI_HD void fft_pass3_load(int t, const cpx* zA, Pass3Regs<P>& r) {
 #pragma unroll
   for (int i = 0; i < P::R1 / 4; ++i) {
     const int p2 = t / P::R1 + kStep * i;
-    const cpx* q = zA + 68 * p1 + 4 * p2;
+    const cpx* q = zA + P::kBlockPitch * p1 + 4 * p2;
     r.q[i][0] = q[0]; r.q[i][1] = q[1]; r.q[i][2] = q[2]; r.q[i][3] = q[3];
     dft4(r.q[i][0], r.q[i][1], r.q[i][2], r.q[i][3]);
   }
