@@ -10,6 +10,10 @@ int launch_assign_tc(const float*, const isi_rows_layout&, int64_t, int, int, co
                      int64_t*, float*, cudaStream_t);
 int launch_prepare(const float*, int, int, const Prepared&, cudaStream_t);
 int launch_prepare_tc(const float*, int, int, const Prepared&, cudaStream_t);
+bool assign_pair_supported(const isi_rows_layout&, int64_t, int, int);
+int launch_prepare_pair(const float*, int, int, const Prepared&, cudaStream_t);
+int launch_assign_pair(const float*, const isi_rows_layout&, int64_t, int, int, const Prepared&,
+                       int64_t*, float*, cudaStream_t);
 size_t gather_workspace_bytes(int64_t);
 int launch_gather_stats(const float*, const isi_rows_layout&, const int64_t*, int64_t, int, int,
                         const Prepared&, float*, const isi_rows_layout&, float*, int, void*,
@@ -56,7 +60,9 @@ ISI_API int isi_vq_prepare_codebook(const float* embed, int dim, int n_embed, vo
   Prepared p = prepared_view(prepared, dim, n_embed);
   int rc = launch_prepare(embed, dim, n_embed, p, (cudaStream_t)stream);
   if (rc) return rc;
-  return launch_prepare_tc(embed, dim, n_embed, p, (cudaStream_t)stream);
+  rc = launch_prepare_tc(embed, dim, n_embed, p, (cudaStream_t)stream);
+  if (rc) return rc;
+  return launch_prepare_pair(embed, dim, n_embed, p, (cudaStream_t)stream);
 }
 
 ISI_API int isi_vq_assign(const float* x, const isi_rows_layout* xl, int64_t n_rows, int dim, int n_embed,
@@ -67,6 +73,11 @@ ISI_API int isi_vq_assign(const float* x, const isi_rows_layout* xl, int64_t n_r
   if (n_rows == 0) return ISI_OK;
   Prepared p = prepared_view(prepared, dim, n_embed);
   const bool tc_ok = assign_tc_supported(*xl, n_rows, dim, n_embed);
+  const bool pair_ok = assign_pair_supported(*xl, n_rows, dim, n_embed);
+  if (algo == ISI_ASSIGN_TCGEN05_PAIR && !pair_ok) return ISI_ERR_UNSUPPORTED;
+  if (algo == ISI_ASSIGN_TCGEN05_PAIR || (algo == ISI_ASSIGN_AUTO && pair_ok))
+    return launch_assign_pair(x, *xl, n_rows, dim, n_embed, p, out_index, out_score,
+                              (cudaStream_t)stream);
   if (algo == ISI_ASSIGN_TCGEN05 && !tc_ok) return ISI_ERR_UNSUPPORTED;
   if (algo == ISI_ASSIGN_TCGEN05 || (algo == ISI_ASSIGN_AUTO && tc_ok))
     return launch_assign_tc(x, *xl, n_rows, dim, n_embed, p, out_index, out_score,

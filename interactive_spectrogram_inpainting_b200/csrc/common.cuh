@@ -28,6 +28,7 @@ struct Prepared {
   float* ed;      // [D, K]     snapshot of the codebook as the caller holds it
   float* b_hi;    // tensor-core operand: TF32 "hi" part of -2E, canonical UMMA tiles
   float* b_lo;    // tensor-core operand: TF32 "lo" part of -2E
+  float* b_pair;  // 2-CTA kernel: per CTA rank the resident image of its half of every 256-code tile
   size_t bytes;
 };
 
@@ -45,6 +46,8 @@ __host__ __device__ inline Prepared prepared_view(const void* base, int dim, int
   off += align_up((size_t)padded_codes(n_embed) * dim * 4, 1024);
   p.b_lo = (float*)(c + off);
   off += align_up((size_t)padded_codes(n_embed) * dim * 4, 1024);
+  p.b_pair = (float*)(c + off);
+  off += align_up((size_t)padded_codes(n_embed) * dim * 8, 1024);
   p.bytes = off;
   return p;
 }

@@ -262,7 +262,8 @@ vq_gather_stats_smem_kernel(const float* __restrict__ x, const int64_t* __restri
                             int32_t* __restrict__ status_flag, int64_t n_tiles) {
   constexpr int VPL = D / 32;                       // accumulator floats per lane
   constexpr int C4 = D / 4;                         // float4 chunks per row
-  extern __shared__ __align__(128) float smem[];
+  extern __shared__ __align__(16) float smem[];     // bulk copies need 16-byte alignment;
+                                                    // the stage offsets below are 128-byte multiples
   float* acc = smem;                                // [K][D]
   float* cnt = acc + (size_t)n_embed * D;           // [K]
   float* xs = cnt + ((n_embed + 31) & ~31);         // [STAGES][kHalfRows][D]

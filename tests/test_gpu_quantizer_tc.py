@@ -62,3 +62,36 @@ def test_tcgen05_forward_end_to_end_and_rerun_is_deterministic():
     q2, d2, i2, p2 = m(x)
     assert torch.equal(i1, i2) and torch.equal(q1, q2) and d1.item() == d2.item()
     assert torch.equal(q1, m.embed_code(i1)) or (q1 - m.embed_code(i1)).abs().max() < 1e-6
+
+
+# ---- the CTA-pair (cta_group::2) kernel with the resident codebook -------------------------
+@pytest.mark.parametrize("n_embed,rows", [(512, 4096), (512, 40960), (512, 4097), (512, 100003),
+                                          (64, 8192), (300, 5000), (256, 9999)])
+def test_pair_kernel_matches_fp64_outside_near_ties(n_embed, rows):
+    embed = synthetic.synthetic_codebook(64, n_embed)
+    x = synthetic.synthetic_features(rows, embed)
+    m = make(64, n_embed, embed, "tcgen05_pair").eval()
+    ind = m.assign(x.to(DEV))
+    near, flipped = assert_indices_match(ind, x, embed)
+    simt = make(64, n_embed, embed, "simt").eval().assign(x.to(DEV))
+    agree = (simt == ind).float().mean().item()
+    print(f"[pair] K={n_embed} N={rows}: {near} near ties, {flipped} flipped vs FP64, "
+          f"agreement with the FP32 SIMT kernel {agree:.6f}")
+    assert agree > 0.999
+
+
+def test_pair_kernel_nchw_ties_and_determinism():
+    embed = synthetic.synthetic_codebook(64, 512)
+    embed[:, 300] = embed[:, 17]
+    embed[:, 511] = embed[:, 0]
+    x = synthetic.synthetic_features(8 * 64 * 8 * 4, embed).view(8, 64, 32, 64)
+    x[0, 0, 5] = embed[:, 17]
+    x[0, 0, 6] = embed[:, 511]
+    view = x.permute(0, 3, 1, 2).contiguous().to(DEV).permute(0, 2, 3, 1)
+    m = make(64, 512, embed, "tcgen05_pair").eval()
+    ind = m.assign(view)
+    assert_indices_match(ind, x.reshape(-1, 64), embed)
+    flat = ind.reshape(-1).cpu()
+    assert flat[5] == 17 and flat[6] == 0 and not ((flat == 300) | (flat == 511)).any()
+    assert torch.equal(m.assign(view), ind)
+    assert torch.equal(make(64, 512, embed, "tcgen05").eval().assign(view), ind)
