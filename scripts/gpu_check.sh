@@ -45,6 +45,10 @@ for s in $steps; do
       timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus $n --steps 3 --warmup 1 2>&1 | tail -1 | cut -c1-200 ;;
     multi_test)
       timeout 600 python -m pytest tests/test_gpu_multi.py -q 2>&1 | tail -5 ;;
+    extra)
+      timeout 600 python tools/bench_extra.py > gpurun_out/extra_$tag.json 2> gpurun_out/extra_$tag.err; tail -3 gpurun_out/extra_$tag.err; head -c 600 gpurun_out/extra_$tag.json ;;
+    smoke)
+      timeout 300 python __graft_entry__.py smoke 2>&1 | tail -2 ;;
     probe)
       timeout 120 ./tools/umma_probe.bin 2>&1 | tee gpurun_out/umma_probe_$tag.log ;;
     all_tests)
