@@ -94,7 +94,7 @@ def cfg5():
             with torch.cuda.graph(graph):
                 static_out = model.decode_code(top, bottom)
             graph_ms = timed(graph.replay)
-            assert torch.equal(static_out, model.decode_code(top, bottom))
+            assert torch.allclose(static_out, model.decode_code(top, bottom), rtol=1e-3, atol=1e-4)
         out.append({"batch": b, "embed_code_top_plus_bottom_ms": lookup_ms,
                     "decode_code_eager_ms": eager_ms, "decode_code_cuda_graph_ms": graph_ms})
     return out
