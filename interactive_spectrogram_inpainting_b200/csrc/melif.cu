@@ -115,20 +115,22 @@ melif_kernel(const float* __restrict__ audio, int64_t n_samples, isi_melif_param
   cpx w_item[IPT];
 #pragma unroll
   for (int i = 0; i < IPT; ++i) w_item[i] = tw_global[tid + i * NT];
-  // per output row: first FFT bin | band length << 16 | warp-uniform band length << 24.  The
-  // band weights themselves are re-read from the (L1-resident, 24 KB) table in the emit phase:
-  // holding 4 rows x 8 weights in registers cost 112 bytes of spills at 80 registers.
-  int row_meta[RPT];
+  int row_bin[RPT], row_cnt[RPT], row_cnt_warp[RPT];
+  float row_w[RPT][MEL ? kMaxMelWidth : 1];
 #pragma unroll
   for (int r = 0; r < RPT; ++r) {
     const int row = tid + r * NT;
-    int bin = row + dc, cnt = 0, cnt_warp = 0;
+    row_cnt[r] = 0;
+    row_bin[r] = row + dc;
+    row_cnt_warp[r] = 0;
     if (MEL) {
-      bin = p.mel_start[row] + dc;
-      cnt = p.mel_count[row];
-      cnt_warp = __reduce_max_sync(0xffffffffu, cnt);
+      row_bin[r] = p.mel_start[row] + dc;
+      row_cnt[r] = p.mel_count[row];
+#pragma unroll
+      for (int i = 0; i < kMaxMelWidth; ++i)
+        row_w[r][i] = (i < p.mel_width) ? p.mel_weight[(int64_t)row * p.mel_width + i] : 0.f;
+      row_cnt_warp[r] = __reduce_max_sync(0xffffffffu, row_cnt[r]);
     }
-    row_meta[r] = bin | (cnt << 16) | (cnt_warp << 24);
   }
   BinState sa[IPT], sb[IPT], sc{1.f, 0.f};
 #pragma unroll
@@ -210,10 +212,9 @@ melif_kernel(const float* __restrict__ audio, int64_t n_samples, isi_melif_param
         const int row = tid + r * NT;
         float v0[FB], v1[FB];
         if (MEL)
-          emit_mel<FB>(zA, P::kPitchA, row_meta[r] & 0xffff, (row_meta[r] >> 16) & 0xff, row_meta[r] >> 24,
-                       p.mel_weight + (int64_t)row * p.mel_width, f0 == 0, eps, v0, v1);
+          emit_mel<FB>(zA, P::kPitchA, row_bin[r], row_cnt[r], row_cnt_warp[r], row_w[r], f0 == 0, eps, v0, v1);
         else
-          emit_linear<FB>(zA, P::kPitchA, row_meta[r] & 0xffff, v0, v1);
+          emit_linear<FB>(zA, P::kPitchA, row_bin[r], v0, v1);
         if (p.channels_last) {
           // [B, F, T', 2]: the FB time steps of both channels are one contiguous run
           float* d = out + (((int64_t)note_idx * M + row) * p.n_frames + f0) * 2;

@@ -25,11 +25,6 @@
 #else
 #define ISI_HD inline
 #endif
-#ifdef __CUDA_ARCH__
-#define ISI_LDG(ptr) __ldg(ptr)          // read-only path, stays in L1
-#else
-#define ISI_LDG(ptr) (*(ptr))
-#endif
 
 namespace isi {
 namespace melif {
@@ -302,7 +297,7 @@ ISI_HD void polar_item(int it, cpx* z, cpx w /* W_N^it */, bool first_frame, flo
 
 // ---- emit: one output row, all FB frames of the batch at once; frame fb's values sit at
 //      z[fb * pitch + bin].  `bin0` is the FFT bin of the row (linear mode) or of the first
-//      band element (mel mode); `w` points at the row's band weights (global, L1-resident);
+//      band element (mel mode); mel weights live in registers, zero beyond `count`;
 //      `count_uniform` >= count is uniform across the warp so whole taps are skipped without
 //      divergence. ----
 constexpr int kMaxMelWidth = 8;
@@ -323,12 +318,11 @@ ISI_HD void emit_mel(const cpx* z, int pitch, int bin0, int count, int count_uni
   for (int i = 0; i < kMaxMelWidth; ++i) {
     if (i < count_uniform) {
       if (i < count) {
-        const float wi = ISI_LDG(w + i);
 #pragma unroll
         for (int fb = 0; fb < FB; ++fb) {
           const cpx v = z[fb * pitch + bin0 + i];
-          m2[fb] = fmaf(wi, v.re, m2[fb]);
-          mp[fb] = fmaf(wi, v.im, mp[fb]);
+          m2[fb] = fmaf(w[i], v.re, m2[fb]);
+          mp[fb] = fmaf(w[i], v.im, mp[fb]);
         }
       }
     }
