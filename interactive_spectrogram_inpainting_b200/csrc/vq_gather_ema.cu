@@ -235,9 +235,9 @@ vq_gather_rowmajor_kernel(const float* __restrict__ x, int64_t x_row_stride,
 // first summed in registers.  Global memory sees one vector reduction per (CTA, used code)
 // at the very end: 148 x 128 KB at most, instead of 256 B of atomics per row.
 // ---------------------------------------------------------------------------
-constexpr int kStatsThreads = 512;
-constexpr int kStatsWarps = kStatsThreads / 32;
-constexpr int kHalfRows = kGatherRows / 2;          // pipeline granule: half a 128-row tile
+constexpr int kStatsWarps = 16;                     // consumer warps; one more warp produces
+constexpr int kStatsThreads = (kStatsWarps + 1) * 32;
+constexpr int kGranuleRows = 64;                    // rows per pipeline stage
 
 __device__ __forceinline__ uint32_t st_s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void st_mbar_wait(uint32_t bar, uint32_t parity) {
@@ -249,167 +249,160 @@ __device__ __forceinline__ void st_mbar_wait(uint32_t bar, uint32_t parity) {
       "bra W_%=;\n\t"
       "D_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
+__device__ __forceinline__ void st_mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
 
-// The rows must be fully contiguous ([N, D] with row stride D): every 64-row granule is then
-// ONE cp.async.bulk into a ring of shared-memory stages, several granules ahead of the
-// consumers, which keeps enough bytes in flight to stream at HBM rate from one CTA per SM.
+// Rows must be fully contiguous ([N, D], row stride D).  A producer warp streams 64-row
+// granules (rows AND their int64 codes) into a ring of shared-memory stages with
+// cp.async.bulk; 16 consumer warps run free of CTA-wide barriers: each takes its 4 rows of
+// the granule for lookup / commitment / output, then adds the rows whose code it owns to the
+// accumulator, and signals the stage empty on an mbarrier.  Warps drift apart, so uneven code
+// ownership averages out over granules instead of stalling a barrier.
 template <int D, int STAGES>
 __global__ void __launch_bounds__(kStatsThreads, 1)
 vq_gather_stats_smem_kernel(const float* __restrict__ x, const int64_t* __restrict__ index,
                             int64_t n_rows, int n_embed, const float* __restrict__ et,
                             float* __restrict__ out_q, int64_t q_row_stride,
                             float* __restrict__ stats, double* __restrict__ partials,
-                            int32_t* __restrict__ status_flag, int64_t n_tiles) {
+                            int32_t* __restrict__ status_flag) {
   constexpr int VPL = D / 32;                       // accumulator floats per lane
-  constexpr int C4 = D / 4;                         // float4 chunks per row
-  extern __shared__ __align__(16) float smem[];     // bulk copies need 16-byte alignment;
-                                                    // the stage offsets below are 128-byte multiples
+  constexpr int C4 = D / 4;                         // float4 chunks (= lanes) per row
+  constexpr int kRowsPerInstr = 32 / C4;            // rows one warp instruction covers
+  constexpr int kRowsPerWarp = kGranuleRows / kStatsWarps;   // 4
+  extern __shared__ __align__(16) float smem[];     // stage offsets below are 128-byte multiples
   float* acc = smem;                                // [K][D]
   float* cnt = acc + (size_t)n_embed * D;           // [K]
-  float* xs = cnt + ((n_embed + 31) & ~31);         // [STAGES][kHalfRows][D]
-  int* codes = reinterpret_cast<int*>(xs + STAGES * kHalfRows * D);   // [STAGES][kHalfRows]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(codes + STAGES * kHalfRows);
-  __shared__ double warp_part[kStatsWarps];
+  float* xs = cnt + ((n_embed + 31) & ~31);         // [STAGES][kGranuleRows][D]
+  long long* idx = reinterpret_cast<long long*>(xs + STAGES * kGranuleRows * D);   // [STAGES][kGranuleRows]
+  uint64_t* full = reinterpret_cast<uint64_t*>(idx + STAGES * kGranuleRows);
+  uint64_t* empty = full + STAGES;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < n_embed * D + ((n_embed + 31) & ~31); i += kStatsThreads) smem[i] = 0.f;
   if (tid == 0) {
-    for (int s = 0; s < STAGES; ++s)
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(st_s32(bars + s)));
+    for (int s = 0; s < STAGES; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(st_s32(full + s)));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(st_s32(empty + s)), "r"(kStatsWarps));
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  const int64_t my_tiles = (int64_t)blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  const int64_t total = 2 * my_tiles;               // granules this CTA walks
-  auto granule_row0 = [&](int64_t g) {
-    return ((int64_t)blockIdx.x + (g >> 1) * gridDim.x) * kGatherRows + (g & 1) * kHalfRows;
-  };
-  auto issue = [&](int64_t g) {                     // thread 0 only
-    const int s = (int)(g % STAGES);
-    const int64_t row0 = granule_row0(g);
-    int64_t rows = n_rows - row0;
-    rows = rows < 0 ? 0 : (rows > kHalfRows ? kHalfRows : rows);
-    const uint32_t bar = st_s32(bars + s);
-    if (rows > 0) {
-      const uint32_t bytes = (uint32_t)rows * D * 4u;
-      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-      asm volatile(
-          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-              "r"(st_s32(xs + (size_t)s * kHalfRows * D)),
-          "l"(x + row0 * D), "r"(bytes), "r"(bar) : "memory");
-    } else {
-      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-    }
-  };
-  auto load_code = [&](int64_t g) {                 // threads < kHalfRows
-    const int64_t row = granule_row0(g) + tid;
-    int c = -1;
-    if (row < n_rows) {
-      const int64_t v = __ldg(index + row);
-      if (v >= 0 && v < n_embed) c = (int)v;
-      else if (status_flag) atomicExch(status_flag, 1);
-    }
-    return c;
-  };
+  const int64_t n_granules = (n_rows + kGranuleRows - 1) / kGranuleRows;
+  const int64_t total = (int64_t)blockIdx.x < n_granules
+                            ? (n_granules - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
-  if (tid == 0)
-    for (int64_t g = 0; g < total && g < STAGES; ++g) issue(g);
-  int next_code = (tid < kHalfRows && total > 0) ? load_code(0) : -1;
-
-  float run[VPL];
-  int run_code = -1, run_len = 0;
-  auto flush_run = [&]() {
-    if (run_code >= 0) {
-      float* a = acc + (size_t)run_code * D + lane * VPL;
+  if (warp == kStatsWarps) {
+    // ===================== producer =====================
+    for (int64_t g = 0; g < total; ++g) {
+      const int s = (int)(g % STAGES);
+      const int64_t row0 = ((int64_t)blockIdx.x + g * gridDim.x) * kGranuleRows;
+      const int64_t left = n_rows - row0;
+      const int rows = (int)(left > kGranuleRows ? kGranuleRows : left);
+      st_mbar_wait(st_s32(empty + s), (uint32_t)(((g / STAGES) & 1) ^ 1));
+      float* xt = xs + (size_t)s * kGranuleRows * D;
+      long long* it = idx + s * kGranuleRows;
+      if (rows == kGranuleRows) {
+        if (lane == 0) {
+          const uint32_t bar = st_s32(full + s);
+          const uint32_t bytes = kGranuleRows * D * 4u + kGranuleRows * 8u;
+          asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+                           "r"(st_s32(xt)), "l"(x + row0 * D), "r"(kGranuleRows * D * 4u), "r"(bar) : "memory");
+          asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+                           "r"(st_s32(it)), "l"(index + row0), "r"(kGranuleRows * 8u), "r"(bar) : "memory");
+        }
+      } else {
+        // ragged last granule: plain copies by the whole warp (sizes need not be 16-byte multiples)
+        for (int e = lane; e < rows * C4; e += 32)
+          reinterpret_cast<float4*>(xt)[e] = __ldg(reinterpret_cast<const float4*>(x + row0 * D) + e);
+        for (int r = lane; r < kGranuleRows; r += 32) it[r] = r < rows ? index[row0 + r] : -1;
+        __syncwarp();
+        if (lane == 0) st_mbar_arrive(st_s32(full + s));
+      }
+    }
+  } else {
+    // ===================== consumers =====================
+    float run[VPL];
+    int run_code = -1, run_len = 0;
+    auto flush_run = [&]() {
+      if (run_code >= 0) {
+        float* a = acc + (size_t)run_code * D + lane * VPL;
 #pragma unroll
-      for (int v = 0; v < VPL; ++v) a[v] += run[v];
-      if (lane == 0) cnt[run_code] += (float)run_len;
-    }
-  };
-  double tile_sq = 0.0;                             // thread 0: commitment sum of the open tile
-
-  for (int64_t g = 0; g < total; ++g) {
-    const int s = (int)(g % STAGES);
-    const float* xt = xs + (size_t)s * kHalfRows * D;
-    int* ct = codes + s * kHalfRows;
-    const int64_t row0 = granule_row0(g);
-    int64_t rows64 = n_rows - row0;
-    const int rows_here = (int)(rows64 < 0 ? 0 : (rows64 > kHalfRows ? kHalfRows : rows64));
-    if (tid < kHalfRows) {
-      ct[tid] = next_code;
-      if (g + 1 < total) next_code = load_code(g + 1);       // overlaps this granule's work
-    }
-    st_mbar_wait(st_s32(bars + s), (uint32_t)((g / STAGES) & 1));
-    __syncthreads();
-    // lookup, commitment term, output
+        for (int v = 0; v < VPL; ++v) a[v] += run[v];
+        if (lane == 0) cnt[run_code] += (float)run_len;
+      }
+    };
     float sq = 0.f;
-#pragma unroll 2
-    for (int e = tid; e < kHalfRows * C4; e += kStatsThreads) {
-      const int r = e / C4, j = e % C4;
-      if (r < rows_here) {
-        const int c = ct[r];
-        const float4 xv = reinterpret_cast<const float4*>(xt + r * D)[j];
-        float4 q = c >= 0 ? __ldg(reinterpret_cast<const float4*>(et + (int64_t)c * D) + j)
-                          : make_float4(0.f, 0.f, 0.f, 0.f);
-        const float4 t = make_float4(q.x - xv.x, q.y - xv.y, q.z - xv.z, q.w - xv.w);
-        sq = fmaf(t.x, t.x, sq); sq = fmaf(t.y, t.y, sq); sq = fmaf(t.z, t.z, sq); sq = fmaf(t.w, t.w, sq);
-        q = make_float4(xv.x + t.x, xv.y + t.y, xv.z + t.z, xv.w + t.w);     // bottleneck.py:95
-        if (out_q) reinterpret_cast<float4*>(out_q + (row0 + r) * q_row_stride)[j] = q;
+    for (int64_t g = 0; g < total; ++g) {
+      const int s = (int)(g % STAGES);
+      const float* xt = xs + (size_t)s * kGranuleRows * D;
+      const long long* it = idx + s * kGranuleRows;
+      const int64_t row0 = ((int64_t)blockIdx.x + g * gridDim.x) * kGranuleRows;
+      const int64_t left = n_rows - row0;
+      const int rows_here = (int)(left > kGranuleRows ? kGranuleRows : left);
+      st_mbar_wait(st_s32(full + s), (uint32_t)((g / STAGES) & 1));
+      // lookup, commitment term, output for this warp's rows of the granule
+#pragma unroll
+      for (int k = 0; k < kRowsPerWarp; k += kRowsPerInstr) {
+        const int r = warp * kRowsPerWarp + k + lane / C4, j = lane % C4;
+        if (r < rows_here) {
+          const long long v = it[r];
+          const bool ok = v >= 0 && v < n_embed;
+          if (!ok && j == 0 && status_flag) atomicExch(status_flag, 1);
+          const float4 xv = reinterpret_cast<const float4*>(xt + r * D)[j];
+          float4 q = ok ? __ldg(reinterpret_cast<const float4*>(et + v * D) + j)
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4 t = make_float4(q.x - xv.x, q.y - xv.y, q.z - xv.z, q.w - xv.w);
+          sq = fmaf(t.x, t.x, sq); sq = fmaf(t.y, t.y, sq); sq = fmaf(t.z, t.z, sq); sq = fmaf(t.w, t.w, sq);
+          q = make_float4(xv.x + t.x, xv.y + t.y, xv.z + t.z, xv.w + t.w);     // bottleneck.py:95
+          if (out_q) reinterpret_cast<float4*>(out_q + (row0 + r) * q_row_stride)[j] = q;
+        }
       }
-    }
-    sq = warp_sum(sq);
-    if (lane == 0) warp_part[warp] = (double)sq;
-    // statistics: this warp adds the rows whose code it owns
+      // statistics: rows of a 32-row group that share a code this warp owns are grouped
+      // with match.any and summed in registers, then added to the accumulator once
 #pragma unroll 1
-    for (int grp = 0; grp < kHalfRows / 32; ++grp) {
-      // Rows of this 32-row group that share an owned code are grouped with match.any and
-      // summed in registers, so a popular code costs one accumulator update per group
-      // however its rows are interleaved with others.
-      const int c_l = ct[grp * 32 + lane];
-      const bool owned = c_l >= 0 && (c_l % kStatsWarps) == warp;
-      const unsigned peers = __match_any_sync(0xffffffffu, owned ? c_l : -1 - lane);
-      unsigned leaders = __ballot_sync(0xffffffffu, owned && lane == __ffs(peers) - 1);
-      while (leaders) {
-        const int src = __ffs(leaders) - 1;
-        leaders &= leaders - 1;
-        const unsigned members = __shfl_sync(0xffffffffu, peers, src);
-        const int c = __shfl_sync(0xffffffffu, c_l, src);
-        if (c != run_code) {
-          flush_run();
-          run_code = c; run_len = 0;
+      for (int grp = 0; grp < kGranuleRows / 32; ++grp) {
+        const long long v = it[grp * 32 + lane];
+        const int c_l = (grp * 32 + lane < rows_here && v >= 0 && v < n_embed) ? (int)v : -1;
+        const bool owned = c_l >= 0 && (c_l % kStatsWarps) == warp;
+        const unsigned peers = __match_any_sync(0xffffffffu, owned ? c_l : -1 - lane);
+        unsigned leaders = __ballot_sync(0xffffffffu, owned && lane == __ffs(peers) - 1);
+        while (leaders) {
+          const int src = __ffs(leaders) - 1;
+          leaders &= leaders - 1;
+          const unsigned members = __shfl_sync(0xffffffffu, peers, src);
+          const int c = __shfl_sync(0xffffffffu, c_l, src);
+          if (c != run_code) {
+            flush_run();
+            run_code = c; run_len = 0;
 #pragma unroll
-          for (int v = 0; v < VPL; ++v) run[v] = 0.f;
-        }
-        for (unsigned m = members; m; m &= m - 1) {
-          const float* xr = xt + (grp * 32 + __ffs(m) - 1) * D + lane * VPL;
+            for (int v2 = 0; v2 < VPL; ++v2) run[v2] = 0.f;
+          }
+          for (unsigned m = members; m; m &= m - 1) {
+            const float* xr = xt + (grp * 32 + __ffs(m) - 1) * D + lane * VPL;
 #pragma unroll
-          for (int v = 0; v < VPL; ++v) run[v] += xr[v];
+            for (int v2 = 0; v2 < VPL; ++v2) run[v2] += xr[v2];
+          }
+          run_len += __popc(members);
         }
-        run_len += __popc(members);
       }
+      __syncwarp();
+      if (lane == 0) st_mbar_arrive(st_s32(empty + s));       // this warp is done with the stage
     }
-    __syncthreads();          // every warp is done with this stage
-    if (tid == 0) {
-      double sum = 0.0;
-      for (int w = 0; w < kStatsWarps; ++w) sum += warp_part[w];
-      if (g & 1) partials[blockIdx.x + (g >> 1) * gridDim.x] = tile_sq + sum;
-      else tile_sq = sum;
-      if (g + STAGES < total) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        issue(g + STAGES);
+    flush_run();
+    sq = warp_sum(sq);
+    if (lane == 0 && sq != 0.f) atomicAdd(&partials[blockIdx.x], (double)sq);
+    asm volatile("bar.sync 1, %0;" ::"n"(kStatsWarps * 32) : "memory");   // consumers only
+    // one vector reduction per used code of this CTA
+    for (int k = warp; k < n_embed; k += kStatsWarps) {
+      const float n = cnt[k];
+      if (n > 0.f) {
+        if (lane == 0) atomicAdd(&stats[k], n);
+        if (lane < C4) atomicAdd(reinterpret_cast<float4*>(stats + n_embed + (int64_t)k * D) + lane,
+                                 reinterpret_cast<const float4*>(acc + (size_t)k * D)[lane]);
       }
-    }
-  }
-  flush_run();
-  __syncthreads();
-  // one vector reduction per used code of this CTA
-  for (int k = warp; k < n_embed; k += kStatsWarps) {
-    const float n = cnt[k];
-    if (n > 0.f) {
-      if (lane == 0) atomicAdd(&stats[k], n);
-      if (lane < C4) atomicAdd(reinterpret_cast<float4*>(stats + n_embed + (int64_t)k * D) + lane,
-                               reinterpret_cast<const float4*>(acc + (size_t)k * D)[lane]);
     }
   }
 }
@@ -562,11 +555,15 @@ int launch_gather_stats(const float* x, const isi_rows_layout& xl, const int64_t
   // rows are fully contiguous (one bulk copy per 64-row granule)
   const int stages = dim <= 64 ? 4 : 2;
   const size_t stats_smem = ((size_t)n_embed * dim + ((n_embed + 31) & ~31) +
-                             (size_t)stages * kHalfRows * dim) * 4 + stages * kHalfRows * 4 + 64;
+                             (size_t)stages * kGranuleRows * dim) * 4 + stages * kGranuleRows * 8 + 128;
   if (fast && x && stats && !counts_only && (dim == 32 || dim == 64 || dim == 128) &&
-      xl.row_stride == dim && stats_smem <= 220 * 1024) {
-    const int64_t want = (grid + 3) / 4;
+      xl.row_stride == dim && ((uintptr_t)index & 15) == 0 && stats_smem <= 220 * 1024) {
+    const int64_t granules = (n_rows + kGranuleRows - 1) / kGranuleRows;
+    const int64_t want = (granules + 7) / 8;
     const unsigned ctas = (unsigned)(want < kNumSms ? (want < 1 ? 1 : want) : kNumSms);
+    // per-CTA commitment sums are accumulated into the first `ctas` partial slots
+    cudaError_t em = cudaMemsetAsync(partials, 0, (size_t)grid * sizeof(double), stream);
+    if (em != cudaSuccess) return (int)em;
 #define ISI_STATS_CASE(DD, ST)                                                                  \
     case DD: {                                                                                  \
       cudaError_t e = cudaFuncSetAttribute(vq_gather_stats_smem_kernel<DD, ST>,                 \
@@ -574,8 +571,7 @@ int launch_gather_stats(const float* x, const isi_rows_layout& xl, const int64_t
                                            (int)stats_smem);                                    \
       if (e != cudaSuccess) return (int)e;                                                      \
       vq_gather_stats_smem_kernel<DD, ST><<<ctas, kStatsThreads, stats_smem, stream>>>(         \
-          x, index, n_rows, n_embed, p.et, out_q, ql.row_stride, stats, partials, status_flag,  \
-          grid);                                                                                \
+          x, index, n_rows, n_embed, p.et, out_q, ql.row_stride, stats, partials, status_flag); \
       break;                                                                                    \
     }
     switch (dim) { ISI_STATS_CASE(32, 4) ISI_STATS_CASE(64, 4) ISI_STATS_CASE(128, 2) }
