@@ -50,8 +50,10 @@ enum isi_assign_algo {
   ISI_ASSIGN_SIMT_FP32 = 1, /* CUDA-core FP32 FMA, any D / K / layout          */
   ISI_ASSIGN_TCGEN05 = 2,   /* tcgen05.mma kind::tf32, 3xTF32 split, TMEM accum; */
                             /* codebook streamed in 64-code tiles (D = 64, any K)  */
-  ISI_ASSIGN_TCGEN05_PAIR = 3 /* the same on a CTA pair (cta_group::2) with the    */
+  ISI_ASSIGN_TCGEN05_PAIR = 3, /* the same on a CTA pair (cta_group::2) with the   */
                             /* codebook resident in shared memory (D = 64, K<=512) */
+  ISI_ASSIGN_TCGEN05_PAIR_STREAM = 4 /* CTA pair, codebook streamed in 128-code    */
+                            /* tiles (D = 64 or 128, K <= 4096)                    */
 };
 
 /*

@@ -17,9 +17,9 @@ _LIB_PATH = pathlib.Path(__file__).resolve().parent / "libisi_b200.so"
 _lock = threading.Lock()
 _lib = None
 
-ASSIGN_AUTO, ASSIGN_SIMT_FP32, ASSIGN_TCGEN05, ASSIGN_TCGEN05_PAIR = 0, 1, 2, 3
+ASSIGN_AUTO, ASSIGN_SIMT_FP32, ASSIGN_TCGEN05, ASSIGN_TCGEN05_PAIR, ASSIGN_TCGEN05_PAIR_STREAM = range(5)
 _ALGOS = {"auto": ASSIGN_AUTO, "simt": ASSIGN_SIMT_FP32, "tcgen05": ASSIGN_TCGEN05,
-          "tcgen05_pair": ASSIGN_TCGEN05_PAIR}
+          "tcgen05_pair": ASSIGN_TCGEN05_PAIR, "tcgen05_pair_stream": ASSIGN_TCGEN05_PAIR_STREAM}
 
 
 class RowsLayout(ctypes.Structure):
@@ -151,7 +151,7 @@ def rows_layout(t: torch.Tensor) -> Optional[RowsLayout]:
 
 # kernels each entry point enqueues (for bench.py's `gpu_launches` claim)
 KERNELS_PER_CALL = {
-    "isi_vq_prepare_codebook": 3, "isi_vq_assign": 1, "isi_vq_gather_stats": 1,
+    "isi_vq_prepare_codebook": 4, "isi_vq_assign": 1, "isi_vq_gather_stats": 1,
     "isi_vq_finish": 1, "isi_vq_ema_update": 2, "isi_embed_code": 1, "isi_melif_forward": 1,
 }
 launch_counts = {name: 0 for name in KERNELS_PER_CALL}

@@ -14,6 +14,10 @@ bool assign_pair_supported(const isi_rows_layout&, int64_t, int, int);
 int launch_prepare_pair(const float*, int, int, const Prepared&, cudaStream_t);
 int launch_assign_pair(const float*, const isi_rows_layout&, int64_t, int, int, const Prepared&,
                        int64_t*, float*, cudaStream_t);
+bool assign_pstream_supported(const isi_rows_layout&, int64_t, int, int);
+int launch_prepare_pstream(const float*, int, int, const Prepared&, cudaStream_t);
+int launch_assign_pstream(const float*, const isi_rows_layout&, int64_t, int, int, const Prepared&,
+                          int64_t*, float*, cudaStream_t);
 size_t gather_workspace_bytes(int64_t);
 int launch_gather_stats(const float*, const isi_rows_layout&, const int64_t*, int64_t, int, int,
                         const Prepared&, float*, const isi_rows_layout&, float*, int, void*,
@@ -62,7 +66,9 @@ ISI_API int isi_vq_prepare_codebook(const float* embed, int dim, int n_embed, vo
   if (rc) return rc;
   rc = launch_prepare_tc(embed, dim, n_embed, p, (cudaStream_t)stream);
   if (rc) return rc;
-  return launch_prepare_pair(embed, dim, n_embed, p, (cudaStream_t)stream);
+  rc = launch_prepare_pair(embed, dim, n_embed, p, (cudaStream_t)stream);
+  if (rc) return rc;
+  return launch_prepare_pstream(embed, dim, n_embed, p, (cudaStream_t)stream);
 }
 
 ISI_API int isi_vq_assign(const float* x, const isi_rows_layout* xl, int64_t n_rows, int dim, int n_embed,
@@ -78,6 +84,11 @@ ISI_API int isi_vq_assign(const float* x, const isi_rows_layout* xl, int64_t n_r
   if (algo == ISI_ASSIGN_TCGEN05_PAIR || (algo == ISI_ASSIGN_AUTO && pair_ok))
     return launch_assign_pair(x, *xl, n_rows, dim, n_embed, p, out_index, out_score,
                               (cudaStream_t)stream);
+  const bool pstream_ok = !pair_ok && assign_pstream_supported(*xl, n_rows, dim, n_embed);
+  if (algo == ISI_ASSIGN_TCGEN05_PAIR_STREAM && !pstream_ok) return ISI_ERR_UNSUPPORTED;
+  if (algo == ISI_ASSIGN_TCGEN05_PAIR_STREAM || (algo == ISI_ASSIGN_AUTO && pstream_ok))
+    return launch_assign_pstream(x, *xl, n_rows, dim, n_embed, p, out_index, out_score,
+                                 (cudaStream_t)stream);
   if (algo == ISI_ASSIGN_TCGEN05 && !tc_ok) return ISI_ERR_UNSUPPORTED;
   if (algo == ISI_ASSIGN_TCGEN05 || (algo == ISI_ASSIGN_AUTO && tc_ok))
     return launch_assign_tc(x, *xl, n_rows, dim, n_embed, p, out_index, out_score,

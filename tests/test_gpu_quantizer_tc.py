@@ -95,3 +95,29 @@ def test_pair_kernel_nchw_ties_and_determinism():
     assert flat[5] == 17 and flat[6] == 0 and not ((flat == 300) | (flat == 511)).any()
     assert torch.equal(m.assign(view), ind)
     assert torch.equal(make(64, 512, embed, "tcgen05").eval().assign(view), ind)
+
+
+# ---- the streaming CTA-pair kernel: codebooks that do not fit in shared memory --------------
+@pytest.mark.parametrize("dim,n_embed,rows", [(64, 1000, 5000), (64, 4096, 8192), (128, 4096, 8192),
+                                              (128, 512, 4097), (128, 200, 20000), (64, 640, 33333)])
+def test_pair_stream_kernel_matches_fp64_outside_near_ties(dim, n_embed, rows):
+    embed = synthetic.synthetic_codebook(dim, n_embed)
+    x = synthetic.synthetic_features(rows, embed)
+    m = make(dim, n_embed, embed, "tcgen05_pair_stream").eval()
+    ind = m.assign(x.to(DEV))
+    near, flipped = assert_indices_match(ind, x, embed)
+    simt = make(dim, n_embed, embed, "simt").eval().assign(x.to(DEV))
+    agree = (simt == ind).float().mean().item()
+    print(f"[pair-stream] D={dim} K={n_embed} N={rows}: {near} near ties, {flipped} flipped vs FP64, "
+          f"agreement with the FP32 SIMT kernel {agree:.6f}")
+    assert agree > 0.999
+
+
+def test_pair_stream_kernel_nchw_view_d128():
+    embed = synthetic.synthetic_codebook(128, 1024)
+    x = synthetic.synthetic_features(4 * 48 * 24, embed).view(4, 48, 24, 128)
+    view = x.permute(0, 3, 1, 2).contiguous().to(DEV).permute(0, 2, 3, 1)
+    m = make(128, 1024, embed, "tcgen05_pair_stream").eval()
+    ind = m.assign(view)
+    assert_indices_match(ind, x.reshape(-1, 128), embed)
+    assert torch.equal(m.assign(view), ind)
