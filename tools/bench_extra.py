@@ -61,14 +61,19 @@ def cfg3():
 
 def cfg4():
     out = []
-    embed = synthetic.synthetic_codebook(128, 4096)
-    m = QuantizedBottleneck(128, 4096).to(DEV).eval()
-    m.embed.copy_(embed)
-    for n in (8192, 65536, 262144, 1048576):
-        x = synthetic.synthetic_features(n, embed, 5).to(DEV)
-        ms = timed(lambda: m.assign(x), iters=5, warmup=2)
-        out.append({"rows": n, "ms": ms, "algorithmic_tflops": 2.0 * n * 4096 * 128 / (ms * 1e-3) / 1e12,
-                    "kernel": "vq_assign_simt (D=128 is outside the tensor-core kernels' shape)"})
+    for dim, n_embed, algos in ((128, 4096, ("auto", "simt")), (64, 4096, ("auto", "tcgen05", "simt"))):
+        embed = synthetic.synthetic_codebook(dim, n_embed)
+        m = QuantizedBottleneck(dim, n_embed).to(DEV).eval()
+        m.embed.copy_(embed)
+        for n in (8192, 65536, 262144, 1048576):
+            x = synthetic.synthetic_features(n, embed, 5).to(DEV)
+            for algo in algos:
+                if algo == "simt" and n > 262144:
+                    continue
+                m.assign_algo = algo
+                ms = timed(lambda: m.assign(x), iters=5, warmup=2)
+                out.append({"dim": dim, "n_embed": n_embed, "rows": n, "algo": algo, "ms": ms,
+                            "algorithmic_tflops": 2.0 * n * n_embed * dim / (ms * 1e-3) / 1e12})
     return out
 
 
