@@ -235,8 +235,8 @@ vq_gather_rowmajor_kernel(const float* __restrict__ x, int64_t x_row_stride,
 // first summed in registers.  Global memory sees one vector reduction per (CTA, used code)
 // at the very end: 148 x 128 KB at most, instead of 256 B of atomics per row.
 // ---------------------------------------------------------------------------
-constexpr int kStatsWarps = 16;                     // consumer warps; one more warp produces
-constexpr int kStatsThreads = (kStatsWarps + 1) * 32;
+constexpr int kStatsWarps = 16;                     // consumer warps (+ producer + dispatcher)
+constexpr int kStatsThreads = (kStatsWarps + 2) * 32;
 constexpr int kGranuleRows = 64;                    // rows per pipeline stage
 
 __device__ __forceinline__ uint32_t st_s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -253,12 +253,22 @@ __device__ __forceinline__ void st_mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-// Rows must be fully contiguous ([N, D], row stride D).  A producer warp streams 64-row
-// granules (rows AND their int64 codes) into a ring of shared-memory stages with
-// cp.async.bulk; 16 consumer warps run free of CTA-wide barriers: each takes its 4 rows of
-// the granule for lookup / commitment / output, then adds the rows whose code it owns to the
-// accumulator, and signals the stage empty on an mbarrier.  Warps drift apart, so uneven code
-// ownership averages out over granules instead of stalling a barrier.
+// per-stage work lists: for every consumer warp the granule rows whose code it owns
+struct StageLists {
+  unsigned char row[kStatsWarps][kGranuleRows];     // row ids, grouped by owner
+  int count[kStatsWarps];
+};
+
+// Rows must be fully contiguous ([N, D], row stride D).  Three roles, no CTA-wide barrier:
+//  * a producer warp streams 64-row granules (rows AND their int64 codes) into a ring of
+//    shared-memory stages with cp.async.bulk;
+//  * a dispatcher warp turns each granule's codes into per-owner row lists (owner = code % 16;
+//    two match.any + prefix popcounts per granule);
+//  * 16 consumer warps each take 4 rows of the granule for lookup / commitment / output, then
+//    walk THEIR list and add those rows to the CTA-private [K, D] accumulator with plain
+//    ld/add/st -- a code is only ever touched by its owner, so there are no atomics and no
+//    conflicts -- and finally signal the stage empty.
+// Global memory sees one red.global.add.v4.f32 per (CTA, used code) at the very end.
 template <int D, int STAGES>
 __global__ void __launch_bounds__(kStatsThreads, 1)
 vq_gather_stats_smem_kernel(const float* __restrict__ x, const int64_t* __restrict__ index,
@@ -275,14 +285,17 @@ vq_gather_stats_smem_kernel(const float* __restrict__ x, const int64_t* __restri
   float* cnt = acc + (size_t)n_embed * D;           // [K]
   float* xs = cnt + ((n_embed + 31) & ~31);         // [STAGES][kGranuleRows][D]
   long long* idx = reinterpret_cast<long long*>(xs + STAGES * kGranuleRows * D);   // [STAGES][kGranuleRows]
-  uint64_t* full = reinterpret_cast<uint64_t*>(idx + STAGES * kGranuleRows);
-  uint64_t* empty = full + STAGES;
+  StageLists* lists = reinterpret_cast<StageLists*>(idx + STAGES * kGranuleRows);  // [STAGES]
+  uint64_t* full = reinterpret_cast<uint64_t*>(lists + STAGES);
+  uint64_t* ready = full + STAGES;
+  uint64_t* empty = ready + STAGES;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < n_embed * D + ((n_embed + 31) & ~31); i += kStatsThreads) smem[i] = 0.f;
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(st_s32(full + s)));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(st_s32(ready + s)));
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(st_s32(empty + s)), "r"(kStatsWarps));
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -292,14 +305,18 @@ vq_gather_stats_smem_kernel(const float* __restrict__ x, const int64_t* __restri
   const int64_t n_granules = (n_rows + kGranuleRows - 1) / kGranuleRows;
   const int64_t total = (int64_t)blockIdx.x < n_granules
                             ? (n_granules - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  auto rows_in = [&](int64_t g, int64_t& row0) {
+    row0 = ((int64_t)blockIdx.x + g * gridDim.x) * kGranuleRows;
+    const int64_t left = n_rows - row0;
+    return (int)(left > kGranuleRows ? kGranuleRows : left);
+  };
 
   if (warp == kStatsWarps) {
     // ===================== producer =====================
     for (int64_t g = 0; g < total; ++g) {
       const int s = (int)(g % STAGES);
-      const int64_t row0 = ((int64_t)blockIdx.x + g * gridDim.x) * kGranuleRows;
-      const int64_t left = n_rows - row0;
-      const int rows = (int)(left > kGranuleRows ? kGranuleRows : left);
+      int64_t row0;
+      const int rows = rows_in(g, row0);
       st_mbar_wait(st_s32(empty + s), (uint32_t)(((g / STAGES) & 1) ^ 1));
       float* xt = xs + (size_t)s * kGranuleRows * D;
       long long* it = idx + s * kGranuleRows;
@@ -322,26 +339,49 @@ vq_gather_stats_smem_kernel(const float* __restrict__ x, const int64_t* __restri
         if (lane == 0) st_mbar_arrive(st_s32(full + s));
       }
     }
+  } else if (warp == kStatsWarps + 1) {
+    // ===================== dispatcher =====================
+    for (int64_t g = 0; g < total; ++g) {
+      const int s = (int)(g % STAGES);
+      int64_t row0;
+      const int rows = rows_in(g, row0);
+      st_mbar_wait(st_s32(full + s), (uint32_t)((g / STAGES) & 1));
+      const long long* it = idx + s * kGranuleRows;
+      StageLists& L = lists[s];
+      int base = 0;        // rows of the first half already listed for this lane's owner
+#pragma unroll
+      for (int half = 0; half < kGranuleRows / 32; ++half) {
+        const int r = half * 32 + lane;
+        const long long v = it[r];
+        const bool ok = r < rows && v >= 0 && v < n_embed;
+        if (r < rows && !ok && status_flag) atomicExch(status_flag, 1);
+        const int owner = ok ? (int)(v % kStatsWarps) : -1 - lane;      // invalid rows match nobody
+        const unsigned peers = __match_any_sync(0xffffffffu, owner);
+        const int pos = __popc(peers & ((1u << lane) - 1));
+        if (half == 1 && ok) base = L.count[owner];
+        if (ok) L.row[owner][base + pos] = (unsigned char)r;
+        __syncwarp();
+        if (half == 0) {
+          // counts of the first half: written by group leaders, zero for owners without rows
+          if (lane < kStatsWarps) L.count[lane] = 0;
+          __syncwarp();
+          if (ok && pos == 0) L.count[owner] = __popc(peers);
+        } else if (ok && pos == 0) {
+          L.count[owner] = base + __popc(peers);
+        }
+        __syncwarp();
+      }
+      if (lane == 0) st_mbar_arrive(st_s32(ready + s));
+    }
   } else {
     // ===================== consumers =====================
-    float run[VPL];
-    int run_code = -1, run_len = 0;
-    auto flush_run = [&]() {
-      if (run_code >= 0) {
-        float* a = acc + (size_t)run_code * D + lane * VPL;
-#pragma unroll
-        for (int v = 0; v < VPL; ++v) a[v] += run[v];
-        if (lane == 0) cnt[run_code] += (float)run_len;
-      }
-    };
     float sq = 0.f;
     for (int64_t g = 0; g < total; ++g) {
       const int s = (int)(g % STAGES);
       const float* xt = xs + (size_t)s * kGranuleRows * D;
       const long long* it = idx + s * kGranuleRows;
-      const int64_t row0 = ((int64_t)blockIdx.x + g * gridDim.x) * kGranuleRows;
-      const int64_t left = n_rows - row0;
-      const int rows_here = (int)(left > kGranuleRows ? kGranuleRows : left);
+      int64_t row0;
+      const int rows_here = rows_in(g, row0);
       st_mbar_wait(st_s32(full + s), (uint32_t)((g / STAGES) & 1));
       // lookup, commitment term, output for this warp's rows of the granule
 #pragma unroll
@@ -350,7 +390,6 @@ vq_gather_stats_smem_kernel(const float* __restrict__ x, const int64_t* __restri
         if (r < rows_here) {
           const long long v = it[r];
           const bool ok = v >= 0 && v < n_embed;
-          if (!ok && j == 0 && status_flag) atomicExch(status_flag, 1);
           const float4 xv = reinterpret_cast<const float4*>(xt + r * D)[j];
           float4 q = ok ? __ldg(reinterpret_cast<const float4*>(et + v * D) + j)
                         : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -360,38 +399,23 @@ vq_gather_stats_smem_kernel(const float* __restrict__ x, const int64_t* __restri
           if (out_q) reinterpret_cast<float4*>(out_q + (row0 + r) * q_row_stride)[j] = q;
         }
       }
-      // statistics: rows of a 32-row group that share a code this warp owns are grouped
-      // with match.any and summed in registers, then added to the accumulator once
-#pragma unroll 1
-      for (int grp = 0; grp < kGranuleRows / 32; ++grp) {
-        const long long v = it[grp * 32 + lane];
-        const int c_l = (grp * 32 + lane < rows_here && v >= 0 && v < n_embed) ? (int)v : -1;
-        const bool owned = c_l >= 0 && (c_l % kStatsWarps) == warp;
-        const unsigned peers = __match_any_sync(0xffffffffu, owned ? c_l : -1 - lane);
-        unsigned leaders = __ballot_sync(0xffffffffu, owned && lane == __ffs(peers) - 1);
-        while (leaders) {
-          const int src = __ffs(leaders) - 1;
-          leaders &= leaders - 1;
-          const unsigned members = __shfl_sync(0xffffffffu, peers, src);
-          const int c = __shfl_sync(0xffffffffu, c_l, src);
-          if (c != run_code) {
-            flush_run();
-            run_code = c; run_len = 0;
+      // statistics: walk this warp's list of owned rows
+      st_mbar_wait(st_s32(ready + s), (uint32_t)((g / STAGES) & 1));
+      const StageLists& L = lists[s];
+      const int n_mine = L.count[warp];
+#pragma unroll 2
+      for (int k = 0; k < n_mine; ++k) {
+        const int r = L.row[warp][k];
+        const int c = (int)it[r];
+        float* a = acc + (size_t)c * D + lane * VPL;
+        const float* xr = xt + r * D + lane * VPL;
 #pragma unroll
-            for (int v2 = 0; v2 < VPL; ++v2) run[v2] = 0.f;
-          }
-          for (unsigned m = members; m; m &= m - 1) {
-            const float* xr = xt + (grp * 32 + __ffs(m) - 1) * D + lane * VPL;
-#pragma unroll
-            for (int v2 = 0; v2 < VPL; ++v2) run[v2] += xr[v2];
-          }
-          run_len += __popc(members);
-        }
+        for (int v2 = 0; v2 < VPL; ++v2) a[v2] += xr[v2];
+        if (lane == 0) cnt[c] += 1.f;
       }
       __syncwarp();
       if (lane == 0) st_mbar_arrive(st_s32(empty + s));       // this warp is done with the stage
     }
-    flush_run();
     sq = warp_sum(sq);
     if (lane == 0 && sq != 0.f) atomicAdd(&partials[blockIdx.x], (double)sq);
     asm volatile("bar.sync 1, %0;" ::"n"(kStatsWarps * 32) : "memory");   // consumers only
@@ -555,7 +579,8 @@ int launch_gather_stats(const float* x, const isi_rows_layout& xl, const int64_t
   // rows are fully contiguous (one bulk copy per 64-row granule)
   const int stages = dim <= 64 ? 4 : 2;
   const size_t stats_smem = ((size_t)n_embed * dim + ((n_embed + 31) & ~31) +
-                             (size_t)stages * kGranuleRows * dim) * 4 + stages * kGranuleRows * 8 + 128;
+                             (size_t)stages * kGranuleRows * dim) * 4 + stages * kGranuleRows * 8 +
+                            stages * sizeof(StageLists) + 3 * stages * 8 + 64;
   if (fast && x && stats && !counts_only && (dim == 32 || dim == 64 || dim == 128) &&
       xl.row_stride == dim && ((uintptr_t)index & 15) == 0 && stats_smem <= 220 * 1024) {
     const int64_t granules = (n_rows + kGranuleRows - 1) / kGranuleRows;
