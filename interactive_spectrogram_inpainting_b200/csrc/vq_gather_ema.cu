@@ -376,6 +376,16 @@ vq_gather_stats_smem_kernel(const float* __restrict__ x, const int64_t* __restri
   } else {
     // ===================== consumers =====================
     float sq = 0.f;
+    float sticky[VPL];
+    int sticky_code = -1, sticky_len = 0, misses = 0;
+    auto flush_sticky = [&]() {
+      if (sticky_code >= 0) {
+        float* a = acc + (size_t)sticky_code * D + lane * VPL;
+#pragma unroll
+        for (int v2 = 0; v2 < VPL; ++v2) a[v2] += sticky[v2];
+        if (lane == 0) cnt[sticky_code] += (float)sticky_len;
+      }
+    };
     for (int64_t g = 0; g < total; ++g) {
       const int s = (int)(g % STAGES);
       const float* xt = xs + (size_t)s * kGranuleRows * D;
@@ -403,19 +413,35 @@ vq_gather_stats_smem_kernel(const float* __restrict__ x, const int64_t* __restri
       st_mbar_wait(st_s32(ready + s), (uint32_t)((g / STAGES) & 1));
       const StageLists& L = lists[s];
       const int n_mine = L.count[warp];
+      // A "sticky" code is accumulated in registers (a popular code would otherwise serialise
+      // on the read-modify-write of its accumulator row); every other code goes straight to
+      // shared memory, where distinct rows pipeline.  After 8 consecutive misses the sticky
+      // slot is flushed and handed to the current code.
 #pragma unroll 2
       for (int k = 0; k < n_mine; ++k) {
         const int r = L.row[warp][k];
         const int c = (int)it[r];
-        float* a = acc + (size_t)c * D + lane * VPL;
         const float* xr = xt + r * D + lane * VPL;
+        if (c == sticky_code) {
 #pragma unroll
-        for (int v2 = 0; v2 < VPL; ++v2) a[v2] += xr[v2];
-        if (lane == 0) cnt[c] += 1.f;
+          for (int v2 = 0; v2 < VPL; ++v2) sticky[v2] += xr[v2];
+          ++sticky_len; misses = 0;
+        } else if (++misses > 8 || sticky_code < 0) {
+          flush_sticky();
+          sticky_code = c; sticky_len = 1; misses = 0;
+#pragma unroll
+          for (int v2 = 0; v2 < VPL; ++v2) sticky[v2] = xr[v2];
+        } else {
+          float* a = acc + (size_t)c * D + lane * VPL;
+#pragma unroll
+          for (int v2 = 0; v2 < VPL; ++v2) a[v2] += xr[v2];
+          if (lane == 0) cnt[c] += 1.f;
+        }
       }
       __syncwarp();
       if (lane == 0) st_mbar_arrive(st_s32(empty + s));       // this warp is done with the stage
     }
+    flush_sticky();
     sq = warp_sum(sq);
     if (lane == 0 && sq != 0.f) atomicAdd(&partials[blockIdx.x], (double)sq);
     asm volatile("bar.sync 1, %0;" ::"n"(kStatsWarps * 32) : "memory");   // consumers only
