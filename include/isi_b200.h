@@ -190,6 +190,11 @@ typedef struct isi_melif_params {
   int32_t channels_last;    /* 0: out is [B,2,F,T'] planes (the reference layout);   */
                             /* 1: the same logical tensor in torch channels_last     */
                             /*    storage [B,F,T',2] (what the cuDNN convs consume)  */
+  /* fused epilogue (both live in GANsynth_pytorch in the reference):       */
+  int32_t mask_phase;       /* 1: channel 1 := 0 where channel 0 < mask_threshold (the       */
+  float mask_threshold;     /*    masked-phase transform, extract_code.py:178-181)           */
+  float out_scale[2];       /* then channel c := c * out_scale[c] + out_bias[c] (the         */
+  float out_bias[2];        /*    DataNormalizer affine of vqvae.py:254-255); 1 / 0 = off    */
 } isi_melif_params;
 
 /*

@@ -34,7 +34,9 @@ class MelifParams(ctypes.Structure):
                 ("mel_width", ctypes.c_int32), ("safelog_eps", ctypes.c_float),
                 ("window", ctypes.c_void_p), ("twiddle", ctypes.c_void_p),
                 ("mel_start", ctypes.c_void_p), ("mel_count", ctypes.c_void_p),
-                ("mel_weight", ctypes.c_void_p), ("channels_last", ctypes.c_int32)]
+                ("mel_weight", ctypes.c_void_p), ("channels_last", ctypes.c_int32),
+                ("mask_phase", ctypes.c_int32), ("mask_threshold", ctypes.c_float),
+                ("out_scale", ctypes.c_float * 2), ("out_bias", ctypes.c_float * 2)]
 
 
 EXPORTS = {

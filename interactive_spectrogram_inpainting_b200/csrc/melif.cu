@@ -215,6 +215,8 @@ melif_kernel(const float* __restrict__ audio, int64_t n_samples, isi_melif_param
           emit_mel<FB>(zA, P::kPitchA, row_bin[r], row_cnt[r], row_cnt_warp[r], row_w[r], f0 == 0, eps, v0, v1);
         else
           emit_linear<FB>(zA, P::kPitchA, row_bin[r], v0, v1);
+        apply_epilogue<FB>(v0, v1, p.mask_phase != 0, p.mask_threshold, p.out_scale[0], p.out_bias[0],
+                           p.out_scale[1], p.out_bias[1]);
         if (p.channels_last) {
           // [B, F, T', 2]: the FB time steps of both channels are one contiguous run
           float* d = out + (((int64_t)note_idx * M + row) * p.n_frames + f0) * 2;

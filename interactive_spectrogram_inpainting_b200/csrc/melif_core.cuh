@@ -334,5 +334,17 @@ ISI_HD void emit_mel(const cpx* z, int pitch, int bin0, int count, int count_uni
   }
 }
 
+// ---- fused epilogue: masked-phase transform, then the per-channel affine normalisation ----
+template <int FB>
+ISI_HD void apply_epilogue(float* v0, float* v1, bool mask_phase, float mask_threshold, float s0,
+                           float b0, float s1, float b1) {
+#pragma unroll
+  for (int fb = 0; fb < FB; ++fb) {
+    const float ph = (mask_phase && v0[fb] < mask_threshold) ? 0.f : v1[fb];
+    v0[fb] = fmaf(v0[fb], s0, b0);
+    v1[fb] = fmaf(ph, s1, b1);
+  }
+}
+
 }  // namespace melif
 }  // namespace isi

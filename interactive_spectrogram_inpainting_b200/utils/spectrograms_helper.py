@@ -92,7 +92,9 @@ class SpectrogramsHelper(nn.Module):
                  window_length: int = 2048, safelog_eps: float = 1e-6, *,
                  pad_left: Optional[int] = None, n_frames: Optional[int] = None,
                  drop_bin: str = "dc", window_periodic: bool = True,
-                 channels_last: bool = False):
+                 channels_last: bool = False,
+                 masked_phase_threshold: Optional[float] = None,
+                 output_affine=None):
         super().__init__()
         if n_fft not in SUPPORTED_N_FFT:
             raise ValueError(f"n_fft must be one of {SUPPORTED_N_FFT}, got {n_fft}")
@@ -111,6 +113,13 @@ class SpectrogramsHelper(nn.Module):
         # True: to_spectrogram returns the same [B,2,F,T'] tensor in torch.channels_last
         # storage, which is what the cuDNN conv encoder wants (no layout-conversion kernels)
         self.channels_last = channels_last
+        # Fused epilogue (both are GANsynth_pytorch features the reference applies right after
+        # the transform): the masked-phase transform -- IF := 0 where the log-magnitude is below
+        # a threshold (extract_code.py:178-181, train_vqvae.py:586-589) -- and then a per-channel
+        # affine ``((scale0, bias0), (scale1, bias1))``, the shape of DataNormalizer.normalize
+        # (vqvae.py:254-255).  None = off.
+        self.masked_phase_threshold = masked_phase_threshold
+        self.output_affine = output_affine
 
         w = torch.hann_window(window_length, periodic=window_periodic, dtype=torch.float64)
         if window_length < n_fft:
@@ -140,6 +149,11 @@ class SpectrogramsHelper(nn.Module):
         p.window, p.twiddle = self.window.data_ptr(), self.twiddle.data_ptr()
         p.mel_start = p.mel_count = p.mel_weight = None
         p.channels_last = 1 if self.channels_last else 0
+        p.mask_phase = 0 if self.masked_phase_threshold is None else 1
+        p.mask_threshold = 0.0 if self.masked_phase_threshold is None else float(self.masked_phase_threshold)
+        affine = self.output_affine or ((1.0, 0.0), (1.0, 0.0))
+        for c in range(2):
+            p.out_scale[c], p.out_bias[c] = float(affine[c][0]), float(affine[c][1])
         return p
 
     def to_spectrogram(self, audio: torch.Tensor) -> torch.Tensor:

@@ -184,6 +184,21 @@ def to_spectrogram(audio: torch.Tensor, cfg: FrontEndConfig = FrontEndConfig()
     return linear_to_mel(spec, cfg) if cfg.use_mel_scale else spec
 
 
+def epilogue(spec: torch.Tensor, masked_phase_threshold: Optional[float] = None,
+             output_affine=None) -> torch.Tensor:
+    """What the reference applies right after the transform: the masked-phase transform
+    (IF := 0 where log-magnitude < threshold; extract_code.py:178-181) and then a per-channel
+    affine normalisation ``((scale0, bias0), (scale1, bias1))`` (vqvae.py:254-255).  Both live
+    in GANsynth_pytorch: unpinned, hence parameters."""
+    out = spec.clone()
+    if masked_phase_threshold is not None:
+        out[:, 1] = torch.where(spec[:, 0] < masked_phase_threshold, torch.zeros_like(spec[:, 1]), spec[:, 1])
+    if output_affine is not None:
+        for c in range(2):
+            out[:, c] = out[:, c] * output_affine[c][0] + output_affine[c][1]
+    return out
+
+
 def stability_mask(audio: torch.Tensor, cfg: FrontEndConfig = FrontEndConfig(),
                    wrap_margin: float = 1e-2, mag_floor: float = 1e-4) -> torch.Tensor:
     """bool ``[B, n_freq, frames]``: True where the IF channel is numerically

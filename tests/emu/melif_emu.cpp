@@ -15,7 +15,8 @@ template <int NFFT, int FB, int NT, bool MEL>
 static void emulate(const float* audio, int64_t n_notes, int64_t n_samples, int hop, int pad_left,
                     int n_frames, int drop_dc, int use_mel, int mel_width, float eps,
                     const float* window, const float* twiddle, const int32_t* mel_start,
-                    const int32_t* mel_count, const float* mel_weight, float* out, int seg_frames) {
+                    const int32_t* mel_count, const float* mel_weight, float* out, int seg_frames,
+                    int mask_phase, float mask_threshold, const float* affine) {
   using P = Plan<NFFT>;
   constexpr int M = P::M, IPT = (M / 2) / NT, RPT = M / NT, kGroups = NT / 64;
   const cpx* tw = reinterpret_cast<const cpx*>(twiddle);
@@ -80,6 +81,7 @@ static void emulate(const float* audio, int64_t n_notes, int64_t n_samples, int 
             float v0[FB], v1[FB];
             if (MEL) emit_mel<FB>(zA.data(), P::kPitchA, bin0, cnt, kMaxMelWidth, w, f0 == 0, eps, v0, v1);
             else     emit_linear<FB>(zA.data(), P::kPitchA, bin0, v0, v1);
+            apply_epilogue<FB>(v0, v1, mask_phase != 0, mask_threshold, affine[0], affine[1], affine[2], affine[3]);
             for (int fb = 0; fb < nf; ++fb) {
               out0[(int64_t)row * n_frames + f0 + fb] = v0[fb];
               out1[(int64_t)row * n_frames + f0 + fb] = v1[fb];
@@ -93,9 +95,10 @@ extern "C" int melif_emulate(const float* audio, int64_t n_notes, int64_t n_samp
                              int hop, int pad_left, int n_frames, int drop_dc, int use_mel,
                              int mel_width, float eps, const float* window, const float* twiddle,
                              const int32_t* mel_start, const int32_t* mel_count,
-                             const float* mel_weight, float* out, int seg_frames) {
+                             const float* mel_weight, float* out, int seg_frames, int mask_phase,
+                             float mask_threshold, const float* affine) {
 #define ARGS audio, n_notes, n_samples, hop, pad_left, n_frames, drop_dc, use_mel, mel_width, eps, \
-             window, twiddle, mel_start, mel_count, mel_weight, out, seg_frames
+             window, twiddle, mel_start, mel_count, mel_weight, out, seg_frames, mask_phase, mask_threshold, affine
   if (seg_frames <= 0) seg_frames = (n_frames + 3) / 4 * 4;
 #define CASE(N, FB, NT) case N: if (use_mel) emulate<N, FB, NT, true>(ARGS); else emulate<N, FB, NT, false>(ARGS); return 0;
   switch (n_fft) {

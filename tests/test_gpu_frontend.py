@@ -83,3 +83,14 @@ def test_small_batches_are_split_into_frame_segments_identically():
     whole = helper.to_spectrogram(audio)
     for i in (0, 7, 299):
         assert torch.equal(helper.to_spectrogram(audio[i:i + 1])[0], whole[i])
+
+
+def test_fused_masked_phase_and_normaliser_epilogue():
+    audio = synthetic.synthetic_notes(2)
+    kw = dict(masked_phase_threshold=-3.0, output_affine=((0.1, 0.5), (2.0, -0.25)))
+    for cl in (False, True):
+        plain = MelSpectrogramsHelper(channels_last=cl).to(DEV).to_spectrogram(audio.to(DEV))
+        fused = MelSpectrogramsHelper(channels_last=cl, **kw).to(DEV).to_spectrogram(audio.to(DEV))
+        want = fo.epilogue(plain.cpu(), **kw)
+        assert torch.allclose(fused.cpu(), want, rtol=0, atol=1e-6)
+        assert (fused[:, 1][plain[:, 0] < -3.0] == -0.25).all()

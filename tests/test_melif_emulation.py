@@ -46,7 +46,11 @@ def _run(emu, helper, audio, seg_frames=0):
                            helper.n_fft, helper.hop_length, helper.pad_left, frames,
                            1 if helper.drop_bin == "dc" else 0, int(helper.use_mel_scale), width,
                            ctypes.c_float(helper.safelog_eps), ptr(win), ptr(tw), *mel_args,
-                           ptr(out), seg_frames)
+                           ptr(out), seg_frames,
+                           0 if helper.masked_phase_threshold is None else 1,
+                           ctypes.c_float(helper.masked_phase_threshold or 0.0),
+                           ptr(np.array([v for pair in (helper.output_affine or ((1, 0), (1, 0))) for v in pair],
+                                        dtype=np.float32)))
     assert rc == 0
     return torch.from_numpy(out)
 
@@ -123,6 +127,16 @@ def test_emulated_segments_equal_whole_note(emu):
     whole = _run(emu, helper, audio)
     for seg in (16, 44, 64):
         assert torch.equal(_run(emu, helper, audio, seg_frames=seg), whole)
+
+
+def test_emulated_fused_epilogue_matches_oracle(emu):
+    audio = synthetic.synthetic_notes(1)
+    kw = dict(masked_phase_threshold=-3.0, output_affine=((0.1, 0.5), (2.0, -0.25)))
+    got = _run(emu, sh.MelSpectrogramsHelper(**kw), audio)
+    plain = _run(emu, sh.MelSpectrogramsHelper(), audio)
+    want = fo.epilogue(plain, **kw)
+    assert torch.allclose(got, want, rtol=0, atol=1e-6)
+    assert (got[:, 1][plain[:, 0] < -3.0] == -0.25).all()      # masked phase -> bias only
 
 
 def test_emulated_kernel_nyquist_knob(emu):
