@@ -4,6 +4,7 @@
 // Replaces bottleneck.py:75-100,103-104 of the reference; see include/isi_b200.h
 // for the statement-by-statement mapping.
 #include "common.cuh"
+#include "umma.cuh"
 
 namespace isi {
 
@@ -239,20 +240,6 @@ constexpr int kStatsWarps = 16;                     // consumer warps (+ produce
 constexpr int kStatsThreads = (kStatsWarps + 2) * 32;
 constexpr int kGranuleRows = 64;                    // rows per pipeline stage
 
-__device__ __forceinline__ uint32_t st_s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void st_mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "W_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@p bra D_%=;\n\t"
-      "bra W_%=;\n\t"
-      "D_%=:\n\t}" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void st_mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-
 // per-stage work lists: for every consumer warp the granule rows whose code it owns
 struct StageLists {
   unsigned char row[kStatsWarps][kGranuleRows];     // row ids, grouped by owner
@@ -294,9 +281,9 @@ vq_gather_stats_smem_kernel(const float* __restrict__ x, const int64_t* __restri
   for (int i = tid; i < n_embed * D + ((n_embed + 31) & ~31); i += kStatsThreads) smem[i] = 0.f;
   if (tid == 0) {
     for (int s = 0; s < STAGES; ++s) {
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(st_s32(full + s)));
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(st_s32(ready + s)));
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(st_s32(empty + s)), "r"(kStatsWarps));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(umma::s32(full + s)));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(umma::s32(ready + s)));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(umma::s32(empty + s)), "r"(kStatsWarps));
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -317,18 +304,18 @@ vq_gather_stats_smem_kernel(const float* __restrict__ x, const int64_t* __restri
       const int s = (int)(g % STAGES);
       int64_t row0;
       const int rows = rows_in(g, row0);
-      st_mbar_wait(st_s32(empty + s), (uint32_t)(((g / STAGES) & 1) ^ 1));
+      umma::mbar_wait(umma::s32(empty + s), (uint32_t)(((g / STAGES) & 1) ^ 1));
       float* xt = xs + (size_t)s * kGranuleRows * D;
       long long* it = idx + s * kGranuleRows;
       if (rows == kGranuleRows) {
         if (lane == 0) {
-          const uint32_t bar = st_s32(full + s);
+          const uint32_t bar = umma::s32(full + s);
           const uint32_t bytes = kGranuleRows * D * 4u + kGranuleRows * 8u;
           asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
           asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-                           "r"(st_s32(xt)), "l"(x + row0 * D), "r"(kGranuleRows * D * 4u), "r"(bar) : "memory");
+                           "r"(umma::s32(xt)), "l"(x + row0 * D), "r"(kGranuleRows * D * 4u), "r"(bar) : "memory");
           asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
-                           "r"(st_s32(it)), "l"(index + row0), "r"(kGranuleRows * 8u), "r"(bar) : "memory");
+                           "r"(umma::s32(it)), "l"(index + row0), "r"(kGranuleRows * 8u), "r"(bar) : "memory");
         }
       } else {
         // ragged last granule: plain copies by the whole warp (sizes need not be 16-byte multiples)
@@ -336,7 +323,7 @@ vq_gather_stats_smem_kernel(const float* __restrict__ x, const int64_t* __restri
           reinterpret_cast<float4*>(xt)[e] = __ldg(reinterpret_cast<const float4*>(x + row0 * D) + e);
         for (int r = lane; r < kGranuleRows; r += 32) it[r] = r < rows ? index[row0 + r] : -1;
         __syncwarp();
-        if (lane == 0) st_mbar_arrive(st_s32(full + s));
+        if (lane == 0) umma::mbar_arrive(umma::s32(full + s));
       }
     }
   } else if (warp == kStatsWarps + 1) {
@@ -345,7 +332,7 @@ vq_gather_stats_smem_kernel(const float* __restrict__ x, const int64_t* __restri
       const int s = (int)(g % STAGES);
       int64_t row0;
       const int rows = rows_in(g, row0);
-      st_mbar_wait(st_s32(full + s), (uint32_t)((g / STAGES) & 1));
+      umma::mbar_wait(umma::s32(full + s), (uint32_t)((g / STAGES) & 1));
       const long long* it = idx + s * kGranuleRows;
       StageLists& L = lists[s];
       int base = 0;        // rows of the first half already listed for this lane's owner
@@ -371,7 +358,7 @@ vq_gather_stats_smem_kernel(const float* __restrict__ x, const int64_t* __restri
         }
         __syncwarp();
       }
-      if (lane == 0) st_mbar_arrive(st_s32(ready + s));
+      if (lane == 0) umma::mbar_arrive(umma::s32(ready + s));
     }
   } else {
     // ===================== consumers =====================
@@ -392,7 +379,7 @@ vq_gather_stats_smem_kernel(const float* __restrict__ x, const int64_t* __restri
       const long long* it = idx + s * kGranuleRows;
       int64_t row0;
       const int rows_here = rows_in(g, row0);
-      st_mbar_wait(st_s32(full + s), (uint32_t)((g / STAGES) & 1));
+      umma::mbar_wait(umma::s32(full + s), (uint32_t)((g / STAGES) & 1));
       // lookup, commitment term, output for this warp's rows of the granule
 #pragma unroll
       for (int k = 0; k < kRowsPerWarp; k += kRowsPerInstr) {
@@ -410,7 +397,7 @@ vq_gather_stats_smem_kernel(const float* __restrict__ x, const int64_t* __restri
         }
       }
       // statistics: walk this warp's list of owned rows
-      st_mbar_wait(st_s32(ready + s), (uint32_t)((g / STAGES) & 1));
+      umma::mbar_wait(umma::s32(ready + s), (uint32_t)((g / STAGES) & 1));
       const StageLists& L = lists[s];
       const int n_mine = L.count[warp];
       // A "sticky" code is accumulated in registers (a popular code would otherwise serialise
@@ -439,7 +426,7 @@ vq_gather_stats_smem_kernel(const float* __restrict__ x, const int64_t* __restri
         }
       }
       __syncwarp();
-      if (lane == 0) st_mbar_arrive(st_s32(empty + s));       // this warp is done with the stage
+      if (lane == 0) umma::mbar_arrive(umma::s32(empty + s));       // this warp is done with the stage
     }
     flush_sticky();
     sq = warp_sum(sq);
