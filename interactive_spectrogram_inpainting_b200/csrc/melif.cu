@@ -65,7 +65,7 @@ __host__ __device__ inline MelifSmem melif_smem_layout(int hop) {
   using P = Plan<NFFT>;
   MelifSmem s;
   int off = 0;
-  s.tw = off;    off += (NFFT / 2) * 8;                     // W_M^e, e < M
+  s.tw = off;    off += (NFFT / 2) * 8;                     // FFT twiddles (fft_table_source)
   s.win = off;   off += NFFT * 4;
   s.stage = off; off += (((FB - 1) * hop + NFFT + 3) / 4) * 16;
   s.za = off;    off += FB * P::kPitchA * 8;                // FFT workspace, spectrum, polar values
@@ -106,7 +106,7 @@ melif_kernel(const float* __restrict__ audio, int64_t n_samples, isi_melif_param
 
   // ---- one-time setup: tables to shared memory, per-thread constants to registers ----
   const cpx* tw_global = reinterpret_cast<const cpx*>(p.twiddle);     // W_N^j, j < N
-  for (int i = tid; i < M; i += NT) twm[i] = tw_global[2 * i];
+  for (int i = tid; i < M; i += NT) twm[i] = tw_global[fft_table_source<P>(i)];
   for (int i = tid; i < NFFT; i += NT) win[i] = p.window[i];
   if (tid == 0) {
     mbar_init(bar, 1);
@@ -115,24 +115,11 @@ melif_kernel(const float* __restrict__ audio, int64_t n_samples, isi_melif_param
   cpx w_item[IPT];
 #pragma unroll
   for (int i = 0; i < IPT; ++i) w_item[i] = tw_global[tid + i * NT];
-  int row_bin[RPT], row_cnt[RPT], row_cnt_warp[RPT];
-  float row_w[RPT][MEL ? kMaxMelWidth : 1];
-#pragma unroll
-  for (int r = 0; r < RPT; ++r) {
-    const int row = tid + r * NT;
-    row_cnt[r] = 0;
-    row_bin[r] = row + dc;
-    row_cnt_warp[r] = 0;
-    if (MEL) {
-      row_bin[r] = p.mel_start[row] + dc;
-      row_cnt[r] = p.mel_count[row];
-#pragma unroll
-      for (int i = 0; i < kMaxMelWidth; ++i)
-        row_w[r][i] = (i < p.mel_width) ? p.mel_weight[(int64_t)row * p.mel_width + i] : 0.f;
-      row_cnt_warp[r] = __reduce_max_sync(0xffffffffu, row_cnt[r]);
-    }
-  }
-  BinState sa[IPT], sb[IPT], sc{1.f, 0.f};
+  // Per-row band constants (first bin, length, weights) are NOT kept in registers across the
+  // transform (they would spill): each batch re-reads them from the L1-resident tables ahead
+  // of the barrier that precedes emit.
+  const bool w_vec = MEL && p.mel_width == kMaxMelWidth && (reinterpret_cast<uintptr_t>(p.mel_weight) & 15) == 0;
+  BinState sa[IPT], sb[IPT];
 #pragma unroll
   for (int i = 0; i < IPT; ++i) { sa[i] = BinState{1.f, 0.f}; sb[i] = BinState{1.f, 0.f}; }
   __syncthreads();
@@ -201,18 +188,45 @@ melif_kernel(const float* __restrict__ audio, int64_t n_samples, isi_melif_param
     for (int fb = 0; fb < nf; ++fb) {
 #pragma unroll
       for (int i = 0; i < IPT; ++i)
-        polar_item<P, MEL>(tid + i * NT, zA + fb * P::kPitchA, w_item[i],
-                           lookback || (f0 + fb == 0), eps, sa[i], sb[i], sc);
+        if (i == 0)
+          polar_item<P, MEL, true>(tid, zA + fb * P::kPitchA, w_item[0], dc ? M : 0,
+                                   lookback || (f0 + fb == 0), eps, sa[0], sb[0]);
+        else
+          polar_item<P, MEL, false>(tid + i * NT, zA + fb * P::kPitchA, w_item[i], 0,
+                                    lookback || (f0 + fb == 0), eps, sa[i], sb[i]);
     }
     if (!lookback) {
+      float row_w[RPT][MEL ? kMaxMelWidth : 1];
+      int row_bin[RPT], row_cnt[RPT];
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) {
+        const int row = tid + r * NT;
+        row_bin[r] = row + dc;
+        row_cnt[r] = 0;
+        if (MEL) {
+          row_bin[r] = __ldg(p.mel_start + row) + dc;
+          row_cnt[r] = __ldg(p.mel_count + row);
+          if (w_vec) {
+            const float4* wt = reinterpret_cast<const float4*>(p.mel_weight) + (int64_t)row * 2;
+            const float4 a = __ldg(wt), c = __ldg(wt + 1);
+            row_w[r][0] = a.x; row_w[r][1] = a.y; row_w[r][2] = a.z; row_w[r][3] = a.w;
+            row_w[r][4] = c.x; row_w[r][5] = c.y; row_w[r][6] = c.z; row_w[r][7] = c.w;
+          } else {
+#pragma unroll
+            for (int i = 0; i < kMaxMelWidth; ++i)
+              row_w[r][i] = (i < p.mel_width) ? __ldg(p.mel_weight + (int64_t)row * p.mel_width + i) : 0.f;
+          }
+        }
+      }
       __syncthreads();
       // emit: all FB time steps of a row at once
 #pragma unroll
       for (int r = 0; r < RPT; ++r) {
         const int row = tid + r * NT;
+        const int row_cnt_warp = MEL ? __reduce_max_sync(0xffffffffu, row_cnt[r]) : 0;
         float v0[FB], v1[FB];
         if (MEL)
-          emit_mel<FB>(zA, P::kPitchA, row_bin[r], row_cnt[r], row_cnt_warp[r], row_w[r], f0 == 0, eps, v0, v1);
+          emit_mel<FB>(zA, P::kPitchA, row_bin[r], row_cnt[r], row_cnt_warp, row_w[r], f0 == 0, eps, v0, v1);
         else
           emit_linear<FB>(zA, P::kPitchA, row_bin[r], v0, v1);
         apply_epilogue<FB>(v0, v1, p.mask_phase != 0, p.mask_threshold, p.out_scale[0], p.out_bias[0],

@@ -29,7 +29,7 @@
 namespace isi {
 namespace melif {
 
-struct cpx { float re, im; };
+struct alignas(8) cpx { float re, im; };   // 8-byte aligned: one LDS.64 / STS.64 per value
 
 ISI_HD cpx cmul(cpx a, cpx b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
 ISI_HD cpx cadd(cpx a, cpx b) { return {a.re + b.re, a.im + b.im}; }
@@ -165,11 +165,20 @@ ISI_HD void stage_fill(int t, int nt, float* stage, int span, const float* audio
   }
 }
 
-// twiddle table in shared memory: twm[e] = exp(-2 pi i e / M), e in [0, M)
+// Twiddle table in shared memory, M entries laid out for conflict-free reads:
+//   tws[e]          = W_64^e           e in [0, 64)              (pass 2, warp-broadcast reads)
+//   tws[64 p + j]   = W_M^(j p)        p in [1, R1), j in [0, 64) (pass 1, lanes along j)
+// fft_table_source(i) is the index into the caller's W_N^k table (k < N) that slot i holds.
+template <typename P>
+ISI_HD int fft_table_source(int i) {
+  const int p = i / 64, j = i % 64;
+  return p == 0 ? (2 * P::M / 64) * j : 2 * j * p;
+}
+
 // ---- pass 1 (thread j of 64): window, pack, radix R1 over stride 64 ----
 template <typename P>
 ISI_HD void fft_pass1(int j, const float* frame /* stage + fb*hop */, bool frame_aligned8,
-                      const float* win, const cpx* twm, cpx* zA) {
+                      const float* win, const cpx* tws, cpx* zA) {
   cpx v[P::R1];
   if (frame_aligned8) {
 #pragma unroll
@@ -189,14 +198,14 @@ ISI_HD void fft_pass1(int j, const float* frame /* stage + fb*hop */, bool frame
   }
   dft_small<P::R1>(v);
 #pragma unroll
-  for (int p = 1; p < P::R1; ++p) v[p] = cmul(v[p], twm[j * p]);               // W_M^(j p)
+  for (int p = 1; p < P::R1; ++p) v[p] = cmul(v[p], tws[64 * p + j]);          // W_M^(j p)
 #pragma unroll
   for (int p = 0; p < P::R1; ++p) zA[j + P::kBlockPitch * p] = v[p];
 }
 
 // ---- pass 2: inside each 64-block, radix 16 over stride 4 ----
 template <typename P>
-ISI_HD void fft_pass2(int t, const cpx* twm, cpx* zA) {
+ISI_HD void fft_pass2(int t, const cpx* tws, cpx* zA) {
   for (int item = t; item < 4 * P::R1; item += P::kFftThreads) {
     const int b = item % P::R1, j = item / P::R1;       // lanes along b: bank = b (pitch 65)
     cpx* blk = zA + P::kBlockPitch * b;
@@ -206,7 +215,7 @@ ISI_HD void fft_pass2(int t, const cpx* twm, cpx* zA) {
     dft16(v);
     if (j != 0) {
 #pragma unroll
-      for (int p = 1; p < 16; ++p) v[p] = cmul(v[p], twm[P::R1 * j * p]);      // W_64^(j p)
+      for (int p = 1; p < 16; ++p) v[p] = cmul(v[p], tws[j * p]);               // W_64^(j p)
     }
 #pragma unroll
     for (int p = 0; p < 16; ++p) blk[j + 4 * p] = v[p];
@@ -272,27 +281,32 @@ ISI_HD cpx polar_bin(cpx x, bool first_frame, float eps, BinState& st) {
 }
 
 // ---- polar: work item `it` (0..M/2-1) of one frame, in place on its natural-order
-//      spectrum z[0..M].  Item 0 owns bin M/2 and the two purely real bins 0 and M; item it>0
-//      owns bins it and M-it.  z[k] <- (v0, v1): mel mode (|X|+eps)^2 and the phase step,
-//      linear mode log(|X|+eps) and IF. ----
-template <typename P, bool MEL>
-ISI_HD void polar_item(int it, cpx* z, cpx w /* W_N^it */, bool first_frame, float eps,
-                       BinState& sa, BinState& sb, BinState& sc) {
+//      spectrum z[0..M].  Item it>0 owns bins it and M-it.  Item 0 owns bin M/2 and ONE of the
+//      two purely real bins: `real_bin` = M when the DC bin is the dropped one, else 0 (the
+//      other one is never read by emit and keeps its raw FFT value).  Item 0 runs the same
+//      instruction stream as every other item — only operands are selected — so the warp that
+//      holds it does not execute a second, divergent path (that path used to make one warp
+//      1.75x slower than the rest and stall the CTA at the barrier before emit).
+//      z[k] <- (v0, v1): mel mode (|X|+eps)^2 and the phase step, linear mode log(|X|+eps), IF.
+//      MAYBE_ZERO = false compiles the selects out for items that cannot be item 0. ----
+template <typename P, bool MEL, bool MAYBE_ZERO = true>
+ISI_HD void polar_item(int it, cpx* z, cpx w /* W_N^it */, int real_bin, bool first_frame, float eps,
+                       BinState& sa, BinState& sb) {
   constexpr int M = P::M;
-  if (it == 0) {
-    const cpx z0 = z[0], zh = z[M / 2];
-    z[M / 2] = polar_bin<MEL>(cpx{zh.re, -zh.im}, first_frame, eps, sa);      // X[M/2]
-    z[0] = polar_bin<MEL>(cpx{z0.re + z0.im, 0.f}, first_frame, eps, sb);     // X[0]
-    z[M] = polar_bin<MEL>(cpx{z0.re - z0.im, 0.f}, first_frame, eps, sc);     // X[M]
-  } else {
-    const cpx a = z[it], b = z[M - it];
-    const cpx e = cpx{0.5f * (a.re + b.re), 0.5f * (a.im - b.im)};            // (A + conj B)/2
-    const cpx d = cpx{0.5f * (a.re - b.re), 0.5f * (a.im + b.im)};            // (A - conj B)/2
-    const cpx p = cmul(w, mul_neg_i(d));                                      // W_N^k (-i) d
-    const cpx m = csub(e, p);
-    z[it] = polar_bin<MEL>(cadd(e, p), first_frame, eps, sa);
-    z[M - it] = polar_bin<MEL>(cpx{m.re, -m.im}, first_frame, eps, sb);
+  const bool special = MAYBE_ZERO && it == 0;
+  const int ka = special ? M / 2 : it, kb = special ? real_bin : M - it;
+  const cpx a = z[it], b = z[special ? M / 2 : M - it];
+  const cpx e = cpx{0.5f * (a.re + b.re), 0.5f * (a.im - b.im)};              // (A + conj B)/2
+  const cpx d = cpx{0.5f * (a.re - b.re), 0.5f * (a.im + b.im)};              // (A - conj B)/2
+  const cpx p = cmul(w, mul_neg_i(d));                                        // W_N^k (-i) d
+  const cpx m = csub(e, p);
+  cpx xa = cadd(e, p), xb = cpx{m.re, -m.im};
+  if (special) {
+    xa = cpx{b.re, -b.im};                                                    // X[M/2] = conj Z[M/2]
+    xb = cpx{real_bin == 0 ? a.re + a.im : a.re - a.im, 0.f};                 // X[0] or X[M]
   }
+  z[ka] = polar_bin<MEL>(xa, first_frame, eps, sa);
+  z[kb] = polar_bin<MEL>(xb, first_frame, eps, sb);
 }
 
 // ---- emit: one output row, all FB frames of the batch at once; frame fb's values sit at
@@ -314,16 +328,20 @@ ISI_HD void emit_mel(const cpx* z, int pitch, int bin0, int count, int count_uni
   float m2[FB], mp[FB];
 #pragma unroll
   for (int fb = 0; fb < FB; ++fb) { m2[fb] = 0.f; mp[fb] = 0.f; }
+  // two taps per (warp-uniform) step: all 2*FB loads are issued before the first use
 #pragma unroll
-  for (int i = 0; i < kMaxMelWidth; ++i) {
+  for (int i = 0; i < kMaxMelWidth; i += 2) {
     if (i < count_uniform) {
-      if (i < count) {
+      cpx va[FB], vb[FB];
 #pragma unroll
-        for (int fb = 0; fb < FB; ++fb) {
-          const cpx v = z[fb * pitch + bin0 + i];
-          m2[fb] = fmaf(w[i], v.re, m2[fb]);
-          mp[fb] = fmaf(w[i], v.im, mp[fb]);
-        }
+      for (int fb = 0; fb < FB; ++fb) {
+        va[fb] = (i < count) ? z[fb * pitch + bin0 + i] : cpx{0.f, 0.f};
+        vb[fb] = (i + 1 < count) ? z[fb * pitch + bin0 + i + 1] : cpx{0.f, 0.f};
+      }
+#pragma unroll
+      for (int fb = 0; fb < FB; ++fb) {
+        m2[fb] = fmaf(w[i + 1], vb[fb].re, fmaf(w[i], va[fb].re, m2[fb]));
+        mp[fb] = fmaf(w[i + 1], vb[fb].im, fmaf(w[i], va[fb].im, mp[fb]));
       }
     }
   }

@@ -24,6 +24,9 @@ _MEL_Q = 1127.0
 SUPPORTED_N_FFT = (512, 1024, 2048)
 
 
+_KERNEL_BAND_PITCH = 8     # kMaxMelWidth of csrc/melif_core.cuh
+
+
 def mel_band_table(n_fft: int, fs_hz: float, lower_edge_hertz: float, upper_edge_hertz: float,
                    break_hz: float, width_factor: float):
     """Banded form of the GANSynth linear->mel filterbank for ``n_fft // 2`` linear and as
@@ -249,6 +252,8 @@ class MelSpectrogramsHelper(SpectrogramsHelper):
             mel_bin_width_threshold_factor)
         self.register_buffer("mel_start", torch.from_numpy(starts), persistent=False)
         self.register_buffer("mel_count", torch.from_numpy(counts), persistent=False)
+        if weights.shape[1] < _KERNEL_BAND_PITCH:      # 32-byte rows: two 16-byte loads per band
+            weights = np.pad(weights, ((0, 0), (0, _KERNEL_BAND_PITCH - weights.shape[1])))
         self.register_buffer("mel_weight", torch.from_numpy(weights).float().contiguous(),
                              persistent=False)
 

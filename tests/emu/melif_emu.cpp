@@ -21,7 +21,7 @@ static void emulate(const float* audio, int64_t n_notes, int64_t n_samples, int 
   constexpr int M = P::M, IPT = (M / 2) / NT, RPT = M / NT, kGroups = NT / 64;
   const cpx* tw = reinterpret_cast<const cpx*>(twiddle);
   std::vector<cpx> twm(M);
-  for (int i = 0; i < M; ++i) twm[i] = tw[2 * i];
+  for (int i = 0; i < M; ++i) twm[i] = tw[fft_table_source<P>(i)];
   const bool aligned8 = (hop % 2) == 0;
   const int dc = drop_dc ? 1 : 0;
   std::vector<float> stage((FB - 1) * hop + NFFT);
@@ -53,13 +53,13 @@ static void emulate(const float* audio, int64_t n_notes, int64_t n_samples, int 
       float* out0 = out + n * 2 * M * n_frames;
       float* out1 = out0 + (int64_t)M * n_frames;
       const int fs = seg * seg_frames, fe = std::min(n_frames, fs + seg_frames);
-      std::vector<BinState> sa((size_t)NT * IPT, BinState{1.f, 0.f}), sb = sa, sc(NT, BinState{1.f, 0.f});
+      std::vector<BinState> sa((size_t)NT * IPT, BinState{1.f, 0.f}), sb = sa;
       if (fs > 0) {
         transform(note, fs - 1, 1);
         for (int tid = 0; tid < NT; ++tid)
           for (int i = 0; i < IPT; ++i)
-            polar_item<P, MEL>(tid + i * NT, zA.data(), tw[tid + i * NT], true, eps,
-                               sa[tid * IPT + i], sb[tid * IPT + i], sc[tid]);
+            polar_item<P, MEL>(tid + i * NT, zA.data(), tw[tid + i * NT], dc ? M : 0, true, eps,
+                               sa[tid * IPT + i], sb[tid * IPT + i]);
       }
       for (int f0 = fs; f0 < fe; f0 += FB) {
         const int nf = std::min(FB, fe - f0);
@@ -67,8 +67,8 @@ static void emulate(const float* audio, int64_t n_notes, int64_t n_samples, int 
         for (int tid = 0; tid < NT; ++tid)
           for (int fb = 0; fb < nf; ++fb)
             for (int i = 0; i < IPT; ++i)
-              polar_item<P, MEL>(tid + i * NT, zA.data() + fb * P::kPitchA, tw[tid + i * NT],
-                                 f0 + fb == 0, eps, sa[tid * IPT + i], sb[tid * IPT + i], sc[tid]);
+              polar_item<P, MEL>(tid + i * NT, zA.data() + fb * P::kPitchA, tw[tid + i * NT], dc ? M : 0,
+                                 f0 + fb == 0, eps, sa[tid * IPT + i], sb[tid * IPT + i]);
         for (int tid = 0; tid < NT; ++tid)
           for (int r = 0; r < RPT; ++r) {
             const int row = tid + r * NT;
