@@ -56,6 +56,24 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
       : "memory");
 }
 
+// Cache policy: the band tables (40 KB, re-read by every CTA every batch) should stay in L1,
+// the output stream (1 MB per note, written once) should not displace them.
+__device__ __forceinline__ float4 ld_table4(const float4* p) {
+  float4 v;
+  asm volatile("ld.global.nc.L1::evict_last.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ int ld_table(const int32_t* p) {
+  int v;
+  asm volatile("ld.global.nc.L1::evict_last.s32 %0, [%1];" : "=r"(v) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st_stream4(float* p, float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};"
+               :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 struct MelifSmem {
   int tw, win, stage, za, bar, total;   // byte offsets into dynamic shared memory
 };
@@ -204,11 +222,11 @@ melif_kernel(const float* __restrict__ audio, int64_t n_samples, isi_melif_param
         row_bin[r] = row + dc;
         row_cnt[r] = 0;
         if (MEL) {
-          row_bin[r] = __ldg(p.mel_start + row) + dc;
-          row_cnt[r] = __ldg(p.mel_count + row);
+          row_bin[r] = ld_table(p.mel_start + row) + dc;
+          row_cnt[r] = ld_table(p.mel_count + row);
           if (w_vec) {
             const float4* wt = reinterpret_cast<const float4*>(p.mel_weight) + (int64_t)row * 2;
-            const float4 a = __ldg(wt), c = __ldg(wt + 1);
+            const float4 a = ld_table4(wt), c = ld_table4(wt + 1);
             row_w[r][0] = a.x; row_w[r][1] = a.y; row_w[r][2] = a.z; row_w[r][3] = a.w;
             row_w[r][4] = c.x; row_w[r][5] = c.y; row_w[r][6] = c.z; row_w[r][7] = c.w;
           } else {
@@ -237,7 +255,7 @@ melif_kernel(const float* __restrict__ audio, int64_t n_samples, isi_melif_param
           if (nf == FB && (FB % 2 == 0) && (p.n_frames % 2 == 0)) {
 #pragma unroll
             for (int q = 0; q < FB / 2; ++q)
-              reinterpret_cast<float4*>(d)[q] = make_float4(v0[2 * q], v1[2 * q], v0[2 * q + 1], v1[2 * q + 1]);
+              st_stream4(d + 4 * q, make_float4(v0[2 * q], v1[2 * q], v0[2 * q + 1], v1[2 * q + 1]));
           } else {
 #pragma unroll
             for (int fb = 0; fb < FB; ++fb)
@@ -250,8 +268,8 @@ melif_kernel(const float* __restrict__ audio, int64_t n_samples, isi_melif_param
         if (nf == FB && (FB % 4 == 0) && (p.n_frames % 4 == 0)) {
 #pragma unroll
           for (int q = 0; q < FB / 4; ++q) {
-            reinterpret_cast<float4*>(d0)[q] = make_float4(v0[4 * q], v0[4 * q + 1], v0[4 * q + 2], v0[4 * q + 3]);
-            reinterpret_cast<float4*>(d1)[q] = make_float4(v1[4 * q], v1[4 * q + 1], v1[4 * q + 2], v1[4 * q + 3]);
+            st_stream4(d0 + 4 * q, make_float4(v0[4 * q], v0[4 * q + 1], v0[4 * q + 2], v0[4 * q + 3]));
+            st_stream4(d1 + 4 * q, make_float4(v1[4 * q], v1[4 * q + 1], v1[4 * q + 2], v1[4 * q + 3]));
           }
         } else {
 #pragma unroll

@@ -94,3 +94,20 @@ def test_fused_masked_phase_and_normaliser_epilogue():
         want = fo.epilogue(plain.cpu(), **kw)
         assert torch.allclose(fused.cpu(), want, rtol=0, atol=1e-6)
         assert (fused[:, 1][plain[:, 0] < -3.0] == -0.25).all()
+
+
+def test_band_table_pitch_and_dropped_nyquist_in_mel_mode():
+    """The kernel reads 8-wide band rows with two 16-byte loads and any other pitch with scalar
+    loads: both give the same bits.  Mel mode with the Nyquist bin dropped exercises the
+    branch-free item 0 of the polar step with the DC bin as its real bin."""
+    audio = synthetic.synthetic_notes(2, n_samples=20000)
+    helper = MelSpectrogramsHelper().to(DEV)
+    padded = helper.to_spectrogram(audio.to(DEV))
+    width = int(helper.mel_count.max())
+    assert helper.mel_weight.shape[1] == 8 and width < 8
+    helper.mel_weight = helper.mel_weight[:, :width].contiguous()
+    assert torch.equal(helper.to_spectrogram(audio.to(DEV)), padded)
+
+    helper = MelSpectrogramsHelper(drop_bin="nyquist").to(DEV)
+    cfg = fo.FrontEndConfig(drop_bin="nyquist")
+    check_against_oracle(helper.to_spectrogram(audio.to(DEV)).cpu(), audio, cfg)

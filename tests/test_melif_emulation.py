@@ -145,3 +145,10 @@ def test_emulated_kernel_nyquist_knob(emu):
     got = _run(emu, helper, audio)
     cfg = fo.FrontEndConfig(use_mel_scale=False, drop_bin="nyquist", window_periodic=False)
     check_against_oracle(got, audio, cfg)
+
+
+def test_emulated_mel_mode_with_dropped_nyquist(emu):
+    """Item 0 of the polar step owns bin M/2 and the real bin that is kept (DC here)."""
+    audio = synthetic.synthetic_notes(1, n_samples=16000)
+    helper = sh.MelSpectrogramsHelper(drop_bin="nyquist")
+    check_against_oracle(_run(emu, helper, audio), audio, fo.FrontEndConfig(drop_bin="nyquist"))
