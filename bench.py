@@ -120,6 +120,18 @@ def make_audio(batch: int, seed_offset: int = 0) -> torch.Tensor:
     return out[:batch].contiguous()
 
 
+PCM_SCALE = 1.0 / 32768.0
+
+
+def to_pcm16(audio: torch.Tensor) -> torch.Tensor:
+    """Synthetic notes on the 16-bit grid NSynth's wav files are stored on."""
+    return (audio * 32767.0).round().clamp(-32768, 32767).to(torch.int16)
+
+
+def pcm_to_float(pcm: torch.Tensor) -> torch.Tensor:
+    return pcm.float() * PCM_SCALE
+
+
 # --------------------------------------------------------------------------- reference arm
 def cpu_encode_path(threads: int):
     """The oracle port of the path: torch-CPU front-end restatement, the same conv wiring on
@@ -155,7 +167,7 @@ def reference_arm(args):
     cores = os.cpu_count() or 1
     run, _ = cpu_encode_path(cores)
     sample = 16
-    audio = make_audio(sample)
+    audio = pcm_to_float(to_pcm16(make_audio(sample)))     # the values the B200 arm sees
     value, per_step = time_cpu(run, audio, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "notes/s",
@@ -210,8 +222,14 @@ def b200_arm(args):
         model = model.to(memory_format=torch.channels_last)
     clocks = NvmlClockSampler(local)
     model.quantize_t.assign_algo = model.quantize_b.assign_algo = args.assign_algo
-    host_audio = make_audio(B, seed_offset=rank).pin_memory()
+    # Every leg sees the same sample values: synthetic notes on the 16-bit PCM grid.  `pcm16`
+    # uploads them as stored (int16, converted inside the front-end kernel), `f32` as the
+    # reference's loader would (converted on the host first, twice the bytes).
+    pcm = to_pcm16(make_audio(B, seed_offset=rank))
+    host_by_format = {"pcm16": pcm.pin_memory(), "f32": pcm_to_float(pcm).pin_memory()}
+    host_audio = host_by_format[args.audio]
     audio = host_audio.to(dev)
+    helper.pcm_scale = PCM_SCALE
     host_codes = (torch.empty(B, 32, 4, dtype=torch.int64).pin_memory(),
                   torch.empty(B, 64, 8, dtype=torch.int64).pin_memory())
     ev = lambda: torch.cuda.Event(enable_timing=True)
@@ -257,19 +275,29 @@ def b200_arm(args):
     from interactive_spectrogram_inpainting_b200 import extract
     names = [f"note_{i:07d}" for i in range(B)]
 
-    def e2e_run(n_batches):
-        loader = extract.SpectrogramBatches([(host_audio, names)] * n_batches, helper, dev)
-        return extract.extract_codes(loader, model)
-    e2e_run(W)
-    barrier()
-    t0, t1 = ev(), ev()
-    t0.record()
-    rows = e2e_run(K)
-    t1.record()
-    barrier()
-    assert len(rows) == B * K and rows[0].top.shape == (32, 4) and rows[0].bottom.shape == (64, 8)
-    e2e_ms = max_over_ranks(t0.elapsed_time(t1))
+    e2e_stamps = []
+
+    def e2e_run(n_batches, host):
+        loader = extract.SpectrogramBatches([(host, names)] * n_batches, helper, dev)
+        return extract.extract_codes(loader, model, sink=lambda rows: e2e_stamps.append(time.perf_counter()))
+
+    def e2e_measure(host):
+        e2e_run(W, host)
+        barrier()
+        t0, t1 = ev(), ev()
+        t0.record()
+        e2e_stamps.clear()
+        rows = e2e_run(K, host)
+        t1.record()
+        barrier()
+        assert len(rows) == B * K and rows[0].top.shape == (32, 4) and rows[0].bottom.shape == (64, 8)
+        ms = max_over_ranks(t0.elapsed_time(t1))
+        gaps = [(b - a) * 1e3 for a, b in zip(e2e_stamps[:-1], e2e_stamps[1:])] or [ms / K]
+        return ms, gaps
+    e2e_ms, e2e_gaps = e2e_measure(host_audio)
     e2e_value = world * B * K / (e2e_ms * 1e-3)
+    other = "f32" if args.audio == "pcm16" else "pcm16"
+    other_ms, _ = e2e_measure(host_by_format[other])
 
     # ---- hot path only: (1) + (2) on pre-computed conv features ----
     with torch.no_grad():
@@ -347,7 +375,9 @@ def b200_arm(args):
         del ma, mb
 
     hbm_peak, peak_kind, _ = measured_peaks()
-    melif_gbs = MELIF_BYTES_PER_NOTE * B / (melif_ms * 1e-3) / 1e9
+    # algorithmic bytes per note: the samples as uploaded + the FP32 spectrogram
+    melif_bytes_per_note = MELIF_BYTES_PER_NOTE - (4 - host_audio.element_size()) * N_SAMPLES
+    melif_gbs = melif_bytes_per_note * B / (melif_ms * 1e-3) / 1e9
     assign_tflops = 2.0 * qn * N_EMBED * DIM / (assign_ms * 1e-3) / 1e12
     clk = clocks.summary()
 
@@ -365,14 +395,21 @@ def b200_arm(args):
                    "notes_per_step_per_gpu": B, "sharding": "notes sharded per rank, no collective",
                    "conv_encoder": "torch/cuDNN fp32 (TF32 convs as torch defaults), random init, "
                                    + ("channels_last storage" if cl else "NCHW storage"),
-                   "l2": f"inputs exceed L2 (126 MB): {B * 0.256:.0f} MB audio + "
+                   "l2": f"inputs exceed L2 (126 MB): {B * 0.064 * host_audio.element_size():.0f} MB audio + "
                          f"{B * 1.0486:.0f} MB spectrogram per step",
-                   "assign_algo": args.assign_algo},
+                   "assign_algo": args.assign_algo,
+                   "audio": ("int16 PCM, NSynth's storage format, converted inside the front-end kernel"
+                             if args.audio == "pcm16" else "float32, converted on the host")},
         "e2e": {"value": e2e_value, "unit": "notes/s",
-                "h2d_bytes_per_step": host_audio.numel() * 4,
+                "h2d_bytes_per_step": host_audio.numel() * host_audio.element_size(),
+                "audio": args.audio,
                 "d2h_bytes_per_step": (host_codes[0].numel() + host_codes[1].numel()) * 8,
                 "api": "extract.extract_codes(extract.SpectrogramBatches(pinned host audio))",
-                "ms_per_step": e2e_ms / K},
+                "ms_per_step": e2e_ms / K,
+                "host_ms_between_batches": {"median": statistics.median(e2e_gaps), "max": max(e2e_gaps)},
+                "other_audio_format": {"audio": other, "value": world * B * K / (other_ms * 1e-3),
+                                       "h2d_bytes_per_step": host_by_format[other].numel()
+                                       * host_by_format[other].element_size()}},
         "gpu_launches": launches,
         "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"],
                    "reasons": clk["reasons"], "samples": clk["samples"]},
@@ -383,7 +420,7 @@ def b200_arm(args):
                      # channels_last output), scaled to this batch
                      "traffic": (76.168704e6 + 259.628288e6) / 296 * B if cl else None,
                      "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
-                     "ms_per_launch": melif_ms, "algorithmic_bytes_per_launch": MELIF_BYTES_PER_NOTE * B},
+                     "ms_per_launch": melif_ms, "algorithmic_bytes_per_launch": melif_bytes_per_note * B},
         "rooflines_other": [
             {"kernel": f"vq_assign ({args.assign_algo})", "bound": "tensor",
              "achieved": assign_tflops, "peak": tf32_tflops / 3.0, "unit": "TFLOP/s",
@@ -407,7 +444,7 @@ def b200_arm(args):
         run, cpu_model = cpu_encode_path(cores)
         cpu_model.load_state_dict(model.state_dict())
         sample = 16
-        cpu_audio = host_audio[:sample].clone()
+        cpu_audio = host_by_format["f32"][:sample].clone()
         # size the sample to ~10-20 s of CPU work
         v1, per = time_cpu(run, cpu_audio, 1, 1)
         reps = max(2, min(50, int(12.0 / max(per, 1e-3))))
@@ -431,6 +468,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--assign-algo", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--audio", default="pcm16", choices=["pcm16", "f32"],
+                    help="sample format of the input notes: int16 PCM as the dataset stores them "
+                         "(converted in the front-end kernel) or float32 as the reference uploads them")
     ap.add_argument("--cudnn-benchmark", type=int, default=1)
     ap.add_argument("--channels-last", type=int, default=1,
                     help="1: spectrogram + conv stack in torch.channels_last storage (default)")

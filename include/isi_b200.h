@@ -183,10 +183,12 @@ typedef struct isi_melif_params {
   int32_t mel_width;    /* max non-zeros per mel bin (row pitch of mel_weight)  */
   float safelog_eps;    /* log(v + eps)                                         */
   const float* window;  /* [n_fft] analysis window                              */
-  const float* twiddle; /* [n_fft] interleaved cos,sin of -2*pi*j/n_fft, j<n_fft/2 */
+  const float* twiddle; /* [n_fft, 2] cos,sin of -2*pi*j/n_fft, j<n_fft; 8-byte aligned */
   const int32_t* mel_start; /* [n_fft/2] first linear bin of each mel band      */
   const int32_t* mel_count; /* [n_fft/2] band length (0..mel_width)             */
-  const float* mel_weight;  /* [n_fft/2, mel_width] band weights                */
+  const float* mel_weight;  /* [n_fft/2, mel_width] band weights, zero beyond the band's
+                               length; mel_width == 8 and 16-byte alignment select
+                               two 16-byte loads per band, anything else scalar loads */
   int32_t channels_last;    /* 0: out is [B,2,F,T'] planes (the reference layout);   */
                             /* 1: the same logical tensor in torch channels_last     */
                             /*    storage [B,F,T',2] (what the cuDNN convs consume)  */
@@ -195,16 +197,22 @@ typedef struct isi_melif_params {
   float mask_threshold;     /*    masked-phase transform, extract_code.py:178-181)           */
   float out_scale[2];       /* then channel c := c * out_scale[c] + out_bias[c] (the         */
   float out_bias[2];        /*    DataNormalizer affine of vqvae.py:254-255); 1 / 0 = off    */
+  /* input samples: FP32, or 16-bit PCM as NSynth stores it (the reference's dataset class     */
+  /* converts on the CPU and uploads FP32; reading PCM halves the host->device bytes)          */
+  int32_t audio_format;     /* isi_audio_format                                                */
+  float pcm_scale;          /* PCM16 only: sample = (float)pcm * pcm_scale (e.g. 1/32768)      */
 } isi_melif_params;
 
+typedef enum { ISI_AUDIO_F32 = 0, ISI_AUDIO_PCM16 = 1 } isi_audio_format;
+
 /*
- * audio [n_notes, n_samples] FP32 (contiguous) -> out [n_notes, 2, n_fft/2,
- * n_frames] FP32: channel 0 log-magnitude, channel 1 instantaneous frequency,
+ * audio [n_notes, n_samples] (contiguous; FP32 or int16 per h_params->audio_format)
+ * -> out [n_notes, 2, n_fft/2, n_frames] FP32: channel 0 log-magnitude, channel 1 IF,
  * frequency-major / time-contiguous like the reference tensors
  * (Inference.ipynb:71, flask_server.py:891-896), or channel-interleaved storage of the
  * same logical tensor when h_params->channels_last is set.
  */
-ISI_API int isi_melif_forward(const float* audio, int64_t n_notes, int64_t n_samples,
+ISI_API int isi_melif_forward(const void* audio, int64_t n_notes, int64_t n_samples,
                       const isi_melif_params* h_params, float* out,
                       isi_stream_t stream);
 

@@ -17,6 +17,7 @@ _LIB_PATH = pathlib.Path(__file__).resolve().parent / "libisi_b200.so"
 _lock = threading.Lock()
 _lib = None
 
+AUDIO_F32, AUDIO_PCM16 = 0, 1
 ASSIGN_AUTO, ASSIGN_SIMT_FP32, ASSIGN_TCGEN05, ASSIGN_TCGEN05_PAIR, ASSIGN_TCGEN05_PAIR_STREAM = range(5)
 _ALGOS = {"auto": ASSIGN_AUTO, "simt": ASSIGN_SIMT_FP32, "tcgen05": ASSIGN_TCGEN05,
           "tcgen05_pair": ASSIGN_TCGEN05_PAIR, "tcgen05_pair_stream": ASSIGN_TCGEN05_PAIR_STREAM}
@@ -36,7 +37,8 @@ class MelifParams(ctypes.Structure):
                 ("mel_start", ctypes.c_void_p), ("mel_count", ctypes.c_void_p),
                 ("mel_weight", ctypes.c_void_p), ("channels_last", ctypes.c_int32),
                 ("mask_phase", ctypes.c_int32), ("mask_threshold", ctypes.c_float),
-                ("out_scale", ctypes.c_float * 2), ("out_bias", ctypes.c_float * 2)]
+                ("out_scale", ctypes.c_float * 2), ("out_bias", ctypes.c_float * 2),
+                ("audio_format", ctypes.c_int32), ("pcm_scale", ctypes.c_float)]
 
 
 EXPORTS = {

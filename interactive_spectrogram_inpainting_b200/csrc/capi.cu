@@ -26,7 +26,7 @@ int launch_finish(const void*, int64_t, int, int, const float*, float*, float*, 
 int launch_ema_update(float*, float*, float*, float*, int, int, double, double, cudaStream_t);
 int launch_embed_code(const int64_t*, int64_t, int, int, const Prepared&, float*,
                       const isi_rows_layout&, int32_t*, cudaStream_t);
-int launch_melif(const float*, int64_t, int64_t, const isi_melif_params&, float*, cudaStream_t);
+int launch_melif(const void*, int64_t, int64_t, const isi_melif_params&, float*, cudaStream_t);
 }  // namespace isi
 
 using namespace isi;
@@ -148,13 +148,15 @@ ISI_API int isi_embed_code(const int64_t* index, int64_t n_rows, int dim, int n_
                            *ol, status_flag, (cudaStream_t)stream);
 }
 
-ISI_API int isi_melif_forward(const float* audio, int64_t n_notes, int64_t n_samples,
+ISI_API int isi_melif_forward(const void* audio, int64_t n_notes, int64_t n_samples,
                       const isi_melif_params* hp, float* out, isi_stream_t stream) {
   if (!audio || !hp || !out || !hp->window || !hp->twiddle) return ISI_ERR_NULL;
   if (hp->use_mel && (!hp->mel_start || !hp->mel_count || !hp->mel_weight)) return ISI_ERR_NULL;
   if (n_notes < 0 || n_samples <= 0 || hp->hop <= 0 || hp->n_frames <= 0 || hp->pad_left < 0)
     return ISI_ERR_SHAPE;
   if (hp->use_mel && hp->mel_width <= 0) return ISI_ERR_SHAPE;
+  if (hp->audio_format != ISI_AUDIO_F32 && hp->audio_format != ISI_AUDIO_PCM16) return ISI_ERR_UNSUPPORTED;
+  if ((uintptr_t)audio % (hp->audio_format == ISI_AUDIO_PCM16 ? 2 : 4)) return ISI_ERR_ALIGN;
   if ((uintptr_t)out % 16 || (uintptr_t)hp->twiddle % 8) return ISI_ERR_ALIGN;
   if (n_notes == 0) return ISI_OK;
   return launch_melif(audio, n_notes, n_samples, *hp, out, (cudaStream_t)stream);

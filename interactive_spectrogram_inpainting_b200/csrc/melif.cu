@@ -79,22 +79,22 @@ struct MelifSmem {
 };
 
 template <int NFFT, int FB>
-__host__ __device__ inline MelifSmem melif_smem_layout(int hop) {
+__host__ __device__ inline MelifSmem melif_smem_layout(int hop, int sample_bytes) {
   using P = Plan<NFFT>;
   MelifSmem s;
   int off = 0;
   s.tw = off;    off += (NFFT / 2) * 8;                     // FFT twiddles (fft_table_source)
   s.win = off;   off += NFFT * 4;
-  s.stage = off; off += (((FB - 1) * hop + NFFT + 3) / 4) * 16;
+  s.stage = off; off += (((FB - 1) * hop + NFFT) * sample_bytes + 15) / 16 * 16;
   s.za = off;    off += FB * P::kPitchA * 8;                // FFT workspace, spectrum, polar values
   s.bar = off;   off += 16;
   s.total = off;
   return s;
 }
 
-template <int NFFT, int FB, int NT, bool MEL>
+template <int NFFT, int FB, int NT, bool MEL, typename S>
 __global__ void __launch_bounds__(NT, 3)
-melif_kernel(const float* __restrict__ audio, int64_t n_samples, isi_melif_params p,
+melif_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params p,
              float* __restrict__ out, int bulk_ok, int seg_frames, int n_segs) {
   using P = Plan<NFFT>;
   constexpr int M = P::M;
@@ -104,10 +104,10 @@ melif_kernel(const float* __restrict__ audio, int64_t n_samples, isi_melif_param
   static_assert(IPT >= 1 && (M / 2) % NT == 0 && NT % 64 == 0, "bad thread count");
   static_assert(P::kPitchA >= M + 1, "a frame region must hold bins 0..M");
   extern __shared__ __align__(128) unsigned char smem[];
-  const MelifSmem L = melif_smem_layout<NFFT, FB>(p.hop);
+  const MelifSmem L = melif_smem_layout<NFFT, FB>(p.hop, (int)sizeof(S));
   cpx* twm = reinterpret_cast<cpx*>(smem + L.tw);
   float* win = reinterpret_cast<float*>(smem + L.win);
-  float* stage = reinterpret_cast<float*>(smem + L.stage);
+  S* stage = reinterpret_cast<S*>(smem + L.stage);
   cpx* zA = reinterpret_cast<cpx*>(smem + L.za);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar);
 
@@ -115,12 +115,12 @@ melif_kernel(const float* __restrict__ audio, int64_t n_samples, isi_melif_param
   const int note_idx = blockIdx.x / n_segs, seg = blockIdx.x - note_idx * n_segs;
   const int fs = seg * seg_frames;                          // first frame of this CTA
   const int fe = min(p.n_frames, fs + seg_frames);          // one past its last frame
-  const float* note = audio + (int64_t)note_idx * n_samples;
+  const S* note = audio + (int64_t)note_idx * n_samples;
   float* out0 = out + (int64_t)note_idx * 2 * M * p.n_frames;
   float* out1 = out0 + (int64_t)M * p.n_frames;
   const int dc = p.drop_dc ? 1 : 0;
   const float eps = p.safelog_eps;
-  const bool frames_aligned8 = (p.hop % 2) == 0;
+  const bool pairs_aligned = (p.hop % 2) == 0;   // a frame starts on a sample-pair boundary
 
   // ---- one-time setup: tables to shared memory, per-thread constants to registers ----
   const cpx* tw_global = reinterpret_cast<const cpx*>(p.twiddle);     // W_N^j, j < N
@@ -155,12 +155,12 @@ melif_kernel(const float* __restrict__ audio, int64_t n_samples, isi_melif_param
     int64_t hi = n_samples - s0;                              // one past the last valid index
     hi = hi < 0 ? 0 : (hi > span ? span : hi);
     const int64_t vlo = lo < hi ? lo : hi;
-    for (int i = tid; i < vlo; i += NT) stage[i] = 0.f;
-    for (int i = (int)hi + tid; i < span; i += NT) stage[i] = 0.f;
+    for (int i = tid; i < vlo; i += NT) stage[i] = S(0);
+    for (int i = (int)hi + tid; i < span; i += NT) stage[i] = S(0);
     if (tid == 0) {
       if (hi > lo) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        const uint32_t bytes = (uint32_t)(hi - lo) * 4u;
+        const uint32_t bytes = (uint32_t)(hi - lo) * (uint32_t)sizeof(S);
         mbar_expect_tx(bar, bytes);
         bulk_g2s(stage + lo, note + s0 + lo, bytes, bar);
       } else {
@@ -189,7 +189,7 @@ melif_kernel(const float* __restrict__ audio, int64_t n_samples, isi_melif_param
     // on a named barrier of their own instead of stalling the whole CTA.
     const uint32_t group_bar = 1 + (tid >> 6);
     for (int fb = tid / 64; fb < nf; fb += kGroups)
-      fft_pass1<P>(tid & 63, stage + fb * p.hop, frames_aligned8, win, twm, zA + fb * P::kPitchA);
+      fft_pass1<P>(tid & 63, stage + fb * p.hop, pairs_aligned, p.pcm_scale, win, twm, zA + fb * P::kPitchA);
     asm volatile("bar.sync %0, 64;" ::"r"(group_bar) : "memory");
     for (int fb = tid / 64; fb < nf; fb += kGroups) fft_pass2<P>(tid & 63, twm, zA + fb * P::kPitchA);
     asm volatile("bar.sync %0, 64;" ::"r"(group_bar) : "memory");
@@ -300,33 +300,34 @@ static void choose_segments(int64_t n_notes, int n_frames, int fb, int* seg_fram
   }
 }
 
-template <int NFFT, int FB, int NT, bool MEL>
-static int launch_melif_t(const float* audio, int64_t n_notes, int64_t n_samples,
+template <int NFFT, int FB, int NT, bool MEL, typename S>
+static int launch_melif_t(const S* audio, int64_t n_notes, int64_t n_samples,
                           const isi_melif_params& p, float* out, cudaStream_t stream) {
-  const MelifSmem L = melif_smem_layout<NFFT, FB>(p.hop);
+  const MelifSmem L = melif_smem_layout<NFFT, FB>(p.hop, (int)sizeof(S));
   if (L.total > 227 * 1024) return ISI_ERR_UNSUPPORTED;
-  cudaError_t e = cudaFuncSetAttribute(melif_kernel<NFFT, FB, NT, MEL>,
+  cudaError_t e = cudaFuncSetAttribute(melif_kernel<NFFT, FB, NT, MEL, S>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
   if (e != cudaSuccess) return (int)e;
   // the bulk copy needs 16-byte aligned global addresses and sizes
-  const int bulk_ok = (n_samples % 4 == 0) && (p.hop % 4 == 0) && (p.pad_left % 4 == 0) &&
-                      ((uintptr_t)audio % 16 == 0);
+  constexpr int kPer16 = 16 / (int)sizeof(S);
+  const int bulk_ok = (n_samples % kPer16 == 0) && (p.hop % kPer16 == 0) &&
+                      (p.pad_left % kPer16 == 0) && ((uintptr_t)audio % 16 == 0);
   int seg_frames, n_segs;
   choose_segments(n_notes, p.n_frames, FB, &seg_frames, &n_segs);
   if (n_notes * n_segs > 0x7fffffff) return ISI_ERR_SHAPE;
-  melif_kernel<NFFT, FB, NT, MEL><<<(unsigned)(n_notes * n_segs), NT, L.total, stream>>>(
+  melif_kernel<NFFT, FB, NT, MEL, S><<<(unsigned)(n_notes * n_segs), NT, L.total, stream>>>(
       audio, n_samples, p, out, bulk_ok, seg_frames, n_segs);
   ISI_LAUNCH_CHECK();
   return ISI_OK;
 }
 
-int launch_melif(const float* audio, int64_t n_notes, int64_t n_samples,
-                 const isi_melif_params& p, float* out, cudaStream_t stream) {
-  if (p.use_mel && p.mel_width > kMaxMelWidth) return ISI_ERR_UNSUPPORTED;
-#define ISI_MELIF_CASE(N, FB, NT)                                                            \
-  case N:                                                                                  \
-    return p.use_mel ? launch_melif_t<N, FB, NT, true>(audio, n_notes, n_samples, p, out, stream) \
-                     : launch_melif_t<N, FB, NT, false>(audio, n_notes, n_samples, p, out, stream);
+template <typename S>
+static int launch_melif_s(const S* audio, int64_t n_notes, int64_t n_samples,
+                          const isi_melif_params& p, float* out, cudaStream_t stream) {
+#define ISI_MELIF_CASE(N, FB, NT)                                                               \
+  case N:                                                                                     \
+    return p.use_mel ? launch_melif_t<N, FB, NT, true, S>(audio, n_notes, n_samples, p, out, stream) \
+                     : launch_melif_t<N, FB, NT, false, S>(audio, n_notes, n_samples, p, out, stream);
   switch (p.n_fft) {
     ISI_MELIF_CASE(2048, 4, 256)
     ISI_MELIF_CASE(1024, 4, 128)
@@ -334,6 +335,18 @@ int launch_melif(const float* audio, int64_t n_notes, int64_t n_samples,
     default: return ISI_ERR_UNSUPPORTED;
   }
 #undef ISI_MELIF_CASE
+}
+
+int launch_melif(const void* audio, int64_t n_notes, int64_t n_samples,
+                 const isi_melif_params& p, float* out, cudaStream_t stream) {
+  if (p.use_mel && p.mel_width > kMaxMelWidth) return ISI_ERR_UNSUPPORTED;
+  switch (p.audio_format) {
+    case ISI_AUDIO_F32:
+      return launch_melif_s(static_cast<const float*>(audio), n_notes, n_samples, p, out, stream);
+    case ISI_AUDIO_PCM16:
+      return launch_melif_s(static_cast<const int16_t*>(audio), n_notes, n_samples, p, out, stream);
+    default: return ISI_ERR_UNSUPPORTED;
+  }
 }
 
 }  // namespace isi

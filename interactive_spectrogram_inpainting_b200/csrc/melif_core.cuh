@@ -157,12 +157,31 @@ struct Plan {
 
 // ---- synchronous staging of the audio span of one frame batch (emulation, and the
 //      device path when the span is not 16-byte copyable) ----
-ISI_HD void stage_fill(int t, int nt, float* stage, int span, const float* audio,
+template <typename S>
+ISI_HD void stage_fill(int t, int nt, S* stage, int span, const S* audio,
                        int64_t n_samples, int64_t first_sample) {
   for (int i = t; i < span; i += nt) {
     int64_t s = first_sample + i;
-    stage[i] = (s >= 0 && s < n_samples) ? audio[s] : 0.f;
+    stage[i] = (s >= 0 && s < n_samples) ? audio[s] : S(0);
   }
+}
+
+// Two consecutive samples of a frame as floats.  S = float: the staged values; S = int16_t
+// (PCM as the dataset stores it): float(x) * pcm_scale, the conversion a host loader would do
+// before the upload.  `aligned` = the pair starts on a 2*sizeof(S) boundary (one load).
+struct alignas(4) pcm_pair { int16_t a, b; };
+
+template <bool ALIGNED>
+ISI_HD cpx load_pair(const float* frame, int m, float) {
+  if (ALIGNED) return reinterpret_cast<const cpx*>(frame)[m];
+  return cpx{frame[2 * m], frame[2 * m + 1]};
+}
+template <bool ALIGNED>
+ISI_HD cpx load_pair(const int16_t* frame, int m, float pcm_scale) {
+  pcm_pair q;
+  if (ALIGNED) q = reinterpret_cast<const pcm_pair*>(frame)[m];
+  else q = pcm_pair{frame[2 * m], frame[2 * m + 1]};
+  return cpx{(float)q.a * pcm_scale, (float)q.b * pcm_scale};
 }
 
 // Twiddle table in shared memory, M entries laid out for conflict-free reads:
@@ -176,15 +195,15 @@ ISI_HD int fft_table_source(int i) {
 }
 
 // ---- pass 1 (thread j of 64): window, pack, radix R1 over stride 64 ----
-template <typename P>
-ISI_HD void fft_pass1(int j, const float* frame /* stage + fb*hop */, bool frame_aligned8,
+template <typename P, typename S>
+ISI_HD void fft_pass1(int j, const S* frame /* stage + fb*hop */, bool pair_aligned, float pcm_scale,
                       const float* win, const cpx* tws, cpx* zA) {
   cpx v[P::R1];
-  if (frame_aligned8) {
+  if (pair_aligned) {
 #pragma unroll
     for (int r = 0; r < P::R1; ++r) {
       const int m = j + 64 * r;
-      const cpx a = reinterpret_cast<const cpx*>(frame)[m];
+      const cpx a = load_pair<true>(frame, m, pcm_scale);
       const cpx w = reinterpret_cast<const cpx*>(win)[m];
       v[r] = cpx{a.re * w.re, a.im * w.im};
     }
@@ -192,8 +211,9 @@ ISI_HD void fft_pass1(int j, const float* frame /* stage + fb*hop */, bool frame
 #pragma unroll
     for (int r = 0; r < P::R1; ++r) {
       const int m = j + 64 * r;
+      const cpx a = load_pair<false>(frame, m, pcm_scale);
       const cpx w = reinterpret_cast<const cpx*>(win)[m];
-      v[r] = cpx{frame[2 * m] * w.re, frame[2 * m + 1] * w.im};
+      v[r] = cpx{a.re * w.re, a.im * w.im};
     }
   }
   dft_small<P::R1>(v);

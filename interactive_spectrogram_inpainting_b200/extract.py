@@ -83,25 +83,37 @@ def extract_codes(loader: Iterable[Tuple[torch.Tensor, Sequence[str]]], model,
     reference's ``encode`` 7-tuple.  Returns (and optionally streams to ``sink``) the rows."""
     rows: List[CodeRow] = []
     pending = None
+    # Two pinned staging pairs, reused: allocating page-locked memory per batch is slow and is
+    # an implicit device synchronisation (it breaks the copy/compute overlap).  flush() copies
+    # the maps out of the staging pair before that pair's next use, two batches later.
+    staging: List[Optional[Tuple[torch.Tensor, torch.Tensor]]] = [None, None]
+
+    def staging_pair(slot, id_t, id_b):
+        pair = staging[slot]
+        if pair is None or pair[0].numel() < id_t.numel() or pair[1].numel() < id_b.numel():
+            pair = (torch.empty(id_t.numel(), dtype=id_t.dtype, pin_memory=True),
+                    torch.empty(id_b.numel(), dtype=id_b.dtype, pin_memory=True))
+            staging[slot] = pair
+        return (pair[0][:id_t.numel()].view(id_t.shape), pair[1][:id_b.numel()].view(id_b.shape))
 
     def flush(item):
-        id_t, id_b, names, done = item
+        host_t, host_b, names, done = item
         done.synchronize()
+        tops, bottoms = host_t.numpy().copy(), host_b.numpy().copy()
         batch_rows = [CodeRow(top=t, bottom=b, attributes={}, filename=n)
-                      for t, b, n in zip(id_t.numpy(), id_b.numpy(), names)]
+                      for t, b, n in zip(tops, bottoms, names)]
         if sink is not None:
             sink(batch_rows)
         rows.extend(batch_rows)
 
     model.eval()
-    for spec, names in loader:
+    for step, (spec, names) in enumerate(loader):
         if hasattr(model, "encode_codes"):
             id_t, id_b = model.encode_codes(spec)
         else:
             out = model.encode(spec)
             id_t, id_b = out[3], out[4]
-        host_t = torch.empty(id_t.shape, dtype=id_t.dtype, pin_memory=True)
-        host_b = torch.empty(id_b.shape, dtype=id_b.dtype, pin_memory=True)
+        host_t, host_b = staging_pair(step % 2, id_t, id_b)
         host_t.copy_(id_t, non_blocking=True)
         host_b.copy_(id_b, non_blocking=True)
         done = torch.cuda.Event()

@@ -123,6 +123,10 @@ class SpectrogramsHelper(nn.Module):
         # (vqvae.py:254-255).  None = off.
         self.masked_phase_threshold = masked_phase_threshold
         self.output_affine = output_affine
+        # int16 input only: the float value of one PCM step.  The dataset class the reference
+        # uses (pytorch_nsynth, not in its tree) does this conversion on the CPU; its exact
+        # constant is not pinned here, so it is an attribute.
+        self.pcm_scale = 1.0 / 32768.0
 
         w = torch.hann_window(window_length, periodic=window_periodic, dtype=torch.float64)
         if window_length < n_fft:
@@ -160,7 +164,10 @@ class SpectrogramsHelper(nn.Module):
         return p
 
     def to_spectrogram(self, audio: torch.Tensor) -> torch.Tensor:
-        """``audio [B, T]`` (or ``[T]``) -> ``[B, 2, n_fft/2, frames]`` FP32 on the same GPU."""
+        """``audio [B, T]`` (or ``[T]``) -> ``[B, 2, n_fft/2, frames]`` FP32 on the same GPU.
+
+        ``int16`` audio is read as PCM, ``float(x) * self.pcm_scale`` (bit-identical to
+        converting on the host first); every other dtype is taken as float samples."""
         _lib.require_cuda(audio, "audio")
         if audio.dim() == 1:
             audio = audio[None]
@@ -169,7 +176,7 @@ class SpectrogramsHelper(nn.Module):
         if self.window.device != audio.device:
             raise RuntimeError("helper and audio live on different devices; call .to(device)")
         a = audio.detach()
-        if a.dtype != torch.float32:
+        if a.dtype != torch.int16 and a.dtype != torch.float32:
             a = a.float()
         if not a.is_contiguous():
             a = a.contiguous()
@@ -181,6 +188,8 @@ class SpectrogramsHelper(nn.Module):
                           memory_format=(torch.channels_last if self.channels_last
                                          else torch.contiguous_format))
         params = self._params(frames)
+        if a.dtype == torch.int16:     # 16-bit PCM: converted by the kernel, half the upload
+            params.audio_format, params.pcm_scale = _lib.AUDIO_PCM16, self.pcm_scale
         _lib.invoke("isi_melif_forward", a.data_ptr(), n_notes, n_samples, params,
                                                  out.data_ptr(), _lib.stream_ptr(a.device))
         return out

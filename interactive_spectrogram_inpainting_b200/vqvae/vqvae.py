@@ -25,6 +25,54 @@ from .bottleneck import QuantizedBottleneck
 _DOWN_PLAN = {16: (1, 2, 3, 4), 8: (2, 2, 4), 4: (2, 4), 2: (2,)}
 
 
+# Inference-time epilogue fusion of the conv stacks.  A launch list of one extraction step
+# (profiles/README.md, r02c) showed 49 % of the step in torch's separate bias-add and ReLU
+# kernels around the cuDNN convolutions; under ``torch.no_grad()`` on CUDA the stacks below
+# therefore call cuDNN's fused conv+bias(+residual)+ReLU (``torch.cudnn_convolution_relu`` /
+# ``cudnn_convolution_add_relu``: library code, same math, no extra pass over the
+# activations).  Training and CPU keep the stock modules.
+fused_inference = True
+
+
+def _can_fuse(x: torch.Tensor) -> bool:
+    return (fused_inference and x.is_cuda and not torch.is_grad_enabled()
+            and x.dtype in (torch.float32, torch.float16))
+
+
+def _conv_relu(conv: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
+    return torch.cudnn_convolution_relu(x, conv.weight, conv.bias, conv.stride, conv.padding,
+                                        conv.dilation, conv.groups)
+
+
+def _conv_add_relu(conv: nn.Conv2d, x: torch.Tensor, skip: torch.Tensor) -> torch.Tensor:
+    return torch.cudnn_convolution_add_relu(x, conv.weight, skip, 1.0, conv.bias, conv.stride,
+                                            conv.padding, conv.dilation, conv.groups)
+
+
+def _run_blocks(blocks: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
+    """``blocks(x)``; with fusion, a conv absorbs the ReLU that follows it (explicit, or the
+    one a ResBlock starts with), and a ResBlock absorbs the ReLU that follows IT (the next
+    ResBlock's, or the stack's trailing one) -- so a ResBlock always sees a rectified input,
+    which is also the value its skip connection reads (see ResBlock)."""
+    if not _can_fuse(x):
+        return blocks(x)
+    mods, i, rectified = list(blocks), 0, False
+    while i < len(mods):
+        m = mods[i]
+        nxt = mods[i + 1] if i + 1 < len(mods) else None
+        absorbs = isinstance(nxt, (nn.ReLU, ResBlock))
+        if type(m) is nn.Conv2d and absorbs:
+            x = _conv_relu(m, x)
+        elif isinstance(m, ResBlock) and absorbs:
+            x = x if rectified else torch.relu(x)
+            x = _conv_add_relu(m.conv[3], _conv_relu(m.conv[1], x), x)
+        else:
+            x, absorbs = m(x), False
+        rectified = absorbs or isinstance(m, nn.ReLU)
+        i += 2 if (absorbs and isinstance(nxt, nn.ReLU)) else 1
+    return x
+
+
 class ResBlock(nn.Module):
     """relu -> 3x3 -> relu -> 1x1, added to the *rectified* input: the reference's leading
     in-place ReLU (encoder_decoder.py:22-35) rewrites the tensor the skip reads."""
@@ -60,7 +108,7 @@ class Encoder(nn.Module):
         self.blocks = nn.Sequential(*blocks)
 
     def forward(self, x):
-        return self.blocks(x)
+        return _run_blocks(self.blocks, x)
 
 
 class Decoder(nn.Module):
@@ -85,7 +133,7 @@ class Decoder(nn.Module):
         self.blocks = nn.Sequential(*blocks)
 
     def forward(self, x):
-        return self.blocks(x)
+        return _run_blocks(self.blocks, x)
 
 
 class VQVAE(nn.Module):

@@ -11,6 +11,9 @@ for s in $steps; do
     frontend)
       timeout 900 python -m pytest tests/test_gpu_frontend.py -q 2>&1 | tail -40 > gpurun_out/pytest_frontend_$tag.log
       tail -3 gpurun_out/pytest_frontend_$tag.log ;;
+    extraction)
+      timeout 900 python -m pytest tests/test_gpu_extraction.py -q 2>&1 | tail -40 > gpurun_out/pytest_extraction_$tag.log
+      tail -12 gpurun_out/pytest_extraction_$tag.log ;;
     simt)
       timeout 600 python bench.py --steps 10 --warmup 3 --assign-algo simt --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_simt_$tag.json ;;
     tc)

@@ -34,7 +34,7 @@ static void emulate(const float* audio, int64_t n_notes, int64_t n_samples, int 
       stage_fill(tid, NT, stage.data(), span, note, n_samples, (int64_t)frame * hop - pad_left);
     for (int tid = 0; tid < NT; ++tid)
       for (int fb = tid / 64; fb < nf; fb += kGroups)
-        fft_pass1<P>(tid & 63, stage.data() + fb * hop, aligned8, window, twm.data(), zA.data() + fb * P::kPitchA);
+        fft_pass1<P>(tid & 63, stage.data() + fb * hop, aligned8, 1.f, window, twm.data(), zA.data() + fb * P::kPitchA);
     for (int tid = 0; tid < NT; ++tid)
       for (int fb = tid / 64; fb < nf; fb += kGroups)
         fft_pass2<P>(tid & 63, twm.data(), zA.data() + fb * P::kPitchA);

@@ -1,0 +1,61 @@
+"""GPU checks of the extraction callers around the hot path: the conv stacks with cuDNN's
+fused conv+bias(+skip)+ReLU against the stock module stacks, and ``encode_codes`` end to end."""
+import pytest
+import torch
+
+from interactive_spectrogram_inpainting_b200.utils import synthetic
+from interactive_spectrogram_inpainting_b200.vqvae import vqvae as vq
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+@pytest.fixture
+def fp32_convs():
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32 = old
+    vq.fused_inference = True
+
+
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_fused_conv_stacks_equal_stock_stacks(fp32_convs, channels_last):
+    torch.manual_seed(5)
+    model = vq.VQVAE(in_channel=2, resolution_factors={"bottom": 16, "top": 2}).to(DEV).eval()
+    x = torch.randn(3, 2, 256, 64, device=DEV)
+    if channels_last:
+        model = model.to(memory_format=torch.channels_last)
+        x = x.contiguous(memory_format=torch.channels_last)
+    with torch.no_grad():
+        vq.fused_inference = False
+        stock_b = model.enc_b(x)
+        stock_t = model.enc_t(stock_b)
+        stock_d = model.dec_t(stock_t[:, :64])
+        vq.fused_inference = True
+        fused_b = model.enc_b(x)
+        fused_t = model.enc_t(stock_b)
+        fused_d = model.dec_t(stock_t[:, :64])
+    for got, want in ((fused_b, stock_b), (fused_t, stock_t), (fused_d, stock_d)):
+        assert got.shape == want.shape
+        torch.testing.assert_close(got, want, rtol=1e-4, atol=1e-5)
+    # training (grad enabled) keeps the stock modules: gradients flow
+    y = model.enc_t(stock_b.requires_grad_())
+    y.sum().backward()
+    assert stock_b.grad is not None
+
+
+def test_encode_codes_same_codes_fused_and_stock(fp32_convs):
+    """Same code maps from both paths wherever the search is not a near tie (the two conv
+    paths differ by FP32 rounding only)."""
+    torch.manual_seed(6)
+    model = vq.VQVAE(in_channel=2, resolution_factors={"bottom": 16, "top": 2}).to(DEV).eval()
+    spec = torch.randn(4, 2, 1024, 128, device=DEV)
+    with torch.no_grad():
+        vq.fused_inference = False
+        t0, b0 = model.encode_codes(spec)
+        vq.fused_inference = True
+        t1, b1 = model.encode_codes(spec)
+    assert t0.shape == (4, 32, 4) and b0.shape == (4, 64, 8)
+    assert (t0 == t1).float().mean() > 0.995
+    assert (b0 == b1).float().mean() > 0.995

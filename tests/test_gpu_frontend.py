@@ -111,3 +111,24 @@ def test_band_table_pitch_and_dropped_nyquist_in_mel_mode():
     helper = MelSpectrogramsHelper(drop_bin="nyquist").to(DEV)
     cfg = fo.FrontEndConfig(drop_bin="nyquist")
     check_against_oracle(helper.to_spectrogram(audio.to(DEV)).cpu(), audio, cfg)
+
+
+@pytest.mark.parametrize("n_fft,hop,samples", [(2048, 512, 64000), (2048, 512, 9999), (1024, 256, 8001),
+                                               (512, 128, 4096)])
+def test_pcm16_input_equals_float_input(n_fft, hop, samples):
+    """int16 PCM audio (NSynth's storage format) is converted inside the kernel,
+    float(x) * pcm_scale: the same bits as converting first and uploading FP32 -- on the
+    bulk-copy path (aligned sizes) and on the per-thread staging path (ragged sizes)."""
+    audio = synthetic.synthetic_notes(3, n_samples=samples)
+    pcm = (audio * 32767.0).round().clamp(-32768, 32767).to(torch.int16)
+    helper = MelSpectrogramsHelper(n_fft=n_fft, hop_length=hop, window_length=n_fft).to(DEV)
+    as_float = pcm.to(DEV).float() * helper.pcm_scale
+    want = helper.to_spectrogram(as_float)
+    got = helper.to_spectrogram(pcm.to(DEV))
+    assert got.dtype == torch.float32 and torch.equal(got, want)
+    helper.pcm_scale = 1.0 / 32767.0
+    assert torch.equal(helper.to_spectrogram(pcm.to(DEV)),
+                       helper.to_spectrogram(pcm.to(DEV).float() * torch.tensor(1.0 / 32767.0, device=DEV)))
+    # and the float result is the oracle's
+    cfg = fo.FrontEndConfig(n_fft=n_fft, hop_length=hop, window_length=n_fft)
+    check_against_oracle(want.cpu(), as_float.cpu(), cfg)

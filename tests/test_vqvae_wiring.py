@@ -31,3 +31,33 @@ def test_state_dict_and_encode_match_reference(factors):
         od = ours.decode_code(o[3], o[4])
         torch.testing.assert_close(rd, od)
     assert sum(p.numel() for p in ours.parameters()) == sum(p.numel() for p in ref.parameters())
+
+
+def test_fused_stack_walker_is_the_same_function(monkeypatch):
+    """The inference path that folds bias/ReLU/skip-add into the convolutions (cuDNN fused ops
+    on CUDA) must compute exactly what the module stack computes: run its control flow on
+    the CPU with the two fused calls replaced by their definitions."""
+    import torch.nn.functional as F
+    from interactive_spectrogram_inpainting_b200.vqvae import vqvae as mod
+
+    def conv(c, x):
+        return F.conv2d(x, c.weight, c.bias, c.stride, c.padding, c.dilation, c.groups)
+
+    monkeypatch.setattr(mod, "_can_fuse", lambda x: True)
+    monkeypatch.setattr(mod, "_conv_relu", lambda c, x: torch.relu(conv(c, x)))
+    monkeypatch.setattr(mod, "_conv_add_relu", lambda c, x, skip: torch.relu(conv(c, x) + skip))
+    torch.manual_seed(3)
+    for factor, n_res in ((16, 2), (2, 2), (4, 0), (8, 1)):
+        enc = mod.Encoder(2, 32, n_res, 8, factor).eval()
+        dec = mod.Decoder(32, 2, 32, n_res, 8, factor).eval()
+        x = torch.randn(2, 2, 64, 32)
+        with torch.no_grad():
+            want = enc.blocks(x)
+            got = enc(x)
+            torch.testing.assert_close(got, want, rtol=1e-6, atol=1e-6)
+            torch.testing.assert_close(dec(got), dec.blocks(want), rtol=1e-6, atol=1e-6)
+    # a ResBlock that does not follow a convolution still rectifies its own input
+    stack = torch.nn.Sequential(mod.ResBlock(4, 2), torch.nn.ReLU()).eval()
+    x = torch.randn(1, 4, 8, 8)
+    with torch.no_grad():
+        torch.testing.assert_close(mod._run_blocks(stack, x), stack(x), rtol=1e-6, atol=1e-6)
