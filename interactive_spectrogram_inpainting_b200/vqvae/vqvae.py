@@ -36,6 +36,7 @@ fused_inference = True
 
 def _can_fuse(x: torch.Tensor) -> bool:
     return (fused_inference and x.is_cuda and not torch.is_grad_enabled()
+            and torch.backends.cudnn.enabled and not torch.is_autocast_enabled()
             and x.dtype in (torch.float32, torch.float16))
 
 
@@ -257,3 +258,46 @@ class VQVAE(nn.Module):
     def store_instantiation_parameters(self, path: pathlib.Path) -> None:
         with open(path, 'w') as f:
             json.dump(self._instantiation_parameters, f, indent=4)
+
+
+class GraphedDecodeCode:
+    """``model.decode_code`` for one fixed pair of code-map shapes, replayed from a CUDA graph.
+
+    The interactive server decodes one edited pair of code maps per request
+    (``flask_server.py:593-596``): at batch 1 the two lookups and the ~40 decoder kernels are
+    launch-latency bound (0.46 ms eager, 0.20 ms replayed on a B200, profiles/README.md).  The
+    graph captures the lookup kernels of this repo and the cuDNN decoder on a private stream;
+    a call copies the new codes into the captured input buffers and replays.
+
+    The model must be in eval mode with a codebook that no longer changes (the graph holds
+    the address of the prepared codebook).  The returned tensor is the graph's output buffer:
+    it is overwritten by the next call -- ``clone()`` it to keep it.  Not thread-safe; give
+    each request thread its own instance."""
+
+    def __init__(self, model: VQVAE, code_t: torch.Tensor, code_b: torch.Tensor, warmup: int = 3):
+        if model.training:
+            raise RuntimeError("GraphedDecodeCode needs model.eval()")
+        if not (code_t.is_cuda and code_b.is_cuda):
+            raise RuntimeError("code maps must be CUDA tensors: there is no CPU fallback")
+        self.model = model
+        self._code_t = code_t.detach().long().clone()
+        self._code_b = code_b.detach().long().clone()
+        stream = torch.cuda.Stream(code_t.device)
+        stream.wait_stream(torch.cuda.current_stream(code_t.device))
+        with torch.no_grad(), torch.cuda.stream(stream):
+            for _ in range(max(1, warmup)):        # cuDNN plan selection happens outside the capture
+                model.decode_code(self._code_t, self._code_b)
+        torch.cuda.current_stream(code_t.device).wait_stream(stream)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self._graph):
+            self._out = model.decode_code(self._code_t, self._code_b)
+
+    def __call__(self, code_t: torch.Tensor, code_b: torch.Tensor) -> torch.Tensor:
+        if code_t.shape != self._code_t.shape or code_b.shape != self._code_b.shape:
+            raise ValueError(f"captured for code maps {tuple(self._code_t.shape)} / "
+                             f"{tuple(self._code_b.shape)}, got {tuple(code_t.shape)} / {tuple(code_b.shape)}")
+        self._code_t.copy_(code_t, non_blocking=True)
+        self._code_b.copy_(code_b, non_blocking=True)
+        self._graph.replay()
+        return self._out
+

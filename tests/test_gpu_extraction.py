@@ -59,3 +59,24 @@ def test_encode_codes_same_codes_fused_and_stock(fp32_convs):
     assert t0.shape == (4, 32, 4) and b0.shape == (4, 64, 8)
     assert (t0 == t1).float().mean() > 0.995
     assert (b0 == b1).float().mean() > 0.995
+
+
+def test_graphed_decode_code_equals_eager():
+    torch.manual_seed(7)
+    model = vq.VQVAE(in_channel=2, resolution_factors={"bottom": 16, "top": 2}).to(DEV).eval()
+    top, bottom = synthetic.synthetic_codemaps(2)
+    top, bottom = top.to(DEV), bottom.to(DEV)
+    graphed = vq.GraphedDecodeCode(model, top, bottom)
+    with torch.no_grad():
+        want = model.decode_code(top, bottom)
+        torch.testing.assert_close(graphed(top, bottom), want, rtol=1e-3, atol=1e-4)
+        top2 = (top + 17) % model.n_embed_t
+        bottom2 = (bottom * 3 + 1) % model.n_embed_b
+        want2 = model.decode_code(top2, bottom2)
+        got2 = graphed(top2, bottom2).clone()
+        torch.testing.assert_close(got2, want2, rtol=1e-3, atol=1e-4)
+        assert not torch.allclose(got2, want)
+    with pytest.raises(ValueError):
+        graphed(top[:1], bottom[:1])
+    with pytest.raises(RuntimeError):
+        vq.GraphedDecodeCode(model.train(), top, bottom)

@@ -21,7 +21,7 @@ import torch  # noqa: E402
 
 from interactive_spectrogram_inpainting_b200.utils import synthetic  # noqa: E402
 from interactive_spectrogram_inpainting_b200.vqvae.bottleneck import QuantizedBottleneck  # noqa: E402
-from interactive_spectrogram_inpainting_b200.vqvae.vqvae import VQVAE  # noqa: E402
+from interactive_spectrogram_inpainting_b200.vqvae.vqvae import VQVAE, GraphedDecodeCode  # noqa: E402
 
 DEV = torch.device("cuda:0")
 
@@ -89,17 +89,9 @@ def cfg5():
             lookup_ms = timed(lambda: (model.quantize_t.embed_code(top), model.quantize_b.embed_code(bottom)))
             eager_ms = timed(lambda: model.decode_code(top, bottom))
             # CUDA graph of the whole decode (lookup kernels + conv decoder)
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):
-                for _ in range(3):
-                    model.decode_code(top, bottom)
-            torch.cuda.current_stream().wait_stream(side)
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                static_out = model.decode_code(top, bottom)
-            graph_ms = timed(graph.replay)
-            assert torch.allclose(static_out, model.decode_code(top, bottom), rtol=1e-3, atol=1e-4)
+            graphed = GraphedDecodeCode(model, top, bottom)
+            graph_ms = timed(lambda: graphed(top, bottom))
+            assert torch.allclose(graphed(top, bottom), model.decode_code(top, bottom), rtol=1e-3, atol=1e-4)
         out.append({"batch": b, "embed_code_top_plus_bottom_ms": lookup_ms,
                     "decode_code_eager_ms": eager_ms, "decode_code_cuda_graph_ms": graph_ms})
     return out
