@@ -415,10 +415,13 @@ def b200_arm(args):
                    "reasons": clk["reasons"], "samples": clk["samples"]},
         "roofline": {"kernel": "melif_kernel<2048,4,256>", "bound": "hbm", "achieved": melif_gbs,
                      "peak": hbm_peak, "unit": "GB/s", "frac": melif_gbs / hbm_peak,
-                     # dram__bytes_read+write of one launch from the committed ncu capture
-                     # (profiles/r01_melif_v4b_r01e_ncu_summary.csv: 76.2 + 259.6 MB at 296 notes,
-                     # channels_last output), scaled to this batch
-                     "traffic": (76.168704e6 + 259.628288e6) / 296 * B if cl else None,
+                     # dram__bytes_read + dram__bytes_write of one 444-note launch from the
+                     # committed ncu captures of this kernel (channels_last output), scaled to
+                     # this batch: profiles/r01_melif_v6_pcm16_r02j_ncu_summary.csv (57.4 +
+                     # 414.8 MB) and profiles/r01_melif_v6_r02b_ncu_summary.csv (114.3 + 413.8 MB);
+                     # ~50 MB of the last notes' output is still dirty in L2 when the kernel ends
+                     "traffic": ((57.426944e6 + 414.775296e6) if args.audio == "pcm16"
+                                 else (114.308608e6 + 413.754112e6)) / 444 * B if cl else None,
                      "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
                      "ms_per_launch": melif_ms, "algorithmic_bytes_per_launch": melif_bytes_per_note * B},
         "rooflines_other": [
