@@ -30,6 +30,7 @@ class SpectrogramBatches:
                  device: torch.device, transform: Optional[Callable] = None, prefetch: bool = True):
         self.source, self.helper, self.device, self.transform = source, spectrograms_helper, device, transform
         self.prefetch = prefetch
+        self._side = None        # one copy stream per loader, so its allocator pool is reused
 
     def _upload(self, item, stream):
         audio, names = item
@@ -43,7 +44,9 @@ class SpectrogramBatches:
         """With ``prefetch`` the host->device copy of batch i+1 (pinned source memory) runs
         on a side stream while batch i is transformed and encoded."""
         main = torch.cuda.current_stream(self.device)
-        side = torch.cuda.Stream(self.device) if self.prefetch else main
+        if self.prefetch and self._side is None:
+            self._side = torch.cuda.Stream(self.device)
+        side = self._side if self.prefetch else main
         it = iter(self.source)
         pending = None
         for item in it:
