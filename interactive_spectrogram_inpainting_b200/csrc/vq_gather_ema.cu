@@ -232,13 +232,14 @@ vq_gather_rowmajor_kernel(const float* __restrict__ x, int64_t x_row_stride,
 // Training statistics with CTA-private accumulators (row-major input, K*D*4 <= ~140 KB):
 // the segmented reduction proper.  Persistent CTAs each keep a full [K, D] accumulator in
 // shared memory; inside a CTA every code is OWNED by one warp (code % 16), so rows are
-// added with plain ld/add/st -- no atomics, no conflicts -- and runs of equal codes are
-// first summed in registers.  Global memory sees one vector reduction per (CTA, used code)
-// at the very end: 148 x 128 KB at most, instead of 256 B of atomics per row.
+// added with plain ld/add/st -- no atomics, no conflicts.  Global memory sees one vector
+// reduction per (CTA, used code) at the very end: 148 x 128 KB at most, instead of 256 B of
+// atomics per row.
 // ---------------------------------------------------------------------------
 constexpr int kStatsWarps = 16;                     // consumer warps (+ producer + dispatcher)
 constexpr int kStatsThreads = (kStatsWarps + 2) * 32;
 constexpr int kGranuleRows = 64;                    // rows per pipeline stage
+constexpr int kHotElectionGranule = 1;              // the hot code is elected when this granule is listed
 
 // per-stage work lists: for every consumer warp the granule rows whose code it owns
 struct StageLists {
@@ -251,10 +252,15 @@ struct StageLists {
 //    shared-memory stages with cp.async.bulk;
 //  * a dispatcher warp turns each granule's codes into per-owner row lists (owner = code % 16;
 //    two match.any + prefix popcounts per granule);
-//  * 16 consumer warps each take 4 rows of the granule for lookup / commitment / output, then
-//    walk THEIR list and add those rows to the CTA-private [K, D] accumulator with plain
-//    ld/add/st -- a code is only ever touched by its owner, so there are no atomics and no
-//    conflicts -- and finally signal the stage empty.
+//  * 16 consumer warps each take 4 rows of the granule for lookup / commitment / output (the
+//    codewords are requested from L2 one granule ahead), then walk THEIR list two rows at a
+//    time and add those rows to the CTA-private [K, D] accumulator with plain ld/add/st -- a
+//    code is only ever touched by its owner, so there are no atomics and no conflicts -- and
+//    finally signal the stage empty;
+//  * ownership by code is unbalanced when one code is very popular (silence; a collapsed
+//    codebook): the dispatcher elects the CTA's hot code from the first stages, keeps its rows
+//    out of the lists, and every consumer warp sums the hot rows among its own 4 rows of each
+//    granule in registers (merged into the accumulator once, at the end).
 // Global memory sees one red.global.add.v4.f32 per (CTA, used code) at the very end.
 template <int D, int STAGES>
 __global__ void __launch_bounds__(kStatsThreads, 1)
@@ -276,6 +282,7 @@ vq_gather_stats_smem_kernel(const float* __restrict__ x, const int64_t* __restri
   uint64_t* full = reinterpret_cast<uint64_t*>(lists + STAGES);
   uint64_t* ready = full + STAGES;
   uint64_t* empty = ready + STAGES;
+  int* hot_slot = reinterpret_cast<int*>(empty + STAGES);   // the CTA's hot code (-1: none)
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < n_embed * D + ((n_embed + 31) & ~31); i += kStatsThreads) smem[i] = 0.f;
@@ -328,6 +335,7 @@ vq_gather_stats_smem_kernel(const float* __restrict__ x, const int64_t* __restri
     }
   } else if (warp == kStatsWarps + 1) {
     // ===================== dispatcher =====================
+    int hot = -1;
     for (int64_t g = 0; g < total; ++g) {
       const int s = (int)(g % STAGES);
       int64_t row0;
@@ -335,14 +343,48 @@ vq_gather_stats_smem_kernel(const float* __restrict__ x, const int64_t* __restri
       umma::mbar_wait(umma::s32(full + s), (uint32_t)((g / STAGES) & 1));
       const long long* it = idx + s * kGranuleRows;
       StageLists& L = lists[s];
+      if (g == kHotElectionGranule) {
+        // A code that takes >= 1/12 of the rows in the ring at this point is this CTA's hot
+        // code for the rest of the launch (silence in a spectrogram, a collapsed codebook): its
+        // rows stay out of the owner lists -- one warp would have to add them all -- and every
+        // consumer warp sums the ones among its OWN rows in registers instead.  The sample is
+        // the index arrays of all stages filled so far (whichever granules they hold).
+        const int n_sample = (int)min((int64_t)STAGES, total) * kGranuleRows;
+        for (int64_t ahead = g + 1; ahead < min((int64_t)STAGES, total); ++ahead)   // first fills
+          umma::mbar_wait(umma::s32(full + (int)ahead), 0u);
+        // candidates: the codes of this granule (two per lane); votes: every sampled row
+        const int* low = reinterpret_cast<const int*>(idx);          // low words of the int64 codes
+        int mine[kGranuleRows / 32], votes[kGranuleRows / 32];
+#pragma unroll
+        for (int i = 0; i < kGranuleRows / 32; ++i) {
+          const long long v = it[i * 32 + lane];
+          mine[i] = (i * 32 + lane < rows && v >= 0 && v < n_embed) ? (int)v : -2;
+          votes[i] = 0;
+        }
+#pragma unroll 4
+        for (int j = 0; j < n_sample; ++j) {
+          const int cj = low[2 * j];
+#pragma unroll
+          for (int i = 0; i < kGranuleRows / 32; ++i) votes[i] += (cj == mine[i]);
+        }
+        int best = 0;
+#pragma unroll
+        for (int i = 0; i < kGranuleRows / 32; ++i)
+          if (mine[i] >= 0) best = max(best, (votes[i] << 16) | mine[i]);
+        best = __reduce_max_sync(0xffffffffu, best);
+        hot = (best >> 16) * 12 >= n_sample ? (best & 0xffff) : -1;
+        if (lane == 0) *hot_slot = hot;
+        __syncwarp();
+      }
       int base = 0;        // rows of the first half already listed for this lane's owner
 #pragma unroll
       for (int half = 0; half < kGranuleRows / 32; ++half) {
         const int r = half * 32 + lane;
         const long long v = it[r];
-        const bool ok = r < rows && v >= 0 && v < n_embed;
-        if (r < rows && !ok && status_flag) atomicExch(status_flag, 1);
-        const int owner = ok ? (int)(v % kStatsWarps) : -1 - lane;      // invalid rows match nobody
+        const bool valid = r < rows && v >= 0 && v < n_embed;
+        if (r < rows && !valid && status_flag) atomicExch(status_flag, 1);
+        const bool ok = valid && v != hot;
+        const int owner = ok ? (int)(v % kStatsWarps) : -1 - lane;      // unlisted rows match nobody
         const unsigned peers = __match_any_sync(0xffffffffu, owner);
         const int pos = __popc(peers & ((1u << lane) - 1));
         if (half == 1 && ok) base = L.count[owner];
@@ -363,75 +405,117 @@ vq_gather_stats_smem_kernel(const float* __restrict__ x, const int64_t* __restri
   } else {
     // ===================== consumers =====================
     float sq = 0.f;
-    float sticky[VPL];
-    int sticky_code = -1, sticky_len = 0, misses = 0;
-    auto flush_sticky = [&]() {
-      if (sticky_code >= 0) {
-        float* a = acc + (size_t)sticky_code * D + lane * VPL;
+    float hot_sum[VPL];
+    int hot = -1, hot_len = 0;
 #pragma unroll
-        for (int v2 = 0; v2 < VPL; ++v2) a[v2] += sticky[v2];
-        if (lane == 0) cnt[sticky_code] += (float)sticky_len;
+    for (int v2 = 0; v2 < VPL; ++v2) hot_sum[v2] = 0.f;
+    // The codebook rows of this warp's kRowsPerWarp rows of a granule come from L2 (~600
+    // cycles); they are requested one granule ahead, so the latency hides behind the previous
+    // granule's list walk.
+    constexpr int kIters = kRowsPerWarp / kRowsPerInstr;
+    float4 q_cur[kIters], q_next[kIters];
+    auto request_codewords = [&](int64_t g, float4* q) {
+      const int s = (int)(g % STAGES);
+      const long long* it = idx + s * kGranuleRows;
+      int64_t row0;
+      const int rows_here = rows_in(g, row0);
+      umma::mbar_wait(umma::s32(full + s), (uint32_t)((g / STAGES) & 1));
+#pragma unroll
+      for (int k = 0; k < kIters; ++k) {
+        const int r = warp * kRowsPerWarp + k * kRowsPerInstr + lane / C4, j = lane % C4;
+        const long long v = r < rows_here ? it[r] : -1;
+        q[k] = (v >= 0 && v < n_embed) ? __ldg(reinterpret_cast<const float4*>(et + v * D) + j)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
+    if (total > 0) request_codewords(0, q_cur);
     for (int64_t g = 0; g < total; ++g) {
       const int s = (int)(g % STAGES);
       const float* xt = xs + (size_t)s * kGranuleRows * D;
       const long long* it = idx + s * kGranuleRows;
       int64_t row0;
       const int rows_here = rows_in(g, row0);
-      umma::mbar_wait(umma::s32(full + s), (uint32_t)((g / STAGES) & 1));
-      // lookup, commitment term, output for this warp's rows of the granule
+      // lookup, commitment term, output for this warp's rows of the granule (stage g is full:
+      // request_codewords(g) waited for it)
 #pragma unroll
-      for (int k = 0; k < kRowsPerWarp; k += kRowsPerInstr) {
-        const int r = warp * kRowsPerWarp + k + lane / C4, j = lane % C4;
+      for (int k = 0; k < kIters; ++k) {
+        const int r = warp * kRowsPerWarp + k * kRowsPerInstr + lane / C4, j = lane % C4;
         if (r < rows_here) {
-          const long long v = it[r];
-          const bool ok = v >= 0 && v < n_embed;
           const float4 xv = reinterpret_cast<const float4*>(xt + r * D)[j];
-          float4 q = ok ? __ldg(reinterpret_cast<const float4*>(et + v * D) + j)
-                        : make_float4(0.f, 0.f, 0.f, 0.f);
+          float4 q = q_cur[k];
           const float4 t = make_float4(q.x - xv.x, q.y - xv.y, q.z - xv.z, q.w - xv.w);
           sq = fmaf(t.x, t.x, sq); sq = fmaf(t.y, t.y, sq); sq = fmaf(t.z, t.z, sq); sq = fmaf(t.w, t.w, sq);
           q = make_float4(xv.x + t.x, xv.y + t.y, xv.z + t.z, xv.w + t.w);     // bottleneck.py:95
           if (out_q) reinterpret_cast<float4*>(out_q + (row0 + r) * q_row_stride)[j] = q;
         }
       }
-      // statistics: walk this warp's list of owned rows
+      if (g + 1 < total) request_codewords(g + 1, q_next);
+      // statistics: walk this warp's list of owned rows and add them to the accumulator rows
+      // with plain ld/add/st (nobody else touches the codes this warp owns)
       umma::mbar_wait(umma::s32(ready + s), (uint32_t)((g / STAGES) & 1));
       const StageLists& L = lists[s];
       const int n_mine = L.count[warp];
-      // A "sticky" code is accumulated in registers (a popular code would otherwise serialise
-      // on the read-modify-write of its accumulator row); every other code goes straight to
-      // shared memory, where distinct rows pipeline.  After 8 consecutive misses the sticky
-      // slot is flushed and handed to the current code.
-#pragma unroll 2
-      for (int k = 0; k < n_mine; ++k) {
-        const int r = L.row[warp][k];
-        const int c = (int)it[r];
-        const float* xr = xt + r * D + lane * VPL;
-        if (c == sticky_code) {
+      if (g == kHotElectionGranule) hot = *hot_slot;
+      if (hot >= 0) {
+        // the hot code's rows among this warp's own rows of the granule
 #pragma unroll
-          for (int v2 = 0; v2 < VPL; ++v2) sticky[v2] += xr[v2];
-          ++sticky_len; misses = 0;
-        } else if (++misses > 8 || sticky_code < 0) {
-          flush_sticky();
-          sticky_code = c; sticky_len = 1; misses = 0;
+        for (int k = 0; k < kRowsPerWarp; ++k) {
+          const int r = warp * kRowsPerWarp + k;
+          if (r < rows_here && it[r] == hot) {
 #pragma unroll
-          for (int v2 = 0; v2 < VPL; ++v2) sticky[v2] = xr[v2];
-        } else {
-          float* a = acc + (size_t)c * D + lane * VPL;
+            for (int v2 = 0; v2 < VPL; ++v2) hot_sum[v2] += xt[r * D + lane * VPL + v2];
+            ++hot_len;
+          }
+        }
+      }
+      // the list entries (row, code) are read lane-parallel once and broadcast by shuffles, two
+      // rows per step, so the row loads of a step are independent of each other
+      for (int base = 0; base < n_mine; base += 32) {
+        const int left = min(32, n_mine - base);
+        const int my_r = lane < left ? L.row[warp][base + lane] : 0;
+        const int my_c = lane < left ? (int)it[my_r] : -1;
+        for (int k = 0; k < left; k += 2) {
+          const int ra = __shfl_sync(0xffffffffu, my_r, k), ca = __shfl_sync(0xffffffffu, my_c, k);
+          const int kb = k + 1 < left ? k + 1 : k;
+          const int rb = __shfl_sync(0xffffffffu, my_r, kb), cb = __shfl_sync(0xffffffffu, my_c, kb);
+          float xa[VPL], xb[VPL];
 #pragma unroll
-          for (int v2 = 0; v2 < VPL; ++v2) a[v2] += xr[v2];
-          if (lane == 0) cnt[c] += 1.f;
+          for (int v2 = 0; v2 < VPL; ++v2) {
+            xa[v2] = xt[ra * D + lane * VPL + v2];
+            xb[v2] = xt[rb * D + lane * VPL + v2];
+          }
+          float* pa = acc + (size_t)ca * D + lane * VPL;
+          float* pb = acc + (size_t)cb * D + lane * VPL;
+          if (k + 1 >= left || ca == cb) {
+            const bool two = k + 1 < left;
+#pragma unroll
+            for (int v2 = 0; v2 < VPL; ++v2) pa[v2] += two ? xa[v2] + xb[v2] : xa[v2];
+            if (lane == 0) cnt[ca] += two ? 2.f : 1.f;
+          } else {
+            // two different accumulator rows: independent read-modify-writes, loads first
+            float va[VPL], vb[VPL];
+#pragma unroll
+            for (int v2 = 0; v2 < VPL; ++v2) { va[v2] = pa[v2]; vb[v2] = pb[v2]; }
+#pragma unroll
+            for (int v2 = 0; v2 < VPL; ++v2) { pa[v2] = va[v2] + xa[v2]; pb[v2] = vb[v2] + xb[v2]; }
+            if (lane == 0) { const float na = cnt[ca], nb = cnt[cb]; cnt[ca] = na + 1.f; cnt[cb] = nb + 1.f; }
+          }
         }
       }
       __syncwarp();
       if (lane == 0) umma::mbar_arrive(umma::s32(empty + s));       // this warp is done with the stage
+#pragma unroll
+      for (int k = 0; k < kIters; ++k) q_cur[k] = q_next[k];
     }
-    flush_sticky();
     sq = warp_sum(sq);
     if (lane == 0 && sq != 0.f) atomicAdd(&partials[blockIdx.x], (double)sq);
     asm volatile("bar.sync 1, %0;" ::"n"(kStatsWarps * 32) : "memory");   // consumers only
+    if (hot_len > 0) {        // 16 warps at most, once per launch: shared-memory atomics are fine
+#pragma unroll
+      for (int v2 = 0; v2 < VPL; ++v2) atomicAdd(acc + (size_t)hot * D + lane * VPL + v2, hot_sum[v2]);
+      if (lane == 0) atomicAdd(cnt + hot, (float)hot_len);
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(kStatsWarps * 32) : "memory");
     // one vector reduction per used code of this CTA
     for (int k = warp; k < n_embed; k += kStatsWarps) {
       const float n = cnt[k];
