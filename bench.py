@@ -216,7 +216,8 @@ def b200_arm(args):
     torch.manual_seed(0)
     torch.backends.cudnn.benchmark = bool(args.cudnn_benchmark)   # conv algorithm autotuning
     cl = bool(args.channels_last)
-    helper = MelSpectrogramsHelper(channels_last=cl).to(dev)
+    s2d = bool(args.space_to_depth) and cl
+    helper = MelSpectrogramsHelper(channels_last=cl, space_to_depth=s2d).to(dev)
     model = VQVAE(**MODEL_KW).to(dev).eval()
     if cl:      # same values, NHWC storage end to end: no cuDNN layout-conversion kernels
         model = model.to(memory_format=torch.channels_last)
@@ -236,7 +237,7 @@ def b200_arm(args):
 
     def step(src):
         with torch.no_grad():
-            return model.encode_codes(helper.to_spectrogram(src))
+            return model.encode_codes(helper.to_spectrogram(src), space_to_depth=s2d)
 
     def max_over_ranks(ms):
         if world == 1:
@@ -302,7 +303,7 @@ def b200_arm(args):
     # ---- hot path only: (1) + (2) on pre-computed conv features ----
     with torch.no_grad():
         spec = helper.to_spectrogram(audio)
-        enc_b = model.enc_b(spec)
+        enc_b = model.enc_b(spec, space_to_depth=s2d)
         feat_t = model.quantize_conv_t(model.enc_t(enc_b)).permute(0, 2, 3, 1)
         q_t = model.quantize_t(feat_t)[0].permute(0, 3, 1, 2)
         feat_b = model.quantize_conv_b(torch.cat([model.dec_t(q_t), enc_b], 1)).permute(0, 2, 3, 1)
@@ -394,7 +395,9 @@ def b200_arm(args):
                                "encode (bottom 16 / top 2, K=512, D=64) -> top+bottom codes",
                    "notes_per_step_per_gpu": B, "sharding": "notes sharded per rank, no collective",
                    "conv_encoder": "torch/cuDNN fp32 (TF32 convs as torch defaults), random init, "
-                                   + ("channels_last storage" if cl else "NCHW storage"),
+                                   + ("channels_last storage" if cl else "NCHW storage")
+                                   + (", first conv as 3x3 over the front end's 2x2 space-to-depth output"
+                                      if s2d else ""),
                    "l2": f"inputs exceed L2 (126 MB): {B * 0.064 * host_audio.element_size():.0f} MB audio + "
                          f"{B * 1.0486:.0f} MB spectrogram per step",
                    "assign_algo": args.assign_algo,
@@ -475,6 +478,8 @@ def main():
                     help="sample format of the input notes: int16 PCM as the dataset stores them "
                          "(converted in the front-end kernel) or float32 as the reference uploads them")
     ap.add_argument("--cudnn-benchmark", type=int, default=1)
+    ap.add_argument("--space-to-depth", type=int, default=1,
+                    help="front end writes 2x2 space-to-depth blocks; the first conv runs as 3x3 stride 1")
     ap.add_argument("--channels-last", type=int, default=1,
                     help="1: spectrogram + conv stack in torch.channels_last storage (default)")
     args = ap.parse_args()

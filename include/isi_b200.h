@@ -192,6 +192,10 @@ typedef struct isi_melif_params {
   int32_t channels_last;    /* 0: out is [B,2,F,T'] planes (the reference layout);   */
                             /* 1: the same logical tensor in torch channels_last     */
                             /*    storage [B,F,T',2] (what the cuDNN convs consume)  */
+                            /* 2: 2x2 space-to-depth blocks, [B,F/2,T'/2,(f&1,t&1,c)]: */
+                            /*    the encoder's first conv (4x4, stride 2, 2 input      */
+                            /*    channels, encoder_decoder.py:66-70) becomes a 3x3      */
+                            /*    stride-1 conv over 8 channels; needs even n_frames     */
   /* fused epilogue (both live in GANsynth_pytorch in the reference):       */
   int32_t mask_phase;       /* 1: channel 1 := 0 where channel 0 < mask_threshold (the       */
   float mask_threshold;     /*    masked-phase transform, extract_code.py:178-181)           */
@@ -204,6 +208,7 @@ typedef struct isi_melif_params {
 } isi_melif_params;
 
 typedef enum { ISI_AUDIO_F32 = 0, ISI_AUDIO_PCM16 = 1 } isi_audio_format;
+typedef enum { ISI_SPEC_PLANAR = 0, ISI_SPEC_CHANNELS_LAST = 1, ISI_SPEC_SPACE_TO_DEPTH = 2 } isi_spec_layout;
 
 /*
  * audio [n_notes, n_samples] (contiguous; FP32 or int16 per h_params->audio_format)

@@ -249,6 +249,26 @@ melif_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params p,
           emit_linear<FB>(zA, P::kPitchA, row_bin[r], v0, v1);
         apply_epilogue<FB>(v0, v1, p.mask_phase != 0, p.mask_threshold, p.out_scale[0], p.out_bias[0],
                            p.out_scale[1], p.out_bias[1]);
+        if (p.channels_last == ISI_SPEC_SPACE_TO_DEPTH) {
+          // [B, F/2, T'/2, (f&1, t&1, channel)]: 2x2 spectrogram blocks as 8 channels.  A row
+          // writes 16 bytes per block; the odd/even row pair (neighbouring lanes of the same
+          // instruction) completes each 32-byte sector.
+          float* d = out + ((((int64_t)note_idx * (M / 2) + (row >> 1)) * (p.n_frames >> 1) + (f0 >> 1)) * 8) +
+                     (row & 1) * 4;
+          if (nf == FB && (FB % 2 == 0)) {
+#pragma unroll
+            for (int q = 0; q < FB / 2; ++q)
+              st_stream4(d + 8 * q, make_float4(v0[2 * q], v1[2 * q], v0[2 * q + 1], v1[2 * q + 1]));
+          } else {
+#pragma unroll
+            for (int fb = 0; fb < FB; ++fb)
+              if (fb < nf) {
+                float* e = d + (fb >> 1) * 8 + (fb & 1) * 2;
+                e[0] = v0[fb]; e[1] = v1[fb];
+              }
+          }
+          continue;
+        }
         if (p.channels_last) {
           // [B, F, T', 2]: the FB time steps of both channels are one contiguous run
           float* d = out + (((int64_t)note_idx * M + row) * p.n_frames + f0) * 2;

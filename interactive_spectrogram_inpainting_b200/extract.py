@@ -31,6 +31,9 @@ class SpectrogramBatches:
         self.source, self.helper, self.device, self.transform = source, spectrograms_helper, device, transform
         self.prefetch = prefetch
         self._side = None        # one copy stream per loader, so its allocator pool is reused
+        # the helper may write 2x2 space-to-depth blocks (see SpectrogramsHelper); the encoder
+        # has to be told (extract_codes reads this attribute)
+        self.space_to_depth = bool(getattr(spectrograms_helper, "space_to_depth", False))
 
     def _upload(self, item, stream):
         audio, names = item
@@ -110,10 +113,13 @@ def extract_codes(loader: Iterable[Tuple[torch.Tensor, Sequence[str]]], model,
         rows.extend(batch_rows)
 
     model.eval()
+    s2d = bool(getattr(loader, "space_to_depth", False))
     for step, (spec, names) in enumerate(loader):
         if hasattr(model, "encode_codes"):
-            id_t, id_b = model.encode_codes(spec)
+            id_t, id_b = model.encode_codes(spec, space_to_depth=True) if s2d else model.encode_codes(spec)
         else:
+            if s2d:
+                raise ValueError("space-to-depth spectrograms need this repo's VQVAE.encode_codes")
             out = model.encode(spec)
             id_t, id_b = out[3], out[4]
         host_t, host_b = staging_pair(step % 2, id_t, id_b)

@@ -95,7 +95,7 @@ class SpectrogramsHelper(nn.Module):
                  window_length: int = 2048, safelog_eps: float = 1e-6, *,
                  pad_left: Optional[int] = None, n_frames: Optional[int] = None,
                  drop_bin: str = "dc", window_periodic: bool = True,
-                 channels_last: bool = False,
+                 channels_last: bool = False, space_to_depth: bool = False,
                  masked_phase_threshold: Optional[float] = None,
                  output_affine=None):
         super().__init__()
@@ -116,6 +116,12 @@ class SpectrogramsHelper(nn.Module):
         # True: to_spectrogram returns the same [B,2,F,T'] tensor in torch.channels_last
         # storage, which is what the cuDNN conv encoder wants (no layout-conversion kernels)
         self.channels_last = channels_last
+        # True: to_spectrogram returns the 2x2 space-to-depth form of the spectrogram,
+        # ``[B, 8, F/2, T'/2]`` in channels_last storage with channel = (f&1)*4 + (t&1)*2 + c
+        # (``from_space_to_depth`` undoes it).  The VQ-VAE's first convolution -- 4x4, stride 2
+        # over 2 input channels, the slowest kernel of an extraction step -- is a 3x3 stride-1
+        # convolution over these 8 channels (vqvae.Encoder, ``space_to_depth=True``).
+        self.space_to_depth = space_to_depth
         # Fused epilogue (both are GANsynth_pytorch features the reference applies right after
         # the transform): the masked-phase transform -- IF := 0 where the log-magnitude is below
         # a threshold (extract_code.py:178-181, train_vqvae.py:586-589) -- and then a per-channel
@@ -155,7 +161,8 @@ class SpectrogramsHelper(nn.Module):
         p.safelog_eps = self.safelog_eps
         p.window, p.twiddle = self.window.data_ptr(), self.twiddle.data_ptr()
         p.mel_start = p.mel_count = p.mel_weight = None
-        p.channels_last = 1 if self.channels_last else 0
+        p.channels_last = (_lib.SPEC_SPACE_TO_DEPTH if self.space_to_depth else
+                           _lib.SPEC_CHANNELS_LAST if self.channels_last else _lib.SPEC_PLANAR)
         p.mask_phase = 0 if self.masked_phase_threshold is None else 1
         p.mask_threshold = 0.0 if self.masked_phase_threshold is None else float(self.masked_phase_threshold)
         affine = self.output_affine or ((1.0, 0.0), (1.0, 0.0))
@@ -184,9 +191,15 @@ class SpectrogramsHelper(nn.Module):
         frames = self.num_frames(n_samples)
         if self.hop_length * (frames - 1) + self.n_fft - n_samples - self.pad_left < 0:
             raise ValueError("n_frames too small for the audio length")
-        out = torch.empty(n_notes, 2, self.n_freq, frames, dtype=torch.float32, device=a.device,
-                          memory_format=(torch.channels_last if self.channels_last
-                                         else torch.contiguous_format))
+        if self.space_to_depth:
+            if frames % 2 or self.n_freq % 2:
+                raise ValueError("space_to_depth needs an even number of frames and bins")
+            out = torch.empty(n_notes, self.n_freq // 2, frames // 2, 8, dtype=torch.float32,
+                              device=a.device).permute(0, 3, 1, 2)
+        else:
+            out = torch.empty(n_notes, 2, self.n_freq, frames, dtype=torch.float32, device=a.device,
+                              memory_format=(torch.channels_last if self.channels_last
+                                             else torch.contiguous_format))
         params = self._params(frames)
         if a.dtype == torch.int16:     # 16-bit PCM: converted by the kernel, half the upload
             params.audio_format, params.pcm_scale = _lib.AUDIO_PCM16, self.pcm_scale
@@ -195,6 +208,20 @@ class SpectrogramsHelper(nn.Module):
         return out
 
     forward = to_spectrogram
+
+    @staticmethod
+    def from_space_to_depth(blocks: torch.Tensor) -> torch.Tensor:
+        """``[B, 8, F/2, T/2]`` (channel = (f&1)*4 + (t&1)*2 + c) -> ``[B, 2, F, T]``."""
+        b, c8, f2, t2 = blocks.shape
+        x = blocks.reshape(b, 2, 2, c8 // 4, f2, t2)            # [B, pf, pt, c, F/2, T/2]
+        return x.permute(0, 3, 4, 1, 5, 2).reshape(b, c8 // 4, 2 * f2, 2 * t2)
+
+    @staticmethod
+    def to_space_to_depth(spec: torch.Tensor) -> torch.Tensor:
+        """``[B, C, F, T]`` -> ``[B, 4C, F/2, T/2]`` with channel = (f&1)*2C + (t&1)*C + c."""
+        b, c, f, t = spec.shape
+        x = spec.reshape(b, c, f // 2, 2, t // 2, 2)            # [B, c, F/2, pf, T/2, pt]
+        return x.permute(0, 3, 5, 1, 2, 4).reshape(b, 4 * c, f // 2, t // 2)
 
     # ------------------------------------------------------------------
     # Inverse and file helpers: plain torch (SURVEY.md 8f N4 -- callers of the hot path:

@@ -50,13 +50,15 @@ def _conv_add_relu(conv: nn.Conv2d, x: torch.Tensor, skip: torch.Tensor) -> torc
                                             conv.padding, conv.dilation, conv.groups)
 
 
-def _run_blocks(blocks: nn.Sequential, x: torch.Tensor) -> torch.Tensor:
+def _run_blocks(blocks: Sequence[nn.Module], x: torch.Tensor) -> torch.Tensor:
     """``blocks(x)``; with fusion, a conv absorbs the ReLU that follows it (explicit, or the
     one a ResBlock starts with), and a ResBlock absorbs the ReLU that follows IT (the next
     ResBlock's, or the stack's trailing one) -- so a ResBlock always sees a rectified input,
     which is also the value its skip connection reads (see ResBlock)."""
     if not _can_fuse(x):
-        return blocks(x)
+        for m in blocks:
+            x = m(x)
+        return x
     mods, i, rectified = list(blocks), 0, False
     while i < len(mods):
         m = mods[i]
@@ -107,9 +109,45 @@ class Encoder(nn.Module):
         blocks += [ResBlock(channel, n_res_channel) for _ in range(n_res_block)]
         blocks.append(nn.ReLU())
         self.blocks = nn.Sequential(*blocks)
+        self._s2d_cache = None
 
-    def forward(self, x):
-        return _run_blocks(self.blocks, x)
+    # (offset index d+1 in the 3x3 kernel, parity inside the 2x2 block, tap of the 4x4 kernel):
+    # input row 2f'-1+k of the stride-2 conv is row parity p of block f'+d
+    _S2D_TAPS = ((0, 1, 0), (1, 0, 1), (1, 1, 2), (2, 0, 3))
+
+    def space_to_depth_weight(self) -> torch.Tensor:
+        """The first convolution (4x4, stride 2, padding 1) as the equivalent 3x3 stride-1
+        padding-1 kernel over the 2x2 space-to-depth input, ``[C_out, 4 C_in, 3, 3]`` with input
+        channel = (f&1)*2C_in + (t&1)*C_in + c -- the layout the front-end kernel can write
+        directly (``SpectrogramsHelper(space_to_depth=True)``).  Same products, regrouped."""
+        conv = self.blocks[0]
+        if not (isinstance(conv, nn.Conv2d) and conv.kernel_size == (4, 4) and conv.stride == (2, 2)
+                and conv.padding == (1, 1) and conv.dilation == (1, 1) and conv.groups == 1):
+            raise ValueError("space_to_depth needs a 4x4 / stride 2 / padding 1 first convolution")
+        w = conv.weight
+        key = (w._version, w.device, w.data_ptr())
+        if not torch.is_grad_enabled() and self._s2d_cache is not None and self._s2d_cache[0] == key:
+            return self._s2d_cache[1]
+        c_out, c_in = w.shape[:2]
+        wp = w.new_zeros(c_out, 2, 2, c_in, 3, 3)
+        for df, pf, kf in self._S2D_TAPS:
+            for dt, pt, kt in self._S2D_TAPS:
+                wp[:, pf, pt, :, df, dt] = w[:, :, kf, kt]
+        wp = wp.reshape(c_out, 4 * c_in, 3, 3).contiguous(memory_format=torch.channels_last)
+        if not torch.is_grad_enabled():
+            self._s2d_cache = (key, wp)
+        return wp
+
+    def forward(self, x, space_to_depth: bool = False):
+        if not space_to_depth:
+            return _run_blocks(self.blocks, x)
+        w, conv, rest = self.space_to_depth_weight(), self.blocks[0], list(self.blocks)[1:]
+        if _can_fuse(x) and rest and isinstance(rest[0], (nn.ReLU, ResBlock)):
+            x = torch.cudnn_convolution_relu(x, w, conv.bias, (1, 1), (1, 1), (1, 1), 1)
+            rest = rest[1:] if isinstance(rest[0], nn.ReLU) else rest
+        else:
+            x = torch.nn.functional.conv2d(x, w, conv.bias, 1, 1)
+        return _run_blocks(rest, x)
 
 
 class Decoder(nn.Module):
@@ -193,8 +231,10 @@ class VQVAE(nn.Module):
                            use_local_kernels)
 
     # -- vqvae.py:251-278 --
-    def encode(self, input: torch.Tensor):
-        enc_b = self.enc_b(input)
+    def encode(self, input: torch.Tensor, space_to_depth: bool = False):
+        """``space_to_depth``: ``input`` is the 2x2-blocked spectrogram ``[B, 4C, F/2, T/2]`` that
+        ``SpectrogramsHelper(space_to_depth=True)`` writes; same result, faster first conv."""
+        enc_b = self.enc_b(input, space_to_depth=space_to_depth)
         enc_t = self.enc_t(enc_b)
 
         quant_t, diff_t, id_t, perplexity_t = self.quantize_t(
@@ -211,14 +251,14 @@ class VQVAE(nn.Module):
         return (quant_t, quant_b, diff_t.unsqueeze(0) + diff_b.unsqueeze(0), id_t, id_b,
                 perplexity_t, perplexity_b)
 
-    def encode_codes(self, input: torch.Tensor):
+    def encode_codes(self, input: torch.Tensor, space_to_depth: bool = False):
         """Top and bottom code maps only -- what ``extract_code.py`` stores.  Same codes as
         ``encode``; the bottom quantiser only searches (its lookup, commitment term and
         perplexity feed nothing here)."""
         if self.training or not hasattr(self.quantize_b, "assign"):
-            out = self.encode(input)
+            out = self.encode(input, space_to_depth=space_to_depth)
             return out[3], out[4]
-        enc_b = self.enc_b(input)
+        enc_b = self.enc_b(input, space_to_depth=space_to_depth)
         enc_t = self.enc_t(enc_b)
         quant_t, _, id_t, _ = self.quantize_t(self.quantize_conv_t(enc_t).permute(0, 2, 3, 1))
         dec_t = self.dec_t(quant_t.permute(0, 3, 1, 2))

@@ -80,3 +80,29 @@ def test_graphed_decode_code_equals_eager():
         graphed(top[:1], bottom[:1])
     with pytest.raises(RuntimeError):
         vq.GraphedDecodeCode(model.train(), top, bottom)
+
+
+def test_space_to_depth_extraction_gives_the_same_codes(fp32_convs):
+    """Front end writing 2x2 blocks + first conv as 3x3 stride 1 == the plain path."""
+    from interactive_spectrogram_inpainting_b200 import extract
+    from interactive_spectrogram_inpainting_b200.utils.spectrograms_helper import MelSpectrogramsHelper
+    torch.manual_seed(8)
+    model = vq.VQVAE(in_channel=2, resolution_factors={"bottom": 16, "top": 2}).to(DEV).eval()
+    model = model.to(memory_format=torch.channels_last)
+    audio = synthetic.synthetic_notes(6)
+    names = [f"n{i}" for i in range(6)]
+    rows = {}
+    for s2d in (False, True):
+        helper = MelSpectrogramsHelper(channels_last=True, space_to_depth=s2d).to(DEV)
+        loader = extract.SpectrogramBatches([(audio[:4].pin_memory(), names[:4]), (audio[4:].pin_memory(), names[4:])],
+                                            helper, torch.device(DEV))
+        rows[s2d] = extract.extract_codes(loader, model)
+    assert [r.filename for r in rows[True]] == names
+    same_t = sum((a.top == b.top).mean() for a, b in zip(rows[False], rows[True])) / 6
+    same_b = sum((a.bottom == b.bottom).mean() for a, b in zip(rows[False], rows[True])) / 6
+    assert same_t > 0.995 and same_b > 0.995
+    with torch.no_grad():
+        spec = MelSpectrogramsHelper(channels_last=True).to(DEV).to_spectrogram(audio.to(DEV))
+        blocks = MelSpectrogramsHelper(space_to_depth=True).to(DEV).to_spectrogram(audio.to(DEV))
+        torch.testing.assert_close(model.enc_b(blocks, space_to_depth=True), model.enc_b(spec),
+                                   rtol=1e-4, atol=1e-5)

@@ -132,3 +132,21 @@ def test_pcm16_input_equals_float_input(n_fft, hop, samples):
     # and the float result is the oracle's
     cfg = fo.FrontEndConfig(n_fft=n_fft, hop_length=hop, window_length=n_fft)
     check_against_oracle(want.cpu(), as_float.cpu(), cfg)
+
+
+@pytest.mark.parametrize("samples", [64000, 9001])
+def test_space_to_depth_output_is_the_same_spectrogram(samples):
+    """layout 2: 2x2 blocks of the spectrogram as 8 channels, written directly by the kernel
+    (whole notes, frame segments, the ragged last batch and the fused epilogue included)."""
+    audio = synthetic.synthetic_notes(3, n_samples=samples).to(DEV)
+    kw = dict(masked_phase_threshold=-10.0, output_affine=((0.1, 0.5), (2.0, -0.25)))
+    for extra in ({}, kw):
+        frames = MelSpectrogramsHelper().num_frames(samples)
+        n_frames = frames + (frames % 2)                       # the layout needs an even count
+        plain = MelSpectrogramsHelper(n_frames=n_frames, **extra).to(DEV).to_spectrogram(audio)
+        blocks = MelSpectrogramsHelper(n_frames=n_frames, space_to_depth=True, **extra).to(DEV).to_spectrogram(audio)
+        assert blocks.shape == (3, 8, 512, n_frames // 2)
+        assert blocks.permute(0, 2, 3, 1).is_contiguous()
+        assert torch.equal(MelSpectrogramsHelper.from_space_to_depth(blocks), plain)
+    with pytest.raises(ValueError):
+        MelSpectrogramsHelper(n_frames=127, space_to_depth=True).to(DEV).to_spectrogram(audio)

@@ -61,3 +61,35 @@ def test_fused_stack_walker_is_the_same_function(monkeypatch):
     x = torch.randn(1, 4, 8, 8)
     with torch.no_grad():
         torch.testing.assert_close(mod._run_blocks(stack, x), stack(x), rtol=1e-6, atol=1e-6)
+
+
+def test_space_to_depth_first_conv_is_the_same_convolution():
+    """The 4x4 / stride-2 first convolution regrouped as 3x3 / stride 1 over 2x2 input blocks
+    (the layout the front-end kernel can write directly) gives the same encoder output, codes
+    and gradients."""
+    from interactive_spectrogram_inpainting_b200.utils.spectrograms_helper import SpectrogramsHelper
+    from interactive_spectrogram_inpainting_b200.vqvae import vqvae as mod
+    torch.manual_seed(4)
+    for factor in (16, 8, 4, 2):
+        enc = mod.Encoder(2, 32, 1, 8, factor).eval()
+        x = torch.randn(2, 2, 64, 32)
+        blocks = SpectrogramsHelper.to_space_to_depth(x)
+        assert torch.equal(SpectrogramsHelper.from_space_to_depth(blocks), x)
+        with torch.no_grad():
+            torch.testing.assert_close(enc(blocks, space_to_depth=True), enc(x), rtol=1e-5, atol=1e-6)
+    enc = mod.Encoder(2, 16, 0, 4, 4)
+    x = torch.randn(1, 2, 16, 8)
+    enc(x).square().sum().backward()
+    want = enc.blocks[0].weight.grad.clone()
+    enc.zero_grad()
+    enc(SpectrogramsHelper.to_space_to_depth(x), space_to_depth=True).square().sum().backward()
+    torch.testing.assert_close(enc.blocks[0].weight.grad, want, rtol=1e-4, atol=1e-5)
+    model = VQVAE(in_channel=2, resolution_factors={'bottom': 16, 'top': 2},
+                  bottleneck_cls=OracleBottleneck).eval()
+    x = torch.randn(1, 2, 256, 32)
+    with torch.no_grad():
+        a = model.encode(x)
+        b = model.encode(SpectrogramsHelper.to_space_to_depth(x), space_to_depth=True)
+    assert torch.equal(a[3], b[3]) and torch.equal(a[4], b[4])
+    with pytest.raises(ValueError):
+        mod.Encoder(2, 16, 0, 4, 4, use_local_kernels=True)(x, space_to_depth=True)
