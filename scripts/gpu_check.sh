@@ -46,6 +46,14 @@ for s in $steps; do
       timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 20 --warmup 3 2>&1 | tail -2 > gpurun_out/bench_multi${n}_$tag.json
       cut -c1-300 gpurun_out/bench_multi${n}_$tag.json
       timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus $n --steps 3 --warmup 1 2>&1 | tail -1 | cut -c1-200 ;;
+    train)
+      n=${NGPUS:-1}
+      if [ "$n" = 1 ]; then
+        timeout 600 python tools/bench_train.py 2>&1 | tail -1 > gpurun_out/train${n}_$tag.json
+      else
+        timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29533 tools/bench_train.py 2>&1 | tail -1 > gpurun_out/train${n}_$tag.json
+      fi
+      cut -c1-900 gpurun_out/train${n}_$tag.json ;;
     multi_test)
       timeout 600 python -m pytest tests/test_gpu_multi.py -q 2>&1 | tail -5 ;;
     extra)
