@@ -9,13 +9,15 @@
 // a segment recomputes with one look-back transform) and walks it in batches of FB frames.
 // Per batch the audio span (FB-1)*hop + n_fft is brought into shared memory by ONE bulk
 // async copy (cp.async.bulk, the 1-D TMA path, completion on an mbarrier) issued a whole
-// batch ahead, so HBM latency hides behind the previous batch's transform.  Twiddles and
-// the window sit in shared memory, the mel band of each output row in registers; the
-// complex spectrum, magnitudes and phase steps never leave shared memory / registers.
-// HBM traffic is the audio once (frame overlap is served from shared memory) and the final
-// [2, F, T'] tensor, FB consecutive time steps per row at a time.  The whole working set is one
-// FB-frame buffer (65 KB with tables and stage at n_fft 2048), so three CTAs share an SM and
-// fill each other's barrier and latency stalls.
+// batch ahead, so HBM latency hides behind the previous batch's transform.  The audio is FP32
+// or 16-bit PCM (converted in pass 1).  Twiddles and the window sit in shared memory; the mel
+// band constants of a thread's rows are re-read from L1 each batch (kept in registers across
+// the transform they spill); the complex spectrum, magnitudes and phase steps never leave
+// shared memory / registers.  HBM traffic is the audio once (frame overlap is served from
+// shared memory) and the final tensor, FB consecutive time steps per row at a time, in one of
+// three layouts (planes, channels-last, 2x2 space-to-depth blocks).  The whole working set is
+// one FB-frame buffer (65 KB with tables and stage at n_fft 2048), so three CTAs share an SM
+// and fill each other's barrier and latency stalls.
 #include "common.cuh"
 #include "melif_core.cuh"
 
