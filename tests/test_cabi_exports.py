@@ -60,3 +60,27 @@ def test_rows_layout_detection():
     assert (lay.rows_per_batch, lay.row_stride, lay.col_stride) == (105, 64, 1)
     # strides that are not 'batches of uniformly strided rows' are reported as such (-> copy)
     assert _lib.rows_layout(torch.zeros(4, 6, 9, 5, 64)[:, ::2, ::3, ::2]) is None
+
+
+def test_header_is_plain_c_and_ctypes_mirrors_its_structs(tmp_path):
+    """include/isi_b200.h compiles as C99 (it is what a non-Python host binds), and the ctypes
+    structures have the sizes and field offsets the C compiler gives the header's."""
+    import subprocess
+    src = tmp_path / "probe.c"
+    fields = [name for name, _ in _lib.MelifParams._fields_]
+    prints = "\n".join(f'  printf("{f} %zu\\n", offsetof(isi_melif_params, {f}));' for f in fields)
+    src.write_text(
+        '#include <stddef.h>\n#include <stdio.h>\n#include "isi_b200.h"\n'
+        "int main(void) {\n"
+        '  printf("melif %zu\\n", sizeof(isi_melif_params));\n'
+        '  printf("rows %zu\\n", sizeof(isi_rows_layout));\n'
+        f"{prints}\n  return 0;\n}}\n")
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", f"-I{ROOT / 'include'}",
+                    str(src), "-o", str(exe)], check=True)
+    out = dict(line.split() for line in subprocess.run([str(exe)], check=True, capture_output=True,
+                                                       text=True).stdout.splitlines())
+    assert int(out["melif"]) == ctypes.sizeof(_lib.MelifParams)
+    assert int(out["rows"]) == ctypes.sizeof(_lib.RowsLayout)
+    for f in fields:
+        assert int(out[f]) == getattr(_lib.MelifParams, f).offset, f
