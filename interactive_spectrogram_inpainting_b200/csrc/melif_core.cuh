@@ -217,8 +217,16 @@ ISI_HD void fft_pass1(int j, const S* frame /* stage + fb*hop */, bool pair_alig
     }
   }
   dft_small<P::R1>(v);
+  // W_M^(j p): the twiddles are fetched four at a time so that their shared-memory latency
+  // overlaps instead of serialising load -> multiply -> load
 #pragma unroll
-  for (int p = 1; p < P::R1; ++p) v[p] = cmul(v[p], tws[64 * p + j]);          // W_M^(j p)
+  for (int p0 = 1; p0 < P::R1; p0 += 4) {
+    cpx t[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) if (p0 + i < P::R1) t[i] = tws[64 * (p0 + i) + j];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) if (p0 + i < P::R1) v[p0 + i] = cmul(v[p0 + i], t[i]);
+  }
 #pragma unroll
   for (int p = 0; p < P::R1; ++p) zA[j + P::kBlockPitch * p] = v[p];
 }
@@ -235,7 +243,13 @@ ISI_HD void fft_pass2(int t, const cpx* tws, cpx* zA) {
     dft16(v);
     if (j != 0) {
 #pragma unroll
-      for (int p = 1; p < 16; ++p) v[p] = cmul(v[p], tws[j * p]);               // W_64^(j p)
+      for (int p0 = 1; p0 < 16; p0 += 4) {                                        // W_64^(j p)
+        cpx t[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) if (p0 + i < 16) t[i] = tws[j * (p0 + i)];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) if (p0 + i < 16) v[p0 + i] = cmul(v[p0 + i], t[i]);
+      }
     }
 #pragma unroll
     for (int p = 0; p < 16; ++p) blk[j + 4 * p] = v[p];
