@@ -200,6 +200,8 @@ class SpectrogramsHelper(nn.Module):
             out = torch.empty(n_notes, 2, self.n_freq, frames, dtype=torch.float32, device=a.device,
                               memory_format=(torch.channels_last if self.channels_last
                                              else torch.contiguous_format))
+        if n_notes == 0:
+            return out
         params = self._params(frames)
         if a.dtype == torch.int16:     # 16-bit PCM: converted by the kernel, half the upload
             params.audio_format, params.pcm_scale = _lib.AUDIO_PCM16, self.pcm_scale

@@ -150,3 +150,27 @@ def test_space_to_depth_output_is_the_same_spectrogram(samples):
         assert torch.equal(MelSpectrogramsHelper.from_space_to_depth(blocks), plain)
     with pytest.raises(ValueError):
         MelSpectrogramsHelper(n_frames=127, space_to_depth=True).to(DEV).to_spectrogram(audio)
+
+
+@pytest.mark.parametrize("n_fft,hop,samples", [(512, 125, 3001), (1024, 250, 5000), (2048, 500, 40000)])
+def test_odd_and_unaligned_hops_take_the_scalar_paths(n_fft, hop, samples):
+    """Hops that are odd or not a multiple of the 16-byte bulk-copy granule: per-thread staging
+    and scalar sample loads, for FP32 and for PCM input."""
+    audio = synthetic.synthetic_notes(2, n_samples=samples)
+    helper = MelSpectrogramsHelper(n_fft=n_fft, hop_length=hop, window_length=n_fft).to(DEV)
+    cfg = fo.FrontEndConfig(n_fft=n_fft, hop_length=hop, window_length=n_fft)
+    spec = helper.to_spectrogram(audio.to(DEV))
+    check_against_oracle(spec.cpu(), audio, cfg)
+    pcm = (audio * 32767.0).round().to(torch.int16)
+    assert torch.equal(helper.to_spectrogram(pcm.to(DEV)),
+                       helper.to_spectrogram(pcm.to(DEV).float() * helper.pcm_scale))
+
+
+def test_empty_batch_and_very_short_audio():
+    helper = MelSpectrogramsHelper().to(DEV)
+    empty = helper.to_spectrogram(torch.zeros(0, 64000, device=DEV))
+    assert empty.shape == (0, 2, 1024, 128)
+    short = synthetic.synthetic_notes(2, n_samples=300)
+    spec = helper.to_spectrogram(short.to(DEV))
+    assert spec.shape[:3] == (2, 2, 1024) and torch.isfinite(spec).all()
+    check_against_oracle(spec.cpu(), short, fo.FrontEndConfig())

@@ -152,3 +152,11 @@ def test_emulated_mel_mode_with_dropped_nyquist(emu):
     audio = synthetic.synthetic_notes(1, n_samples=16000)
     helper = sh.MelSpectrogramsHelper(drop_bin="nyquist")
     check_against_oracle(_run(emu, helper, audio), audio, fo.FrontEndConfig(drop_bin="nyquist"))
+
+
+@pytest.mark.parametrize("n_fft,hop,samples", [(512, 125, 3001), (1024, 250, 5000), (2048, 500, 40000)])
+def test_emulated_kernel_odd_and_unaligned_hops(emu, n_fft, hop, samples):
+    audio = synthetic.synthetic_notes(1, n_samples=samples)
+    helper = sh.MelSpectrogramsHelper(n_fft=n_fft, hop_length=hop, window_length=n_fft)
+    cfg = fo.FrontEndConfig(n_fft=n_fft, hop_length=hop, window_length=n_fft)
+    check_against_oracle(_run(emu, helper, audio), audio, cfg)
