@@ -426,7 +426,19 @@ def b200_arm(args):
                      "traffic": ((57.426944e6 + 414.775296e6) if args.audio == "pcm16"
                                  else (114.308608e6 + 413.754112e6)) / 444 * B if cl else None,
                      "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
-                     "ms_per_launch": melif_ms, "algorithmic_bytes_per_launch": melif_bytes_per_note * B},
+                     "ms_per_launch": melif_ms, "algorithmic_bytes_per_launch": melif_bytes_per_note * B,
+                     # what actually bounds this kernel: instruction issue.  Warp instructions
+                     # per note from the committed ncu capture of this variant
+                     # (smsp__inst_executed.sum / 444 notes), against 148 SMs x 4 issue slots
+                     # at the SM clock sampled during the timed region
+                     "issue_bound": (lambda per_note, mhz: {
+                         "warp_instructions_per_note": per_note,
+                         "achieved_ginst_per_s": per_note * B / (melif_ms * 1e-3) / 1e9,
+                         "peak_ginst_per_s": 148 * 4 * mhz * 1e6 / 1e9,
+                         "frac": per_note * B / (melif_ms * 1e-3) / (148 * 4 * mhz * 1e6),
+                         "source": "profiles/r01_melif_v7_s2d_pcm16_r03a_ncu_summary.csv"})(
+                             272791380 / 444 if args.audio == "pcm16" else 260017056 / 444,
+                             clk["sm_mhz"] or 1965.0)},
         "rooflines_other": [
             {"kernel": f"vq_assign ({args.assign_algo})", "bound": "tensor",
              "achieved": assign_tflops, "peak": tf32_tflops / 3.0, "unit": "TFLOP/s",
