@@ -348,12 +348,13 @@ vq_gather_stats_smem_kernel(const float* __restrict__ x, const int64_t* __restri
         // code for the rest of the launch (silence in a spectrogram, a collapsed codebook): its
         // rows stay out of the owner lists -- one warp would have to add them all -- and every
         // consumer warp sums the ones among its OWN rows in registers instead.  The sample is
-        // the index arrays of all stages filled so far (whichever granules they hold).
-        const int n_sample = (int)min((int64_t)STAGES, total) * kGranuleRows;
+        // this granule and the first fills of the later stages (stage 0 may already be being
+        // refilled, so it is left out).
+        const int n_sample = ((int)min((int64_t)STAGES, total) - 1) * kGranuleRows;
         for (int64_t ahead = g + 1; ahead < min((int64_t)STAGES, total); ++ahead)   // first fills
           umma::mbar_wait(umma::s32(full + (int)ahead), 0u);
         // candidates: the codes of this granule (two per lane); votes: every sampled row
-        const int* low = reinterpret_cast<const int*>(idx);          // low words of the int64 codes
+        const int* low = reinterpret_cast<const int*>(idx + kGranuleRows);   // low words of the int64 codes, stages 1..
         int mine[kGranuleRows / 32], votes[kGranuleRows / 32];
 #pragma unroll
         for (int i = 0; i < kGranuleRows / 32; ++i) {

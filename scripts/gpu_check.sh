@@ -54,6 +54,13 @@ for s in $steps; do
         timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29533 tools/bench_train.py 2>&1 | tail -1 > gpurun_out/train${n}_$tag.json
       fi
       cut -c1-900 gpurun_out/train${n}_$tag.json ;;
+    sanitize)
+      for tool in memcheck racecheck synccheck; do
+        for part in frontend quantizer; do
+          timeout 900 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_smoke.py $part > gpurun_out/sanitize_${tool}_${part}_$tag.log 2>&1
+          echo "$tool $part rc=$? $(grep -c "=========     at\|========= Error\|========= Warning\|hazard" gpurun_out/sanitize_${tool}_${part}_$tag.log) findings; $(grep "ERROR SUMMARY\|RACECHECK SUMMARY" gpurun_out/sanitize_${tool}_${part}_$tag.log | tail -1)"
+        done
+      done ;;
     multi_test)
       timeout 600 python -m pytest tests/test_gpu_multi.py -q 2>&1 | tail -5 ;;
     extra)
