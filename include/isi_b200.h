@@ -221,6 +221,47 @@ ISI_API int isi_melif_forward(const void* audio, int64_t n_notes, int64_t n_samp
                       const isi_melif_params* h_params, float* out,
                       isi_stream_t stream);
 
+/* ------------------------------------------------------------------ *
+ *  (1') inverse front end: (mel) log-magnitude + IF -> audio          *
+ * ------------------------------------------------------------------ */
+
+/*
+ * Parameters of SpectrogramsHelper / MelSpectrogramsHelper.to_audio (external
+ * GANsynth_pytorch; reference call sites flask_server.py:596,1016,1110, sample.py:599,
+ * train_vqvae.py:392-394, utils/losses/spectral.py:122-126).  Same transform geometry as
+ * isi_melif_params; the band tables are the TRANSPOSE of the analysis filterbank with
+ * GANSynth's column normalisation (for every linear row the mel rows that feed it).
+ */
+typedef struct isi_imelif_params {
+  int32_t n_fft;        /* 2048 (512 and 1024 also built)                            */
+  int32_t hop;          /* hop_length, <= n_fft                                      */
+  int32_t pad_left;     /* padded samples the forward transform put before sample 0  */
+  int32_t n_frames;     /* input time steps                                          */
+  int32_t drop_dc;      /* 1: rows are bins 1..n_fft/2, 0: bins 0..n_fft/2-1         */
+  int32_t use_mel;      /* 0: linear log|X| + IF in, 1: mel log-mag^2 + mel IF in    */
+  int32_t band_width;   /* row pitch of band_weight (<= 8)                           */
+  float safelog_eps;    /* mel mode: |X| = sqrt(projected mag^2 + eps)               */
+  const float* window;  /* [n_fft] synthesis window (the analysis window)            */
+  const float* twiddle; /* [n_fft, 2] as isi_melif_params.twiddle                    */
+  const int32_t* band_start; /* [n_fft/2] first mel row feeding each linear row      */
+  const int32_t* band_count; /* [n_fft/2] how many (0..band_width)                   */
+  const float* band_weight;  /* [n_fft/2, band_width], zero beyond the count         */
+  const float* ola_scale;    /* [hop*(n_frames-1)+n_fft]: 1 / (n_fft * sum over the   */
+                             /* frames covering the sample of window^2), 0 where none */
+  float in_scale[2];    /* channel c is read as c * in_scale[c] + in_bias[c] (the     */
+  float in_bias[2];     /* shape of DataNormalizer.denormalize); 1 / 0 = off          */
+  int32_t seg_frames;   /* 0 = choose; else frames per CTA (testing / tuning)         */
+} isi_imelif_params;
+
+/*
+ * spec [n_notes, 2, n_fft/2, n_frames] FP32 planes (channel 0 log-magnitude, channel 1 IF,
+ * time contiguous) -> audio [n_notes, n_samples] FP32, sample j = padded position
+ * j + pad_left of the overlap-added inverse STFT; n_samples <= hop*(n_frames-1) + n_fft
+ * - pad_left (hop*n_frames - pad_left undoes isi_melif_forward's padding).
+ */
+ISI_API int isi_melif_inverse(const float* spec, int64_t n_notes, const isi_imelif_params* h_params,
+                      float* audio, int64_t n_samples, isi_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -42,6 +42,18 @@ class MelifParams(ctypes.Structure):
                 ("audio_format", ctypes.c_int32), ("pcm_scale", ctypes.c_float)]
 
 
+class ImelifParams(ctypes.Structure):
+    _fields_ = [("n_fft", ctypes.c_int32), ("hop", ctypes.c_int32),
+                ("pad_left", ctypes.c_int32), ("n_frames", ctypes.c_int32),
+                ("drop_dc", ctypes.c_int32), ("use_mel", ctypes.c_int32),
+                ("band_width", ctypes.c_int32), ("safelog_eps", ctypes.c_float),
+                ("window", ctypes.c_void_p), ("twiddle", ctypes.c_void_p),
+                ("band_start", ctypes.c_void_p), ("band_count", ctypes.c_void_p),
+                ("band_weight", ctypes.c_void_p), ("ola_scale", ctypes.c_void_p),
+                ("in_scale", ctypes.c_float * 2), ("in_bias", ctypes.c_float * 2),
+                ("seg_frames", ctypes.c_int32)]
+
+
 EXPORTS = {
     # name: (restype, argtypes)
     "isi_version": (ctypes.c_int, []),
@@ -72,6 +84,9 @@ EXPORTS = {
     "isi_melif_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
                                          ctypes.POINTER(MelifParams), ctypes.c_void_p,
                                          ctypes.c_void_p]),
+    "isi_melif_inverse": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64,
+                                         ctypes.POINTER(ImelifParams), ctypes.c_void_p,
+                                         ctypes.c_int64, ctypes.c_void_p]),
 }
 
 
@@ -160,6 +175,7 @@ def rows_layout(t: torch.Tensor) -> Optional[RowsLayout]:
 KERNELS_PER_CALL = {
     "isi_vq_prepare_codebook": 3, "isi_vq_assign": 1, "isi_vq_gather_stats": 1,
     "isi_vq_finish": 1, "isi_vq_ema_update": 2, "isi_embed_code": 1, "isi_melif_forward": 1,
+    "isi_melif_inverse": 1,
 }
 launch_counts = {name: 0 for name in KERNELS_PER_CALL}
 

@@ -27,6 +27,7 @@ int launch_ema_update(float*, float*, float*, float*, int, int, double, double, 
 int launch_embed_code(const int64_t*, int64_t, int, int, const Prepared&, float*,
                       const isi_rows_layout&, int32_t*, cudaStream_t);
 int launch_melif(const void*, int64_t, int64_t, const isi_melif_params&, float*, cudaStream_t);
+int launch_imelif(const float*, int64_t, const isi_imelif_params&, float*, int64_t, int, cudaStream_t);
 }  // namespace isi
 
 using namespace isi;
@@ -162,6 +163,20 @@ ISI_API int isi_melif_forward(const void* audio, int64_t n_notes, int64_t n_samp
   if ((uintptr_t)out % 16 || (uintptr_t)hp->twiddle % 8) return ISI_ERR_ALIGN;
   if (n_notes == 0) return ISI_OK;
   return launch_melif(audio, n_notes, n_samples, *hp, out, (cudaStream_t)stream);
+}
+
+ISI_API int isi_melif_inverse(const float* spec, int64_t n_notes, const isi_imelif_params* hp, float* audio,
+                      int64_t n_samples, isi_stream_t stream) {
+  if (!spec || !hp || !audio || !hp->window || !hp->twiddle || !hp->ola_scale) return ISI_ERR_NULL;
+  if (hp->use_mel && (!hp->band_start || !hp->band_count || !hp->band_weight)) return ISI_ERR_NULL;
+  if (n_notes < 0 || n_samples <= 0 || hp->hop <= 0 || hp->n_frames <= 0 || hp->pad_left < 0 || hp->seg_frames < 0)
+    return ISI_ERR_SHAPE;
+  if (hp->hop > hp->n_fft) return ISI_ERR_UNSUPPORTED;
+  if (hp->use_mel && hp->band_width <= 0) return ISI_ERR_SHAPE;
+  if (n_samples > (int64_t)hp->hop * (hp->n_frames - 1) + hp->n_fft - hp->pad_left) return ISI_ERR_SHAPE;
+  if ((uintptr_t)spec % 4 || (uintptr_t)audio % 4 || (uintptr_t)hp->twiddle % 8) return ISI_ERR_ALIGN;
+  if (n_notes == 0) return ISI_OK;
+  return launch_imelif(spec, n_notes, *hp, audio, n_samples, hp->seg_frames, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -8,8 +8,9 @@ call sites (``utils/misc.py:13-27``; ``fs_hz``/``hop_length``/``safelog_eps`` re
 arithmetic is the published GANSynth recipe; the choices the missing source would
 decide are keyword-only arguments ("front end: unpinned").
 
-``to_spectrogram`` is the hot path (isi_melif_forward).  ``to_audio`` is the plain
-torch inverse (not yet a kernel).
+``to_spectrogram`` is the hot path (isi_melif_forward).  ``to_audio`` is its mirror
+(isi_melif_inverse); ``to_audio_differentiable`` is the same arithmetic in
+plain torch for callers that need gradients (utils/losses/spectral.py:122-126).
 """
 import math
 from typing import Optional
@@ -86,6 +87,32 @@ def dense_mel_matrix(starts, counts, weights) -> np.ndarray:
     return m
 
 
+def inverse_band_table(starts, counts, weights):
+    """Banded form of GANSynth's mel->linear matrix (the transpose of the filterbank, every
+    linear column divided by the column sum of ``M M^T``; columns whose sum is ~0 keep that
+    sum): for every linear row the first mel row that feeds it, how many, FP64 weights."""
+    m = dense_mel_matrix(starts, counts, weights)                  # [linear, mel]
+    sums = (m @ m.T).sum(0)
+    scale = np.where(np.abs(sums) > 1e-8, 1.0 / np.where(sums == 0.0, 1.0, sums), sums)
+    back = m * scale[:, None]                                      # [linear, mel]: row l feeds from mel bins
+    n = len(starts)
+    inv_start = np.zeros(n, dtype=np.int32)
+    inv_count = np.zeros(n, dtype=np.int32)
+    bands = []
+    for l in range(n):
+        nz = np.flatnonzero(back[l])
+        if len(nz):
+            inv_start[l], inv_count[l] = nz[0], nz[-1] - nz[0] + 1
+            bands.append(back[l, nz[0]:nz[-1] + 1])
+        else:
+            bands.append(np.zeros(0))
+    width = max(1, int(inv_count.max()))
+    inv_weight = np.zeros((n, width), dtype=np.float64)
+    for l, b in enumerate(bands):
+        inv_weight[l, :len(b)] = b
+    return inv_start, inv_count, inv_weight
+
+
 class SpectrogramsHelper(nn.Module):
     """Linear-frequency log-magnitude + instantaneous-frequency spectrograms."""
 
@@ -133,6 +160,10 @@ class SpectrogramsHelper(nn.Module):
         # uses (pytorch_nsynth, not in its tree) does this conversion on the CPU; its exact
         # constant is not pinned here, so it is an attribute.
         self.pcm_scale = 1.0 / 32768.0
+        # to_audio: per-channel affine applied to the spectrogram first (None = off), and the
+        # frames one CTA synthesises (None = chosen from the batch size)
+        self.input_affine = None
+        self.inverse_seg_frames = None
 
         w = torch.hann_window(window_length, periodic=window_periodic, dtype=torch.float64)
         if window_length < n_fft:
@@ -226,12 +257,72 @@ class SpectrogramsHelper(nn.Module):
         return x.permute(0, 3, 5, 1, 2, 4).reshape(b, 4 * c, f // 2, t // 2)
 
     # ------------------------------------------------------------------
-    # Inverse and file helpers: plain torch (SURVEY.md 8f N4 -- callers of the hot path:
-    # flask_server.py:596,648,1016, sample.py:526,599, train_vqvae.py:392-394).
+    # Inverse (SURVEY.md 8f N4 -- callers of the hot path: flask_server.py:596,1016,1110,
+    # sample.py:599, train_vqvae.py:392-394, utils/losses/spectral.py:122-126).
     # ------------------------------------------------------------------
+    def _ola_scale(self, frames: int, device) -> torch.Tensor:
+        """``1 / (n_fft * sum of squared windows of the frames covering a sample)`` for every
+        padded position of a ``frames``-frame inverse STFT (FP64 on the host, cached)."""
+        key = (frames, str(device))
+        cache = self.__dict__.setdefault("_ola_cache", {})
+        if key not in cache:
+            w2 = self.window.double().cpu() ** 2
+            total = self.hop_length * (frames - 1) + self.n_fft
+            norm = torch.zeros(total, dtype=torch.float64)
+            for t in range(frames):
+                norm[t * self.hop_length:t * self.hop_length + self.n_fft] += w2
+            cache[key] = (1.0 / (self.n_fft * norm.clamp_min(1e-8))).float().to(device)
+        return cache[key]
+
+    def _inverse_params(self, frames: int, device) -> "_lib.ImelifParams":
+        p = _lib.ImelifParams()
+        p.n_fft, p.hop, p.pad_left, p.n_frames = self.n_fft, self.hop_length, self.pad_left, frames
+        p.drop_dc = 1 if self.drop_bin == "dc" else 0
+        p.use_mel, p.band_width = 0, 0
+        p.safelog_eps = self.safelog_eps
+        p.window, p.twiddle = self.window.data_ptr(), self.twiddle.data_ptr()
+        p.band_start = p.band_count = p.band_weight = None
+        p.ola_scale = self._ola_scale(frames, device).data_ptr()
+        affine = self.input_affine or ((1.0, 0.0), (1.0, 0.0))
+        for c in range(2):
+            p.in_scale[c], p.in_bias[c] = float(affine[c][0]), float(affine[c][1])
+        p.seg_frames = int(self.inverse_seg_frames or 0)
+        return p
+
+    def to_audio(self, spec: torch.Tensor) -> torch.Tensor:
+        """``[B, 2, n_fft/2, frames]`` (the layout ``to_spectrogram`` returns) -> ``[B, hop *
+        frames - pad_left]`` FP32 on the same GPU: mel -> linear, IF -> phase by a running sum,
+        inverse STFT with the analysis window, the forward padding removed.  ``self.input_affine``
+        ``((s0, b0), (s1, b1))`` is applied to the channels first (DataNormalizer.denormalize's
+        shape).  No gradient: see ``to_audio_differentiable``."""
+        _lib.require_cuda(spec, "spec")
+        if spec.dim() == 3:
+            spec = spec[None]
+        if spec.dim() != 4 or spec.shape[1] != 2 or spec.shape[2] != self.n_freq:
+            raise ValueError(f"spec must be [batch, 2, {self.n_freq}, frames], got {tuple(spec.shape)}")
+        if self.window.device != spec.device:
+            raise RuntimeError("helper and spectrogram live on different devices; call .to(device)")
+        if spec.requires_grad and torch.is_grad_enabled():
+            raise RuntimeError("to_audio does not record gradients; use to_audio_differentiable")
+        x = spec.detach()
+        if x.dtype != torch.float32:
+            x = x.float()
+        x = x.contiguous()
+        n_notes, frames = x.shape[0], x.shape[3]
+        n_samples = self.hop_length * frames - self.pad_left
+        if frames == 0 or n_samples <= 0:
+            raise ValueError("spectrogram too short for the helper's padding")
+        out = torch.empty(n_notes, n_samples, dtype=torch.float32, device=x.device)
+        if n_notes == 0:
+            return out
+        params = self._inverse_params(frames, x.device)
+        _lib.invoke("isi_melif_inverse", x.data_ptr(), n_notes, params, out.data_ptr(), n_samples,
+                    _lib.stream_ptr(x.device))
+        return out
+
     def _linear_to_audio(self, spec: torch.Tensor) -> torch.Tensor:
         """``[B, 2, F, T']`` linear log-magnitude + IF -> ``[B, samples]`` (GANSynth
-        ``specgrams_to_stfts`` + inverse STFT, padding removed)."""
+        ``specgrams_to_stfts`` + inverse STFT, padding removed), plain torch."""
         logmag, ifreq = spec[:, 0].float(), spec[:, 1].float()
         mag = torch.exp(logmag)
         phase = torch.cumsum(ifreq * math.pi, dim=-1)
@@ -250,8 +341,16 @@ class SpectrogramsHelper(nn.Module):
         pad_right = self.n_fft - self.hop_length
         return audio[:, self.pad_left:total - pad_right]
 
-    def to_audio(self, spec: torch.Tensor) -> torch.Tensor:
-        return self._linear_to_audio(spec)
+    def _denormalised(self, spec: torch.Tensor) -> torch.Tensor:
+        if self.input_affine is None:
+            return spec
+        return torch.stack([spec[:, c] * self.input_affine[c][0] + self.input_affine[c][1]
+                            for c in range(2)], 1)
+
+    def to_audio_differentiable(self, spec: torch.Tensor) -> torch.Tensor:
+        """``to_audio`` as differentiable torch ops (any device), for the spectral training
+        losses of the reference (utils/losses/spectral.py:122-126)."""
+        return self._linear_to_audio(self._denormalised(spec))
 
     def from_wavfile(self, path, duration_n: Optional[int] = None) -> torch.Tensor:
         """Load a wav file (mono mix, resampled to ``fs_hz``, cropped / zero-padded to
@@ -288,6 +387,12 @@ class MelSpectrogramsHelper(SpectrogramsHelper):
         starts, counts, weights = mel_band_table(
             n_fft, fs_hz, lower_edge_hertz, upper_edge_hertz, mel_break_frequency_hertz,
             mel_bin_width_threshold_factor)
+        inv_start, inv_count, inv_weight = inverse_band_table(starts, counts, weights)
+        if inv_weight.shape[1] < _KERNEL_BAND_PITCH:
+            inv_weight = np.pad(inv_weight, ((0, 0), (0, _KERNEL_BAND_PITCH - inv_weight.shape[1])))
+        self.register_buffer("inv_start", torch.from_numpy(inv_start), persistent=False)
+        self.register_buffer("inv_count", torch.from_numpy(inv_count), persistent=False)
+        self.register_buffer("inv_weight", torch.from_numpy(inv_weight).float().contiguous(), persistent=False)
         self.register_buffer("mel_start", torch.from_numpy(starts), persistent=False)
         self.register_buffer("mel_count", torch.from_numpy(counts), persistent=False)
         if weights.shape[1] < _KERNEL_BAND_PITCH:      # 32-byte rows: two 16-byte loads per band
@@ -295,9 +400,10 @@ class MelSpectrogramsHelper(SpectrogramsHelper):
         self.register_buffer("mel_weight", torch.from_numpy(weights).float().contiguous(),
                              persistent=False)
 
-    def to_audio(self, spec: torch.Tensor) -> torch.Tensor:
+    def to_audio_differentiable(self, spec: torch.Tensor) -> torch.Tensor:
         """GANSynth ``melspecgrams_to_specgrams`` (pseudo-inverse filterbank: transpose
-        normalised by the row sums of M M^T) followed by the linear inverse."""
+        normalised by the column sums of M M^T) followed by the linear inverse, plain torch."""
+        spec = self._denormalised(spec)
         logmelmag2, mel_if = spec[:, 0].float(), spec[:, 1].float()
         m = torch.from_numpy(dense_mel_matrix(self.mel_start.cpu().numpy(), self.mel_count.cpu().numpy(),
                                               self.mel_weight.double().cpu().numpy())).to(spec.device)
@@ -310,6 +416,13 @@ class MelSpectrogramsHelper(SpectrogramsHelper):
         phase = torch.einsum("bmt,ml->blt", mel_phase, mel_to_lin)
         ifreq = torch.cat([phase[..., :1], phase[..., 1:] - phase[..., :-1]], -1) / math.pi
         return self._linear_to_audio(torch.stack([logmag, ifreq], 1))
+
+    def _inverse_params(self, frames: int, device) -> "_lib.ImelifParams":
+        p = super()._inverse_params(frames, device)
+        p.use_mel, p.band_width = 1, self.inv_weight.shape[1]
+        p.band_start, p.band_count = self.inv_start.data_ptr(), self.inv_count.data_ptr()
+        p.band_weight = self.inv_weight.data_ptr()
+        return p
 
     def _params(self, n_frames: int) -> "_lib.MelifParams":
         p = super()._params(n_frames)

@@ -199,6 +199,66 @@ def epilogue(spec: torch.Tensor, masked_phase_threshold: Optional[float] = None,
     return out
 
 
+def mel_to_linear_matrix(cfg: FrontEndConfig) -> np.ndarray:
+    """float64 ``[n mel, n linear]`` approximate inverse of the filterbank (magenta
+    ``specgrams_helper._mel_to_linear_matrix``): the transpose, each linear column divided
+    by the column sum of ``M M^T`` (columns whose sum is ~0 keep that sum)."""
+    m = linear_to_mel_matrix(cfg)
+    sums = np.sum(np.matmul(m, m.T), axis=0)
+    d = np.where(np.abs(sums) > 1.0e-8, 1.0 / np.where(sums == 0.0, 1.0, sums), sums)
+    return np.matmul(m.T, np.diag(d))
+
+
+def mel_to_linear(spec: torch.Tensor, cfg: FrontEndConfig) -> torch.Tensor:
+    """magenta ``melspecgrams_to_specgrams``: ``[B, 2, n_freq, frames]`` mel log-mag^2 + mel IF
+    -> linear log-magnitude + IF."""
+    logmelmag2, mel_if = spec[:, 0], spec[:, 1]
+    back = torch.from_numpy(mel_to_linear_matrix(cfg)).to(spec.dtype)     # [mel, lin]
+    mag2 = torch.matmul(back.t(), torch.exp(logmelmag2))
+    logmag = 0.5 * torch.log(mag2 + cfg.safelog_eps)
+    mel_phase = torch.cumsum(mel_if * math.pi, dim=-1)
+    phase = torch.matmul(back.t(), mel_phase)
+    return torch.stack([logmag, instantaneous_frequency(phase)], dim=1)
+
+
+def linear_to_stft(spec: torch.Tensor, cfg: FrontEndConfig) -> torch.Tensor:
+    """magenta ``specgrams_to_stfts``: complex ``[B, n_fft/2 + 1, frames]``, the bin the
+    forward transform dropped re-inserted as zero."""
+    mag = torch.exp(spec[:, 0])
+    phase = torch.cumsum(spec[:, 1] * math.pi, dim=-1)
+    s = torch.polar(mag, phase)
+    zero = torch.zeros_like(s[:, :1])
+    return torch.cat([zero, s], dim=1) if cfg.drop_bin == "dc" else torch.cat([s, zero], dim=1)
+
+
+def to_audio(spec: torch.Tensor, cfg: FrontEndConfig = FrontEndConfig(),
+             input_affine=None) -> torch.Tensor:
+    """``[B, 2, n_freq, frames]`` -> ``[B, hop * frames - pad_left]`` in ``spec.dtype``.
+
+    Inverse of ``to_spectrogram`` (magenta ``melspecgrams_to_waves`` / ``specgrams_to_waves``):
+    mel -> linear, IF -> phase by a running sum, inverse real FFT of every frame, synthesis
+    window = analysis window, overlap-add divided by the summed squared windows of the frames
+    that cover a sample, then the forward transform's padding removed (``n_fft - hop`` on the
+    right).  ``input_affine`` ``((s0, b0), (s1, b1))`` is applied to the channels first (the
+    shape of DataNormalizer.denormalize).  PARITY UNPINNED like the forward transform."""
+    if input_affine is not None:
+        spec = torch.stack([spec[:, c] * input_affine[c][0] + input_affine[c][1] for c in range(2)], dim=1)
+    lin = mel_to_linear(spec, cfg) if cfg.use_mel_scale else spec
+    s = linear_to_stft(lin, cfg)
+    frames = s.shape[-1]
+    pad_l = cfg.n_fft - cfg.hop_length if cfg.pad_left is None else cfg.pad_left
+    total = cfg.hop_length * (frames - 1) + cfg.n_fft
+    w = analysis_window(cfg, spec.dtype)
+    cols = torch.fft.irfft(s, n=cfg.n_fft, dim=1) * w[None, :, None]            # [B, n_fft, frames]
+    out = torch.zeros(spec.shape[0], total, dtype=spec.dtype)
+    norm = torch.zeros(total, dtype=spec.dtype)
+    for t in range(frames):
+        out[:, t * cfg.hop_length:t * cfg.hop_length + cfg.n_fft] += cols[:, :, t]
+        norm[t * cfg.hop_length:t * cfg.hop_length + cfg.n_fft] += w * w
+    out = out / norm.clamp_min(1e-8)
+    return out[:, pad_l:max(pad_l, total - (cfg.n_fft - cfg.hop_length))]
+
+
 def stability_mask(audio: torch.Tensor, cfg: FrontEndConfig = FrontEndConfig(),
                    wrap_margin: float = 1e-2, mag_floor: float = 1e-4) -> torch.Tensor:
     """bool ``[B, n_freq, frames]``: True where the IF channel is numerically

@@ -65,6 +65,20 @@ for s in $steps; do
       timeout 600 python -m pytest tests/test_gpu_multi.py -q 2>&1 | tail -5 ;;
     extra)
       timeout 600 python tools/bench_extra.py > gpurun_out/extra_$tag.json 2> gpurun_out/extra_$tag.err; tail -3 gpurun_out/extra_$tag.err; head -c 600 gpurun_out/extra_$tag.json ;;
+    inverse)
+      timeout 900 python -m pytest tests/test_gpu_inverse.py -q -s 2>&1 | tail -40 > gpurun_out/pytest_inverse_$tag.log
+      tail -8 gpurun_out/pytest_inverse_$tag.log ;;
+    inverse_bench)
+      timeout 300 python tools/bench_inverse.py > gpurun_out/inverse_$tag.json 2> gpurun_out/inverse_$tag.err; tail -3 gpurun_out/inverse_$tag.err; head -c 1500 gpurun_out/inverse_$tag.json ;;
+    inverse_sanitize)
+      for tool in memcheck racecheck; do
+        timeout 600 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_smoke.py inverse > gpurun_out/sanitize_${tool}_inverse_$tag.log 2>&1
+        echo "$tool inverse rc=$? $(grep -c "=========     at\|========= Error\|========= Warning\|hazard" gpurun_out/sanitize_${tool}_inverse_$tag.log) findings; $(grep "ERROR SUMMARY\|RACECHECK SUMMARY" gpurun_out/sanitize_${tool}_inverse_$tag.log | tail -1)"
+      done ;;
+    ncu_inverse)
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:imelif_kernel -s 4 -c 1 \
+        -o gpurun_out/imelif_$tag python tools/bench_inverse.py --only 444 > gpurun_out/ncu_imelif_$tag.log 2>&1
+      tail -1 gpurun_out/ncu_imelif_$tag.log | cut -c1-200 ;;
     smoke)
       timeout 300 python __graft_entry__.py smoke 2>&1 | tail -2 ;;
     probe)

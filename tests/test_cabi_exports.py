@@ -68,12 +68,16 @@ def test_header_is_plain_c_and_ctypes_mirrors_its_structs(tmp_path):
     import subprocess
     src = tmp_path / "probe.c"
     fields = [name for name, _ in _lib.MelifParams._fields_]
-    prints = "\n".join(f'  printf("{f} %zu\\n", offsetof(isi_melif_params, {f}));' for f in fields)
+    inv_fields = [name for name, _ in _lib.ImelifParams._fields_]
+    prints = "\n".join(
+        [f'  printf("{f} %zu\\n", offsetof(isi_melif_params, {f}));' for f in fields] +
+        [f'  printf("inv.{f} %zu\\n", offsetof(isi_imelif_params, {f}));' for f in inv_fields])
     src.write_text(
         '#include <stddef.h>\n#include <stdio.h>\n#include "isi_b200.h"\n'
         "int main(void) {\n"
         '  printf("melif %zu\\n", sizeof(isi_melif_params));\n'
         '  printf("rows %zu\\n", sizeof(isi_rows_layout));\n'
+        '  printf("imelif %zu\\n", sizeof(isi_imelif_params));\n'
         f"{prints}\n  return 0;\n}}\n")
     exe = tmp_path / "probe"
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", f"-I{ROOT / 'include'}",
@@ -82,5 +86,8 @@ def test_header_is_plain_c_and_ctypes_mirrors_its_structs(tmp_path):
                                                        text=True).stdout.splitlines())
     assert int(out["melif"]) == ctypes.sizeof(_lib.MelifParams)
     assert int(out["rows"]) == ctypes.sizeof(_lib.RowsLayout)
+    assert int(out["imelif"]) == ctypes.sizeof(_lib.ImelifParams)
     for f in fields:
         assert int(out[f]) == getattr(_lib.MelifParams, f).offset, f
+    for f in inv_fields:
+        assert int(out["inv." + f]) == getattr(_lib.ImelifParams, f).offset, f

@@ -64,16 +64,36 @@ def test_helper_metadata_matches_reference_call_sites():
         sh.SpectrogramsHelper(n_fft=1000)
 
 
-def test_to_audio_inverts_the_linear_front_end_on_cpu():
-    """``to_audio`` is plain torch: check it against the oracle's forward transform."""
+def test_differentiable_to_audio_inverts_the_linear_front_end_on_cpu():
+    """``to_audio_differentiable`` is plain torch (the spectral losses need its gradient): check
+    it against the oracle's forward transform.  ``to_audio`` itself is the CUDA kernel."""
     from interactive_spectrogram_inpainting_b200.utils import synthetic
     from oracle import frontend_oracle as fo
     audio = synthetic.synthetic_notes(2)
     spec = fo.to_spectrogram(audio.double(), fo.FrontEndConfig(use_mel_scale=False)).float()
-    rebuilt = sh.SpectrogramsHelper().to_audio(spec)
+    rebuilt = sh.SpectrogramsHelper().to_audio_differentiable(spec)
     assert rebuilt.shape == audio.shape
     err = (rebuilt - audio)[:, 2048:-2048].abs().max()
     assert err < 2e-3, err          # exp(log(|X| + eps)) keeps the 1e-6 offset; edges excluded
+
+
+def test_to_audio_has_no_cpu_path():
+    with pytest.raises(RuntimeError, match="no CPU"):
+        sh.SpectrogramsHelper().to_audio(torch.zeros(1, 2, 1024, 8))
+
+
+def test_differentiable_to_audio_matches_the_oracle_and_has_a_gradient():
+    from oracle import frontend_oracle as fo
+    g = torch.Generator().manual_seed(5)
+    spec = torch.stack([torch.randn(1, 1024, 12, generator=g) - 3, torch.rand(1, 1024, 12, generator=g) * 2 - 1], 1)
+    for mel in (True, False):
+        helper = (sh.MelSpectrogramsHelper if mel else sh.SpectrogramsHelper)()
+        want = fo.to_audio(spec.double(), fo.FrontEndConfig(use_mel_scale=mel))
+        x = spec.clone().requires_grad_(True)
+        got = helper.to_audio_differentiable(x)
+        assert (got.double() - want).abs().max() <= 1e-5 * want.abs().max()
+        got.pow(2).sum().backward()
+        assert torch.isfinite(x.grad).all() and x.grad.abs().max() > 0
 
 
 def test_mel_to_audio_runs_and_is_close_in_level():
@@ -81,7 +101,7 @@ def test_mel_to_audio_runs_and_is_close_in_level():
     from oracle import frontend_oracle as fo
     audio = synthetic.synthetic_notes(1)
     spec = fo.to_spectrogram(audio, fo.FrontEndConfig())
-    rebuilt = sh.MelSpectrogramsHelper().to_audio(spec)
+    rebuilt = sh.MelSpectrogramsHelper().to_audio_differentiable(spec)
     assert rebuilt.shape == audio.shape and torch.isfinite(rebuilt).all()
     ratio = rebuilt.pow(2).mean().sqrt() / audio.pow(2).mean().sqrt()
     assert 0.3 < ratio < 3.0, ratio   # the mel pseudo-inverse is lossy; level must survive

@@ -27,6 +27,19 @@ if which in ("all", "frontend"):
     torch.cuda.synchronize()
     print("frontend ok")
 
+if which in ("all", "inverse"):
+    g = torch.Generator().manual_seed(0)
+    for helper, frames, seg in ((MelSpectrogramsHelper(), 32, 8), (SpectrogramsHelper(), 12, None),
+                                (MelSpectrogramsHelper(n_fft=512, hop_length=125, window_length=512), 13, 8),
+                                (MelSpectrogramsHelper(n_fft=1024, hop_length=256, window_length=1024), 18, None)):
+        helper = helper.to(dev)
+        helper.inverse_seg_frames = seg
+        spec = torch.stack([torch.randn(2, helper.n_freq, frames, generator=g) - 3,
+                            torch.rand(2, helper.n_freq, frames, generator=g) * 2 - 1], 1).to(dev)
+        helper.to_audio(spec)
+    torch.cuda.synchronize()
+    print("inverse ok")
+
 if which in ("all", "quantizer"):
     embed = synthetic.synthetic_codebook(64, 512)
     for algo, rows, k in (("simt", 700, 512), ("tcgen05", 5000, 512), ("tcgen05_pair", 5000, 512),
