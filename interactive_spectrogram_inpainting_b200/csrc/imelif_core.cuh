@@ -25,6 +25,8 @@ namespace imelif {
 
 using namespace melif;
 
+struct alignas(16) f4 { float x, y, z, w; };   // one LDS.128 / LDG.128
+
 ISI_HD float fast_exp(float x) {            // one MUFU.EX2 + one multiply
 #ifdef __CUDA_ARCH__
   float r;
@@ -78,6 +80,18 @@ ISI_HD void slab_transform_chunk(float* slab, int q, int M, float s0, float b0, 
   }
 }
 
+// FB consecutive floats of a slab chunk (16-byte aligned when FB = 4)
+template <int FB>
+ISI_HD void load_chunk(const float* p, float* v) {
+  if (FB == 4) {
+    const f4 q = *reinterpret_cast<const f4*>(p);
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+  } else {
+#pragma unroll
+    for (int fb = 0; fb < FB; ++fb) v[fb] = p[fb];
+  }
+}
+
 // ---- build: one linear row, all FB frames.  `phase` (half-turns) is the row's running phase
 //      before frame f0 and is advanced.  Mel mode: band = rows start .. start+count of the slab
 //      with weights w (zero beyond count); `count_uniform` >= count is warp-uniform.  Linear
@@ -93,9 +107,11 @@ ISI_HD void build_row(const float* slab, int M, int start, int count, int count_
     for (int i = 0; i < kMaxMelWidth; ++i) {
       if (i < count_uniform) {
         const bool on = i < count;
-        const float* v0 = slab + (start + (on ? i : 0)) * FB;
-        const float* v1 = v0 + M * FB;
+        const float* s0 = slab + (start + (on ? i : 0)) * FB;
         const float wi = on ? w[i] : 0.f;
+        float v0[FB], v1[FB];
+        load_chunk<FB>(s0, v0);
+        load_chunk<FB>(s0 + M * FB, v1);
 #pragma unroll
         for (int fb = 0; fb < FB; ++fb) { a[fb] = fmaf(wi, v0[fb], a[fb]); d[fb] = fmaf(wi, v1[fb], d[fb]); }
       }
@@ -104,7 +120,8 @@ ISI_HD void build_row(const float* slab, int M, int start, int count, int count_
     for (int fb = 0; fb < FB; ++fb) a[fb] = fast_sqrt(fmaxf(a[fb], 0.f) + eps);
   } else {
 #pragma unroll
-    for (int fb = 0; fb < FB; ++fb) { a[fb] = slab[start * FB + fb]; d[fb] = slab[(M + start) * FB + fb]; }
+    load_chunk<FB>(slab + start * FB, a);
+    load_chunk<FB>(slab + (M + start) * FB, d);
   }
 #pragma unroll
   for (int fb = 0; fb < FB; ++fb) {
@@ -117,8 +134,17 @@ ISI_HD void build_row(const float* slab, int M, int start, int count, int count_
 // ---- look-back (a segment that does not start at frame 0): the running phase before frame
 //      `f_end` is the projection of sum_{t < f_end} of channel 1; sums and projection in FP64
 //      (the sum reaches ~100 half-turns, where FP32 resolves 1e-5), folded, then FP32. ----
-ISI_HD double lookback_row_sum(const float* row /* channel-1 row */, int f_end, float s1, float b1) {
+ISI_HD double lookback_row_sum(const float* row /* channel-1 row */, int f_end, float s1, float b1, bool vec) {
   double acc = 0.0;
+  if (vec) {        // row 16-byte aligned, f_end a multiple of 4: independent 16-byte loads
+#pragma unroll 8
+    for (int t = 0; t < f_end; t += 4) {
+      const f4 q = *reinterpret_cast<const f4*>(row + t);
+      acc += (double)fmaf(q.x, s1, b1); acc += (double)fmaf(q.y, s1, b1);
+      acc += (double)fmaf(q.z, s1, b1); acc += (double)fmaf(q.w, s1, b1);
+    }
+    return acc;
+  }
   for (int t = 0; t < f_end; ++t) acc += (double)fmaf(row[t], s1, b1);
   return acc;
 }
@@ -201,11 +227,11 @@ ISI_HD void ola_quad(const cpx* z, int pitch, const float* win, int n_fft, int h
     const int idx = s0 - fb * hop;
     if (fb < nf && idx >= 0 && idx < n_fft) {
       const cpx y0 = z[fb * pitch + (idx >> 1)], y1 = z[fb * pitch + (idx >> 1) + 1];
-      const float* wq = win + idx;
-      acc[0] = fmaf(y0.re, wq[0], acc[0]);
-      acc[1] = fmaf(-y0.im, wq[1], acc[1]);
-      acc[2] = fmaf(y1.re, wq[2], acc[2]);
-      acc[3] = fmaf(-y1.im, wq[3], acc[3]);
+      const f4 wq = *reinterpret_cast<const f4*>(win + idx);
+      acc[0] = fmaf(y0.re, wq.x, acc[0]);
+      acc[1] = fmaf(-y0.im, wq.y, acc[1]);
+      acc[2] = fmaf(y1.re, wq.z, acc[2]);
+      acc[3] = fmaf(-y1.im, wq.w, acc[3]);
     }
   }
 }

@@ -312,27 +312,38 @@ class GraphedDecodeCode:
     The model must be in eval mode with a codebook that no longer changes (the graph holds
     the address of the prepared codebook).  The returned tensor is the graph's output buffer:
     it is overwritten by the next call -- ``clone()`` it to keep it.  Not thread-safe; give
-    each request thread its own instance."""
+    each request thread its own instance.
 
-    def __init__(self, model: VQVAE, code_t: torch.Tensor, code_b: torch.Tensor, warmup: int = 3):
+    With ``to_audio`` (a spectrograms helper on the same device) the graph continues into the
+    inverse front end (``isi_melif_inverse``), i.e. the server's whole codes -> audio request
+    (``flask_server.py:593-596``: ``decode_code`` then ``spectrograms_helper.to_audio``), and a
+    call returns ``(spectrogram, audio)``."""
+
+    def __init__(self, model: VQVAE, code_t: torch.Tensor, code_b: torch.Tensor, warmup: int = 3,
+                 to_audio=None):
         if model.training:
             raise RuntimeError("GraphedDecodeCode needs model.eval()")
         if not (code_t.is_cuda and code_b.is_cuda):
             raise RuntimeError("code maps must be CUDA tensors: there is no CPU fallback")
         self.model = model
+        self._helper = to_audio
+
+        def run():
+            spec = model.decode_code(self._code_t, self._code_b)
+            return spec if to_audio is None else (spec, to_audio.to_audio(spec))
         self._code_t = code_t.detach().long().clone()
         self._code_b = code_b.detach().long().clone()
         stream = torch.cuda.Stream(code_t.device)
         stream.wait_stream(torch.cuda.current_stream(code_t.device))
         with torch.no_grad(), torch.cuda.stream(stream):
             for _ in range(max(1, warmup)):        # cuDNN plan selection happens outside the capture
-                model.decode_code(self._code_t, self._code_b)
+                run()
         torch.cuda.current_stream(code_t.device).wait_stream(stream)
         self._graph = torch.cuda.CUDAGraph()
         with torch.no_grad(), torch.cuda.graph(self._graph):
-            self._out = model.decode_code(self._code_t, self._code_b)
+            self._out = run()
 
-    def __call__(self, code_t: torch.Tensor, code_b: torch.Tensor) -> torch.Tensor:
+    def __call__(self, code_t: torch.Tensor, code_b: torch.Tensor):
         if code_t.shape != self._code_t.shape or code_b.shape != self._code_b.shape:
             raise ValueError(f"captured for code maps {tuple(self._code_t.shape)} / "
                              f"{tuple(self._code_b.shape)}, got {tuple(code_t.shape)} / {tuple(code_b.shape)}")

@@ -79,6 +79,10 @@ for s in $steps; do
       timeout 600 ncu --set full --clock-control none --import-source on -k regex:imelif_kernel -s 4 -c 1 \
         -o gpurun_out/imelif_$tag python tools/bench_inverse.py --only 444 > gpurun_out/ncu_imelif_$tag.log 2>&1
       tail -1 gpurun_out/ncu_imelif_$tag.log | cut -c1-200 ;;
+    launches_inverse)
+      timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv \
+        --log-file gpurun_out/launches_inverse_$tag.csv python tools/bench_inverse.py --kernel-only > gpurun_out/ncu_launches_inverse_$tag.log 2>&1
+      grep -c imelif gpurun_out/launches_inverse_$tag.csv ;;
     smoke)
       timeout 300 python __graft_entry__.py smoke 2>&1 | tail -2 ;;
     probe)

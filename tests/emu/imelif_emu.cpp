@@ -51,7 +51,7 @@ static void emulate(const float* spec, int64_t n_notes, int hop, int pad_left, i
         }
       }
       if (fstart > 0) {
-        for (int m = 0; m < M; ++m) sums[m] = lookback_row_sum(note1 + (int64_t)m * n_frames, fstart, affine[2], affine[3]);
+        for (int m = 0; m < M; ++m) sums[m] = lookback_row_sum(note1 + (int64_t)m * n_frames, fstart, affine[2], affine[3], n_frames % 4 == 0);
         for (int tid = 0; tid < NT; ++tid)
           for (int r = 0; r < RPT; ++r) {
             const int row = tid + r * NT;

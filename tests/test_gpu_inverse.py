@@ -65,9 +65,9 @@ def test_knobs_nyquist_bin_padding_and_affine():
 
 
 def test_batch_sizes_and_independence():
-    """flask_server batch sizes 1-16 choose different segmentations; a 444-note batch (the
-    extraction step's size) runs whole-note CTAs.  Every note equals the same note alone up to
-    the segmentation's rounding, and equal segmentations are bit-identical."""
+    """flask_server batch sizes 1-16 and a 444-note batch (the extraction step's size) choose
+    different segmentations.  Every note equals the same note alone up to the segmentation's
+    rounding, and within one launch equal inputs give bit-identical outputs."""
     helper = _helper(True)
     spec = _random_spec(2, 1024, 128, seed=21).to(DEV)
     alone = helper.to_audio(spec[:1])
@@ -79,7 +79,8 @@ def test_batch_sizes_and_independence():
     assert big.shape == (444, 64000) and torch.isfinite(big).all()
     assert torch.equal(big[0], big[442]) and torch.equal(big[1], big[443])
     helper.inverse_seg_frames = 128
-    assert torch.equal(helper.to_audio(spec), big[:2])
+    whole = helper.to_audio(spec)
+    assert (whole - big[:2]).abs().max() <= 2e-5 * whole.abs().max()
 
 
 def test_round_trip_through_both_kernels():
@@ -109,3 +110,24 @@ def test_strided_and_3d_inputs_empty_batches_and_errors():
         helper.to_audio(spec.clone().requires_grad_(True))
     got = helper.to_audio_differentiable(spec)
     assert (got - ref).abs().max() <= 1e-4 * ref.abs().max()
+
+
+def test_decode_graph_continues_into_the_inverse_front_end():
+    """The server's request: edited code maps -> decode_code -> to_audio, replayed from one
+    CUDA graph (flask_server.py:593-596), equals the eager calls."""
+    from interactive_spectrogram_inpainting_b200.vqvae.vqvae import VQVAE, GraphedDecodeCode
+    torch.manual_seed(0)
+    model = VQVAE(in_channel=2, resolution_factors={'bottom': 16, 'top': 2},
+                  adapt_quantized_durations=False).to(DEV).eval()
+    helper = _helper(True)
+    top, bottom = synthetic.synthetic_codemaps(2)
+    top, bottom = top.to(DEV), bottom.to(DEV)
+    graphed = GraphedDecodeCode(model, top, bottom, to_audio=helper)
+    for shift in (0, 7):
+        t, b = (top + shift) % 512, (bottom + shift) % 512
+        spec, audio = graphed(t, b)
+        with torch.no_grad():
+            want_spec = model.decode_code(t, b)
+        assert torch.allclose(spec, want_spec, rtol=1e-3, atol=1e-4)
+        assert audio.shape == (2, 64000) and torch.isfinite(audio).all()
+        assert torch.equal(audio, helper.to_audio(spec))      # same launch shape: bit-identical

@@ -78,6 +78,8 @@ def cfg4():
 
 
 def cfg5():
+    from interactive_spectrogram_inpainting_b200.utils.spectrograms_helper import MelSpectrogramsHelper
+    helper = MelSpectrogramsHelper().to(DEV)
     out = []
     torch.manual_seed(0)
     model = VQVAE(in_channel=2, resolution_factors={'bottom': 16, 'top': 2},
@@ -92,8 +94,16 @@ def cfg5():
             graphed = GraphedDecodeCode(model, top, bottom)
             graph_ms = timed(lambda: graphed(top, bottom))
             assert torch.allclose(graphed(top, bottom), model.decode_code(top, bottom), rtol=1e-3, atol=1e-4)
+            # the server's whole request: codes -> spectrogram -> audio (flask_server.py:593-596)
+            to_audio_ms = timed(lambda: helper.to_audio(graphed(top, bottom)))
+            to_audio_torch_ms = timed(lambda: helper.to_audio_differentiable(graphed(top, bottom)), iters=5)
+            full = GraphedDecodeCode(model, top, bottom, to_audio=helper)
+            full_ms = timed(lambda: full(top, bottom))
         out.append({"batch": b, "embed_code_top_plus_bottom_ms": lookup_ms,
-                    "decode_code_eager_ms": eager_ms, "decode_code_cuda_graph_ms": graph_ms})
+                    "decode_code_eager_ms": eager_ms, "decode_code_cuda_graph_ms": graph_ms,
+                    "codes_to_audio_graph_plus_kernel_ms": to_audio_ms,
+                    "codes_to_audio_graph_plus_torch_inverse_ms": to_audio_torch_ms,
+                    "codes_to_audio_one_cuda_graph_ms": full_ms})
     return out
 
 

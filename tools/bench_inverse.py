@@ -48,7 +48,7 @@ def main():
                             torch.rand(b, 1024, 128, generator=g) * 2 - 1], 1).to(DEV)
         with torch.no_grad():
             ms = timed(lambda: helper.to_audio(spec), flush=flush if b >= 16 else None)
-            torch_ms = None if only else timed(lambda: helper.to_audio_differentiable(spec), iters=5, warmup=2)
+            torch_ms = None if (only or "--kernel-only" in sys.argv) else timed(lambda: helper.to_audio_differentiable(spec), iters=5, warmup=2)
         bytes_alg = b * (2 * 1024 * 128 * 4 + 64000 * 4)
         rows.append({"batch": b, "kernel_ms": ms, "torch_ops_ms": torch_ms,
                      "us_per_note": 1e3 * ms / b, "algorithmic_GBps": bytes_alg / (ms * 1e-3) / 1e9})
