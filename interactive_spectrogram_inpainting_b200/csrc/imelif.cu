@@ -236,7 +236,7 @@ imelif_kernel(const float* __restrict__ spec, isi_imelif_params p, float* __rest
 // maximises (wave efficiency) x (useful / useful + re-synthesised frames).
 static void choose_segments(int64_t n_notes, int n_frames, int fb, int lookback, int* seg_frames, int* n_segs) {
   const int frames_padded = (n_frames + fb - 1) / fb * fb;
-  const int max_segs = frames_padded / (2 * fb) > 1 ? frames_padded / (2 * fb) : 1;
+  const int max_segs = frames_padded / fb > 1 ? frames_padded / fb : 1;   // one batch per CTA at most
   const double slots = 2.0 * kNumSms;   // __launch_bounds__(NT, 2)
   const double redo = (lookback + fb - 1) / fb * fb;
   double best = -1.0;
