@@ -164,6 +164,35 @@ ISI_API int isi_embed_code(const int64_t* index, int64_t n_rows, int dim, int n_
                    isi_stream_t stream);
 
 /* ------------------------------------------------------------------ *
+ *  (2') pre-quantiser projection: concat + 1x1 conv + bias            *
+ * ------------------------------------------------------------------ */
+
+/* Bytes of the prepared weight image for `c_in` input channels (multiple of 64). */
+ISI_API size_t isi_vq_project_prepared_bytes(int c_in);
+
+/*
+ * weight [c_out = 64, c_in] FP32 row-major -- the Conv2d(c_in, 64, 1) weight of
+ * quantize_conv_t / quantize_conv_b (vqvae.py:149-150,175-177) -- -> TF32 hi/lo operand
+ * chunks.  Re-run when the weight changes.  `prepared` 128-byte aligned.
+ */
+ISI_API int isi_vq_project_prepare(const float* weight, int c_in, int c_out, void* prepared,
+                           size_t prepared_bytes, isi_stream_t stream);
+
+/*
+ * out[n, 0:64] = bias + W[:, 0:c0] src0[n, :] + W[:, c0:c0+c1] src1[n, :]
+ * Replaces vqvae.py:260 (quantize_conv_t(enc_t)) with src1 = NULL, c1 = 0, and vqvae.py:271-272
+ * (quantize_conv_b(torch.cat([dec_t, enc_b], 1))) with src0 = dec_t, src1 = enc_b: the
+ * concatenation is never materialised.  Sources are channels-last rows: src_s[n, c] =
+ * src_s[n * row_stride_s + c] (what a torch.channels_last [B, C, H, W] tensor is, with n = (b, h,
+ * w)); c0, c1 multiples of 64, c0 + c1 <= 1024; row strides multiples of 4; pointers 16-byte
+ * aligned.  `out` is contiguous [n_rows, 64]: the layout isi_vq_assign reads fastest.
+ * 3xTF32 tensor-core contraction (FP32-equivalent; the reference's conv runs in TF32 on GPU).
+ */
+ISI_API int isi_vq_project(const float* src0, int c0, int64_t row_stride0, const float* src1, int c1,
+                   int64_t row_stride1, int64_t n_rows, int c_out, const void* prepared,
+                   const float* bias, float* out, isi_stream_t stream);
+
+/* ------------------------------------------------------------------ *
  *  (1) front end: STFT -> (mel) -> log-magnitude + instantaneous freq *
  * ------------------------------------------------------------------ */
 

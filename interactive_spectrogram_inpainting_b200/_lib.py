@@ -81,6 +81,13 @@ EXPORTS = {
                                       ctypes.c_void_p, ctypes.c_void_p,
                                       ctypes.POINTER(RowsLayout), ctypes.c_void_p,
                                       ctypes.c_void_p]),
+    "isi_vq_project_prepared_bytes": (ctypes.c_size_t, [ctypes.c_int]),
+    "isi_vq_project_prepare": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int,
+                                              ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+    "isi_vq_project": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p,
+                                      ctypes.c_int, ctypes.c_int64, ctypes.c_int64, ctypes.c_int,
+                                      ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                      ctypes.c_void_p]),
     "isi_melif_forward": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64,
                                          ctypes.POINTER(MelifParams), ctypes.c_void_p,
                                          ctypes.c_void_p]),
@@ -175,7 +182,7 @@ def rows_layout(t: torch.Tensor) -> Optional[RowsLayout]:
 KERNELS_PER_CALL = {
     "isi_vq_prepare_codebook": 3, "isi_vq_assign": 1, "isi_vq_gather_stats": 1,
     "isi_vq_finish": 1, "isi_vq_ema_update": 2, "isi_embed_code": 1, "isi_melif_forward": 1,
-    "isi_melif_inverse": 1,
+    "isi_melif_inverse": 1, "isi_vq_project_prepare": 1, "isi_vq_project": 1,
 }
 launch_counts = {name: 0 for name in KERNELS_PER_CALL}
 

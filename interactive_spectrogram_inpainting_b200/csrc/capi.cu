@@ -26,6 +26,10 @@ int launch_finish(const void*, int64_t, int, int, const float*, float*, float*, 
 int launch_ema_update(float*, float*, float*, float*, int, int, double, double, cudaStream_t);
 int launch_embed_code(const int64_t*, int64_t, int, int, const Prepared&, float*,
                       const isi_rows_layout&, int32_t*, cudaStream_t);
+size_t project_prepared_bytes(int);
+int launch_project_prepare(const float*, int, void*, cudaStream_t);
+int launch_project(const float*, int, int64_t, const float*, int, int64_t, int64_t, const void*, const float*,
+                   float*, cudaStream_t);
 int launch_melif(const void*, int64_t, int64_t, const isi_melif_params&, float*, cudaStream_t);
 int launch_imelif(const float*, int64_t, const isi_imelif_params&, float*, int64_t, int, cudaStream_t);
 }  // namespace isi
@@ -147,6 +151,35 @@ ISI_API int isi_embed_code(const int64_t* index, int64_t n_rows, int dim, int n_
   if (n_rows == 0) return ISI_OK;
   return launch_embed_code(index, n_rows, dim, n_embed, prepared_view(prepared, dim, n_embed), out,
                            *ol, status_flag, (cudaStream_t)stream);
+}
+
+ISI_API size_t isi_vq_project_prepared_bytes(int c_in) {
+  if (c_in <= 0 || c_in % 64 || c_in > 1024) return 0;
+  return project_prepared_bytes(c_in);
+}
+
+ISI_API int isi_vq_project_prepare(const float* weight, int c_in, int c_out, void* prepared,
+                           size_t prepared_bytes, isi_stream_t stream) {
+  if (!weight || !prepared) return ISI_ERR_NULL;
+  if (c_out != 64 || c_in <= 0 || c_in % 64 || c_in > 1024) return ISI_ERR_UNSUPPORTED;
+  if (prepared_bytes < project_prepared_bytes(c_in)) return ISI_ERR_WORKSPACE;
+  if ((uintptr_t)prepared % 128) return ISI_ERR_ALIGN;
+  return launch_project_prepare(weight, c_in, prepared, (cudaStream_t)stream);
+}
+
+ISI_API int isi_vq_project(const float* src0, int c0, int64_t row_stride0, const float* src1, int c1,
+                   int64_t row_stride1, int64_t n_rows, int c_out, const void* prepared,
+                   const float* bias, float* out, isi_stream_t stream) {
+  if (!src0 || !prepared || !out || (c1 > 0 && !src1)) return ISI_ERR_NULL;
+  if (n_rows < 0 || c0 <= 0 || c1 < 0) return ISI_ERR_SHAPE;
+  if (c_out != 64 || c0 % 64 || c1 % 64 || c0 + c1 > 1024) return ISI_ERR_UNSUPPORTED;
+  if (row_stride0 < c0 || (c1 > 0 && row_stride1 < c1)) return ISI_ERR_SHAPE;
+  if (row_stride0 % 4 || (c1 > 0 && row_stride1 % 4) || (uintptr_t)src0 % 16 || (c1 > 0 && (uintptr_t)src1 % 16) ||
+      (uintptr_t)out % 16 || (uintptr_t)prepared % 128 || (bias && (uintptr_t)bias % 4))
+    return ISI_ERR_ALIGN;
+  if (n_rows == 0) return ISI_OK;
+  return launch_project(src0, c0, row_stride0, c1 > 0 ? src1 : src0, c1, c1 > 0 ? row_stride1 : row_stride0,
+                        n_rows, prepared, bias, out, (cudaStream_t)stream);
 }
 
 ISI_API int isi_melif_forward(const void* audio, int64_t n_notes, int64_t n_samples,

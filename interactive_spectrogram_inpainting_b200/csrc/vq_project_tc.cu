@@ -1,0 +1,285 @@
+// Pre-quantiser projection on the tensor cores: the 1x1 `quantize_conv_{t,b}` of the reference
+// (vqvae.py:149-150,175-177, called at :260 and :272) together with the channel concatenation in
+// front of the bottom one (vqvae.py:271), as one kernel -- SURVEY.md section 8(f) N3.
+//
+//   out[n, :] = bias + sum_s W_s f_s[n, :]        f_s = rows of up to two channels-last sources
+//
+// i.e. torch.cat([dec_t, enc_b], 1) -> Conv2d(C, 64, 1) without materialising the concatenation,
+// without a separate bias pass, and with the result written as the contiguous [N, 64] rows the
+// nearest-code search reads.  tcgen05.mma kind::tf32 with the same 3xTF32 split as the search
+// (FP32-equivalent accuracy: the dropped lo*lo term is ~2^-22 relative), accumulators in TMEM.
+//
+// Same skeleton as vq_assign_tc.cu, with the roles of the streamed operand exchanged: the 64
+// output channels are ONE operand tile, and the contraction runs over 64-channel chunks of the
+// inputs, accumulating in the same TMEM columns.  Persistent CTAs, one per SM, 256-row tiles:
+//   warps 0-3  epilogue   tcgen05.ld the 128 x 64 accumulators, add the bias, store rows
+//   warps 4-11 loader     coalesced reads of the NEXT (tile, chunk) into registers while the MMAs
+//                         of the current one run; hi/lo split; st.shared in the UMMA layout
+//   warp  12   W producer streams the pre-split, pre-swizzled 64x64 weight chunks (cp.async.bulk)
+//   warp  13   MMA issuer one elected lane; owns TMEM (2 stages x 2 row tiles x 64 columns)
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace isi {
+
+namespace proj {
+
+constexpr int kRowsPerMma = 128;
+constexpr int kMmaPerTile = 2;
+constexpr int kTileRows = kRowsPerMma * kMmaPerTile;   // 256
+constexpr int kOut = 64;                               // output channels (UMMA N)
+constexpr int kChunk = 64;                             // input channels per contraction chunk
+constexpr int kSlabs = kChunk / 32;
+constexpr int kABytesPart = kSlabs * kRowsPerMma * 128;          // one (m, hi|lo) operand: 32 KB
+constexpr int kABytes = kMmaPerTile * 2 * kABytesPart;            // 128 KB
+constexpr int kWBytesPart = kSlabs * kOut * 128;                 // one (hi|lo) weight chunk: 16 KB
+constexpr int kWStageBytes = 2 * kWBytesPart;                     // 32 KB
+constexpr int kAccStages = 2;
+constexpr int kTmemCols = kAccStages * kMmaPerTile * kOut;        // 256
+constexpr int kFirstLoaderWarp = 4;
+constexpr int kLoaderWarps = 8;
+constexpr int kLoaderThreads = kLoaderWarps * 32;                                   // 256
+constexpr int kChunksPerThread = kTileRows * (kChunk / 4) / kLoaderThreads;         // 16
+constexpr int kProducerWarp = kFirstLoaderWarp + kLoaderWarps;                      // 12
+constexpr int kMmaWarp = kProducerWarp + 1;                                         // 13
+constexpr int kThreads = (kMmaWarp + 1) * 32;                                       // 448
+constexpr int kMaxChunks = 16;                                                      // C <= 1024
+
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kOut >> 3) << 17) |
+                            ((uint32_t)(kRowsPerMma >> 4) << 24);
+
+struct Smem {
+  static constexpr int a = 0;                                   // 1024-aligned operand tiles
+  static constexpr int w = a + kABytes;
+  static constexpr int bias = w + 2 * kWStageBytes;
+  static constexpr int bars = bias + kOut * 4;
+  static constexpr int total = bars + 128;
+};
+
+}  // namespace proj
+
+using namespace umma;
+
+// weight [64, C] (the Conv2d weight [64, C, 1, 1]) -> per 64-channel chunk the TF32 hi and lo
+// parts in exactly the bytes the kernel's shared-memory stage expects
+__global__ void __launch_bounds__(256)
+vq_project_prepare_kernel(const float* __restrict__ weight, int c_total, char* __restrict__ prepared) {
+  using namespace proj;
+  const int total = c_total * kOut;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+    const int n = e / c_total, c = e % c_total;
+    const float v = weight[e];
+    const float hi = to_tf32(v);
+    const float lo = to_tf32(v - hi);
+    const size_t off = (size_t)(c / kChunk) * kWStageBytes + operand_offset(kOut, n, c % kChunk);
+    *reinterpret_cast<float*>(prepared + off) = hi;
+    *reinterpret_cast<float*>(prepared + off + kWBytesPart) = lo;
+  }
+}
+
+__global__ void __launch_bounds__(proj::kThreads, 1)
+vq_project_tc_kernel(const float* __restrict__ src0, int chunks0, int64_t stride0,
+                     const float* __restrict__ src1, int chunks1, int64_t stride1, int64_t n_rows,
+                     const char* __restrict__ w_tiles, const float* __restrict__ bias_global,
+                     float* __restrict__ out) {
+  using namespace proj;
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const uint32_t smem_base = s32(smem);
+  float* bias = reinterpret_cast<float*>(smem + Smem::bias);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::bars);
+  const uint32_t bar_w_full = s32(bars + 0);     // [2]
+  const uint32_t bar_w_empty = s32(bars + 2);    // [2]
+  const uint32_t bar_acc_full = s32(bars + 4);   // [2]
+  const uint32_t bar_acc_empty = s32(bars + 6);  // [2]
+  const uint32_t bar_a_full = s32(bars + 8);
+  const uint32_t bar_a_empty = s32(bars + 9);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_chunks = chunks0 + chunks1;
+  const int64_t n_row_tiles = (n_rows + kTileRows - 1) / kTileRows;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_w_full + 8 * i, 1);
+      mbar_init(bar_w_empty + 8 * i, 1);
+      mbar_init(bar_acc_full + 8 * i, 1);
+      mbar_init(bar_acc_empty + 8 * i, 128);
+    }
+    mbar_init(bar_a_full, kLoaderThreads);
+    mbar_init(bar_a_empty, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_slot)),
+                 "n"(kTmemCols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  if (threadIdx.x < kOut) bias[threadIdx.x] = bias_global ? bias_global[threadIdx.x] : 0.f;
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp >= kFirstLoaderWarp && warp < kFirstLoaderWarp + kLoaderWarps) {
+    // ===================== input loader / splitter =====================
+    // Thread t owns 16-byte piece c = t % 16 of rows t / 16 + 16 i: the 16 lanes of a row read
+    // its 256 contiguous bytes of the chunk.
+    const int t = threadIdx.x - kFirstLoaderWarp * 32;
+    const int c4 = t % (kChunk / 4), r0 = t / (kChunk / 4);
+    float4 buf[kChunksPerThread];
+    auto fetch = [&](int64_t tile, int chunk) {
+      const bool first = chunk < chunks0;
+      const float* base = first ? src0 + chunk * kChunk : src1 + (chunk - chunks0) * kChunk;
+      const int64_t stride = first ? stride0 : stride1;
+      const int64_t row0 = tile * kTileRows;
+#pragma unroll
+      for (int i = 0; i < kChunksPerThread; ++i) {
+        const int64_t row = row0 + r0 + i * (kLoaderThreads / (kChunk / 4));
+        buf[i] = row < n_rows ? __ldg(reinterpret_cast<const float4*>(base + row * stride) + c4)
+                              : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    uint32_t step = 0;
+    if ((int64_t)blockIdx.x < n_row_tiles) fetch(blockIdx.x, 0);
+    for (int64_t tile = blockIdx.x; tile < n_row_tiles; tile += gridDim.x) {
+      for (int chunk = 0; chunk < n_chunks; ++chunk, ++step) {
+        mbar_wait(bar_a_empty, (step & 1) ^ 1);            // MMAs of the previous step are done
+#pragma unroll
+        for (int i = 0; i < kChunksPerThread; ++i) {
+          const int r = r0 + i * (kLoaderThreads / (kChunk / 4));
+          const float4 v = buf[i];
+          const float4 hi = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+          const float4 lo = make_float4(to_tf32(v.x - hi.x), to_tf32(v.y - hi.y), to_tf32(v.z - hi.z),
+                                        to_tf32(v.w - hi.w));
+          const int m = r >> 7, rr = r & 127;
+          const uint32_t off = Smem::a + (uint32_t)(m * 2) * kABytesPart + operand_offset(kRowsPerMma, rr, 4 * c4);
+          *reinterpret_cast<float4*>(smem + off) = hi;
+          *reinterpret_cast<float4*>(smem + off + kABytesPart) = lo;
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy
+        mbar_arrive(bar_a_full);
+        if (chunk + 1 < n_chunks) fetch(tile, chunk + 1);
+        else if (tile + gridDim.x < n_row_tiles) fetch(tile + gridDim.x, 0);
+      }
+    }
+  } else if (warp == kProducerWarp) {
+    // ===================== weight producer =====================
+    if (lane == 0) {
+      uint32_t step = 0;
+      for (int64_t tile = blockIdx.x; tile < n_row_tiles; tile += gridDim.x) {
+        for (int chunk = 0; chunk < n_chunks; ++chunk, ++step) {
+          const uint32_t s = step & 1, ph = (step >> 1) & 1;
+          mbar_wait(bar_w_empty + 8 * s, ph ^ 1);
+          mbar_expect_tx(bar_w_full + 8 * s, kWStageBytes);
+          bulk_g2s(smem_base + Smem::w + s * kWStageBytes, w_tiles + (size_t)chunk * kWStageBytes,
+                   kWStageBytes, bar_w_full + 8 * s);
+        }
+      }
+    }
+  } else if (warp == kMmaWarp) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      uint32_t step = 0, it = 0;
+      for (int64_t tile = blockIdx.x; tile < n_row_tiles; tile += gridDim.x, ++it) {
+        const uint32_t sa = it & 1;
+        mbar_wait(bar_acc_empty + 8 * sa, ((it >> 1) & 1) ^ 1);   // the epilogue has drained this stage
+        for (int chunk = 0; chunk < n_chunks; ++chunk, ++step) {
+          const uint32_t s = step & 1, ph = (step >> 1) & 1;
+          mbar_wait(bar_a_full, step & 1);
+          mbar_wait(bar_w_full + 8 * s, ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t w_base = smem_base + Smem::w + s * kWStageBytes;
+#pragma unroll
+          for (int m = 0; m < kMmaPerTile; ++m) {
+            const uint32_t d_tmem = tmem_base + (uint32_t)((sa * kMmaPerTile + m) * kOut);
+            const uint32_t a_base = smem_base + Smem::a + (uint32_t)(m * 2) * kABytesPart;
+            uint32_t acc = chunk > 0 ? 1u : 0u;
+#pragma unroll
+            for (int term = 0; term < 3; ++term) {
+              // (f_lo, w_hi), (f_hi, w_lo), (f_hi, w_hi): small terms first
+              const uint32_t a_part = a_base + (term == 0 ? kABytesPart : 0);
+              const uint32_t w_part = w_base + (term == 1 ? kWBytesPart : 0);
+#pragma unroll
+              for (int slab = 0; slab < kSlabs; ++slab) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                  const uint64_t ad = umma_desc(a_part + slab * (kRowsPerMma * 128) + kk * 32);
+                  const uint64_t wd = umma_desc(w_part + slab * (kOut * 128) + kk * 32);
+                  umma_tf32(d_tmem, ad, wd, kIdesc, acc);
+                  acc = 1;
+                }
+              }
+            }
+          }
+          umma_commit(bar_w_empty + 8 * s);       // the weight stage may be refilled
+          umma_commit(bar_a_empty);                // the input chunk may be overwritten
+        }
+        umma_commit(bar_acc_full + 8 * sa);        // every chunk has been accumulated
+      }
+    }
+  } else {
+    // ===================== epilogue: bias, rows out =====================
+    uint32_t it = 0;
+    const uint32_t lane_field = (uint32_t)(warp * 32) << 16;
+    for (int64_t tile = blockIdx.x; tile < n_row_tiles; tile += gridDim.x, ++it) {
+      const uint32_t sa = it & 1;
+      mbar_wait(bar_acc_full + 8 * sa, (it >> 1) & 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+      for (int m = 0; m < kMmaPerTile; ++m) {
+        float v[kOut];
+        tmem_ld64(tmem_base + lane_field + (uint32_t)((sa * kMmaPerTile + m) * kOut), v);
+        const int64_t row = tile * kTileRows + m * kRowsPerMma + warp * 32 + lane;
+        if (row < n_rows) {
+          float4* dst = reinterpret_cast<float4*>(out + row * kOut);
+#pragma unroll
+          for (int c = 0; c < kOut; c += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(bias + c);
+            dst[c >> 2] = make_float4(v[c] + b.x, v[c + 1] + b.y, v[c + 2] + b.z, v[c + 3] + b.w);
+          }
+        }
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(bar_acc_empty + 8 * sa);
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == kMmaWarp) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
+  }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+size_t project_prepared_bytes(int c_total) {
+  return (size_t)(c_total / proj::kChunk) * proj::kWStageBytes;
+}
+
+int launch_project_prepare(const float* weight, int c_total, void* prepared, cudaStream_t stream) {
+  const int total = c_total * proj::kOut;
+  vq_project_prepare_kernel<<<(total + 255) / 256, 256, 0, stream>>>(weight, c_total,
+                                                                     reinterpret_cast<char*>(prepared));
+  ISI_LAUNCH_CHECK();
+  return ISI_OK;
+}
+
+int launch_project(const float* src0, int c0, int64_t stride0, const float* src1, int c1, int64_t stride1,
+                   int64_t n_rows, const void* prepared, const float* bias, float* out, cudaStream_t stream) {
+  using namespace proj;
+  cudaError_t e = cudaFuncSetAttribute(vq_project_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Smem::total);
+  if (e != cudaSuccess) return (int)e;
+  const int64_t n_row_tiles = (n_rows + kTileRows - 1) / kTileRows;
+  const int grid = (int)(n_row_tiles < kNumSms ? n_row_tiles : kNumSms);
+  vq_project_tc_kernel<<<grid, kThreads, Smem::total, stream>>>(
+      src0, c0 / kChunk, stride0, src1, c1 / kChunk, stride1, n_rows,
+      reinterpret_cast<const char*>(prepared), bias, out);
+  ISI_LAUNCH_CHECK();
+  return ISI_OK;
+}
+
+}  // namespace isi

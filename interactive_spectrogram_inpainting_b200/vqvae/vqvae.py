@@ -19,6 +19,7 @@ from typing import Mapping, Optional, Sequence, Type, Union
 import torch
 from torch import nn
 
+from .. import _lib
 from .bottleneck import QuantizedBottleneck
 
 # channel plan of the strided stages in quarters of `channel` (encoder_decoder.py:52-116)
@@ -74,6 +75,87 @@ def _run_blocks(blocks: Sequence[nn.Module], x: torch.Tensor) -> torch.Tensor:
         rectified = absorbs or isinstance(m, nn.ReLU)
         i += 2 if (absorbs and isinstance(nxt, nn.ReLU)) else 1
     return x
+
+
+def _as_rows(x: torch.Tensor):
+    """``(row_stride)`` if ``x [B, C, H, W]`` is stored channels-last with uniformly strided
+    rows ``(b, h, w)`` of ``C`` contiguous values, else None."""
+    b, c, h, w = x.shape
+    if x.stride(1) != 1 and c != 1:
+        return None
+    rs = x.stride(3) if w > 1 else (x.stride(2) if h > 1 else x.stride(0))
+    if (w > 1 and x.stride(3) != rs) or (h > 1 and x.stride(2) != w * rs) or (b > 1 and x.stride(0) != h * w * rs):
+        return None
+    return rs if rs >= c and rs % 4 == 0 else None
+
+
+class PointwiseProjection:
+    """``conv(torch.cat(sources, 1))`` for a 1x1 ``Conv2d(C, 64)`` as ONE kernel of this repo
+    (``isi_vq_project``, csrc/vq_project_tc.cu): the concatenation is never
+    written, the bias is added in the epilogue, and the result comes back as the contiguous
+    ``[B, H, W, 64]`` rows the nearest-code search reads (the reference permutes the NCHW conv
+    output, vqvae.py:260,272).  ``folded_bias`` is the bias of a transposed convolution that
+    produced ``sources[0]`` and was left out there: ``W[:, :c0] @ folded_bias`` joins the bias.
+
+    Inference only (CUDA, ``no_grad``, channels-last sources with 64 | C, at least
+    ``min_rows`` rows); ``usable`` says whether a call qualifies -- callers keep the stock modules
+    otherwise."""
+
+    min_rows = 1024
+
+    def __init__(self, conv: nn.Conv2d):
+        self.conv = conv
+        self._key = None
+        self._prepared = None
+        self._bias = None
+
+    def usable(self, sources) -> bool:
+        conv = self.conv
+        if not (type(conv) is nn.Conv2d and conv.kernel_size == (1, 1) and conv.stride == (1, 1)
+                and conv.padding == (0, 0) and conv.groups == 1 and conv.out_channels == 64):
+            return False
+        if not 1 <= len(sources) <= 2 or not _can_fuse(sources[0]):
+            return False
+        if sum(x.shape[1] for x in sources) != conv.in_channels or conv.in_channels > 1024:
+            return False
+        shape = sources[0].shape
+        for x in sources:
+            if (x.dim() != 4 or x.dtype != torch.float32 or x.shape[1] % 64 or x.device != conv.weight.device
+                    or x.shape[0] != shape[0] or x.shape[2:] != shape[2:] or _as_rows(x) is None
+                    or x.data_ptr() % 16):
+                return False
+        return shape[0] * shape[2] * shape[3] >= self.min_rows
+
+    def _prepare(self, c0: int, folded_bias):
+        conv = self.conv
+        w, b = conv.weight, conv.bias
+        key = (w._version, w.data_ptr(), None if b is None else (b._version, b.data_ptr()),
+               None if folded_bias is None else (folded_bias._version, folded_bias.data_ptr()), c0)
+        if key == self._key:
+            return
+        c_in = conv.in_channels
+        w2 = w.detach().reshape(64, c_in).contiguous()
+        nbytes = _lib.load().isi_vq_project_prepared_bytes(c_in)
+        self._prepared = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+        _lib.invoke("isi_vq_project_prepare", w2.data_ptr(), c_in, 64, self._prepared.data_ptr(), nbytes,
+                    _lib.stream_ptr(w.device))
+        bias = torch.zeros(64, device=w.device) if b is None else b.detach().clone()
+        if folded_bias is not None:
+            bias = bias + (w2[:, :c0].double() @ folded_bias.detach().double()).float()
+        self._bias = bias.contiguous()
+        self._key = key
+
+    def __call__(self, sources, folded_bias=None) -> torch.Tensor:
+        x0 = sources[0]
+        x1 = sources[1] if len(sources) > 1 else None
+        self._prepare(x0.shape[1], folded_bias)
+        b, _, h, w = x0.shape
+        out = torch.empty(b, h, w, 64, dtype=torch.float32, device=x0.device)
+        _lib.invoke("isi_vq_project", x0.data_ptr(), x0.shape[1], _as_rows(x0),
+                    None if x1 is None else x1.data_ptr(), 0 if x1 is None else x1.shape[1],
+                    0 if x1 is None else _as_rows(x1), b * h * w, 64, self._prepared.data_ptr(),
+                    self._bias.data_ptr(), out.data_ptr(), _lib.stream_ptr(x0.device))
+        return out
 
 
 class ResBlock(nn.Module):
@@ -171,8 +253,15 @@ class Decoder(nn.Module):
             prev = w
         self.blocks = nn.Sequential(*blocks)
 
-    def forward(self, x):
-        return _run_blocks(self.blocks, x)
+    def forward(self, x, without_last_bias: bool = False):
+        """``without_last_bias``: leave out the bias of the final transposed convolution (the
+        caller folds it into the 1x1 projection that consumes the result, PointwiseProjection)."""
+        last = self.blocks[-1]
+        if not (without_last_bias and type(last) is nn.ConvTranspose2d and last.bias is not None):
+            return _run_blocks(self.blocks, x)
+        x = _run_blocks(list(self.blocks)[:-1], x)
+        return torch.nn.functional.conv_transpose2d(x, last.weight, None, last.stride, last.padding,
+                                                    last.output_padding, last.groups, last.dilation)
 
 
 class VQVAE(nn.Module):
@@ -229,6 +318,32 @@ class VQVAE(nn.Module):
             for _ in range(int(math.log2(resolution_factors['top'])))])
         self.dec = Decoder(2 * embed_dim, in_channel, c, rb, rc, resolution_factors['bottom'],
                            use_local_kernels)
+        self._project_t = PointwiseProjection(self.quantize_conv_t)
+        self._project_b = PointwiseProjection(self.quantize_conv_b)
+
+    # -- the two pre-quantiser 1x1 convolutions (vqvae.py:260 and :271-272), as ``[B, H, W, D]`` --
+    def _prequant_top(self, enc_t: torch.Tensor) -> torch.Tensor:
+        if self._project_t.usable([enc_t]):
+            return self._project_t([enc_t])
+        return self.quantize_conv_t(enc_t).permute(0, 2, 3, 1)
+
+    def _prequant_bottom(self, quant_t: torch.Tensor, enc_b: torch.Tensor) -> torch.Tensor:
+        last = self.dec_t.blocks[-1]
+        fold = (not self.adapt_quantized_durations and type(last) is nn.ConvTranspose2d
+                and last.bias is not None and _can_fuse(enc_b) and _as_rows(enc_b) is not None
+                and enc_b.shape[1] % 64 == 0 and self.quantize_conv_b.out_channels == 64
+                and enc_b.shape[0] * enc_b.shape[2] * enc_b.shape[3] >= PointwiseProjection.min_rows)
+        dec_t = self.dec_t(quant_t, without_last_bias=fold)
+        if self.adapt_quantized_durations:
+            n = min(dec_t.shape[-1], enc_b.shape[-1])
+            dec_t, enc_b = dec_t[..., :n], enc_b[..., :n]
+        if fold and self._project_b.usable([dec_t, enc_b]):
+            return self._project_b([dec_t, enc_b], folded_bias=last.bias)
+        if fold:
+            dec_t = dec_t + last.bias.view(1, -1, 1, 1)
+        if self._project_b.usable([dec_t, enc_b]):
+            return self._project_b([dec_t, enc_b])
+        return self.quantize_conv_b(torch.cat([dec_t, enc_b], 1)).permute(0, 2, 3, 1)
 
     # -- vqvae.py:251-278 --
     def encode(self, input: torch.Tensor, space_to_depth: bool = False):
@@ -237,16 +352,10 @@ class VQVAE(nn.Module):
         enc_b = self.enc_b(input, space_to_depth=space_to_depth)
         enc_t = self.enc_t(enc_b)
 
-        quant_t, diff_t, id_t, perplexity_t = self.quantize_t(
-            self.quantize_conv_t(enc_t).permute(0, 2, 3, 1))
+        quant_t, diff_t, id_t, perplexity_t = self.quantize_t(self._prequant_top(enc_t))
         quant_t = quant_t.permute(0, 3, 1, 2)
 
-        dec_t = self.dec_t(quant_t)
-        if self.adapt_quantized_durations:
-            n = min(dec_t.shape[-1], enc_b.shape[-1])
-            dec_t, enc_b = dec_t[..., :n], enc_b[..., :n]
-        quant_b, diff_b, id_b, perplexity_b = self.quantize_b(
-            self.quantize_conv_b(torch.cat([dec_t, enc_b], 1)).permute(0, 2, 3, 1))
+        quant_b, diff_b, id_b, perplexity_b = self.quantize_b(self._prequant_bottom(quant_t, enc_b))
         quant_b = quant_b.permute(0, 3, 1, 2)
         return (quant_t, quant_b, diff_t.unsqueeze(0) + diff_b.unsqueeze(0), id_t, id_b,
                 perplexity_t, perplexity_b)
@@ -260,13 +369,8 @@ class VQVAE(nn.Module):
             return out[3], out[4]
         enc_b = self.enc_b(input, space_to_depth=space_to_depth)
         enc_t = self.enc_t(enc_b)
-        quant_t, _, id_t, _ = self.quantize_t(self.quantize_conv_t(enc_t).permute(0, 2, 3, 1))
-        dec_t = self.dec_t(quant_t.permute(0, 3, 1, 2))
-        if self.adapt_quantized_durations:
-            n = min(dec_t.shape[-1], enc_b.shape[-1])
-            dec_t, enc_b = dec_t[..., :n], enc_b[..., :n]
-        id_b = self.quantize_b.assign(
-            self.quantize_conv_b(torch.cat([dec_t, enc_b], 1)).permute(0, 2, 3, 1))
+        quant_t, _, id_t, _ = self.quantize_t(self._prequant_top(enc_t))
+        id_b = self.quantize_b.assign(self._prequant_bottom(quant_t.permute(0, 3, 1, 2), enc_b))
         return id_t, id_b
 
     # -- vqvae.py:280-295 --

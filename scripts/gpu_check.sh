@@ -83,6 +83,9 @@ for s in $steps; do
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv \
         --log-file gpurun_out/launches_inverse_$tag.csv python tools/bench_inverse.py --kernel-only > gpurun_out/ncu_launches_inverse_$tag.log 2>&1
       grep -c imelif gpurun_out/launches_inverse_$tag.csv ;;
+    projection)
+      timeout 240 python -m pytest tests/test_gpu_projection.py -x -q -s 2>&1 | tail -30 > gpurun_out/pytest_projection_$tag.log
+      tail -12 gpurun_out/pytest_projection_$tag.log ;;
     smoke)
       timeout 300 python __graft_entry__.py smoke 2>&1 | tail -2 ;;
     probe)
