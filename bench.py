@@ -358,6 +358,22 @@ def b200_arm(args):
         ema_ms = statistics.mean(tms["isi_vq_ema_update"])
         gather_bytes = qn * (4 * DIM * 2 + 8) + 4 * N_EMBED * (DIM + 1)
 
+        # inverse front end (to_audio) on one batch of decoded-spectrogram shape
+        inv_helper = MelSpectrogramsHelper().to(dev)
+        inv_spec = torch.stack([torch.randn(B, 1024, 128, device=dev) * 2 - 3,
+                                torch.rand(B, 1024, 128, device=dev) * 2 - 1], 1)
+        for _ in range(2):
+            inv_helper.to_audio(inv_spec)
+        torch.cuda.synchronize()
+        t0, t1 = ev(), ev()
+        t0.record()
+        for _ in range(5):
+            inv_helper.to_audio(inv_spec)
+        t1.record()
+        torch.cuda.synchronize()
+        inverse_ms = t0.elapsed_time(t1) / 5
+        del inv_spec
+
         # TF32 dense peak of this box, measured like MEASURED_PEAKS.json measured BF16
         torch.backends.cuda.matmul.allow_tf32 = True
         ma = torch.randn(8192, 8192, device=dev)
@@ -376,6 +392,7 @@ def b200_arm(args):
         del ma, mb
 
     hbm_peak, peak_kind, _ = measured_peaks()
+    project_bytes = B * (128 * (4 * 128 + 256) + 512 * (4 * 192 + 256))
     # algorithmic bytes per note: the samples as uploaded + the FP32 spectrogram
     melif_bytes_per_note = MELIF_BYTES_PER_NOTE - (4 - host_audio.element_size()) * N_SAMPLES
     melif_gbs = melif_bytes_per_note * B / (melif_ms * 1e-3) / 1e9
@@ -450,7 +467,21 @@ def b200_arm(args):
              "frac": gather_bytes / (gather_ms * 1e-3) / 1e9 / hbm_peak, "ms_per_launch": gather_ms,
              "rows": qn, "note": "N*(4D read + 4D write + 8) + 4K(D+1) algorithmic bytes"},
             {"kernel": "vq_ema_update (2 kernels)", "bound": "latency", "ms_per_launch": ema_ms,
-             "note": "K*D = 32768 elements; launch-latency bound"}],
+             "note": "K*D = 32768 elements; launch-latency bound"},
+            {"kernel": "vq_project_tc (concat + 1x1 quantize_conv + bias, top + bottom call of a step)",
+             "bound": "hbm", "unit": "GB/s", "peak": hbm_peak,
+             "achieved": (project_bytes / (kernel_ms_per_step["isi_vq_project"] * 1e-3) / 1e9
+                          if kernel_ms_per_step.get("isi_vq_project") else None),
+             "frac": (project_bytes / (kernel_ms_per_step["isi_vq_project"] * 1e-3) / 1e9 / hbm_peak
+                      if kernel_ms_per_step.get("isi_vq_project") else None),
+             "ms_per_launch": kernel_ms_per_step.get("isi_vq_project"), "rows": B * 640,
+             "note": "rows * (4 C_in read + 4*64 written): top 128 rows/note of C_in 128, bottom 512 "
+                     "rows/note of C_in 64 + 128; absent when the conv stack is not channels_last"},
+            {"kernel": "imelif_kernel<2048,4,256> (to_audio, inverse front end)", "bound": "hbm",
+             "achieved": MELIF_BYTES_PER_NOTE * B / (inverse_ms * 1e-3) / 1e9, "peak": hbm_peak,
+             "unit": "GB/s", "frac": MELIF_BYTES_PER_NOTE * B / (inverse_ms * 1e-3) / 1e9 / hbm_peak,
+             "ms_per_launch": inverse_ms, "notes": B,
+             "note": "4*2*F*T' read + 4*T written per note; issue/latency bound like the forward kernel"}],
         "kernel_ms_per_step": kernel_ms_per_step,
         "hot_path_only": {"value": world * B * K / (hot_ms * 1e-3), "unit": "notes/s",
                           "ms_per_step": hot_ms / K,

@@ -11,12 +11,15 @@
 //
 // Same skeleton as vq_assign_tc.cu, with the roles of the streamed operand exchanged: the 64
 // output channels are ONE operand tile, and the contraction runs over 64-channel chunks of the
-// inputs, accumulating in the same TMEM columns.  Persistent CTAs, one per SM, 256-row tiles:
-//   warps 0-3  epilogue   tcgen05.ld the 128 x 64 accumulators, add the bias, store rows
-//   warps 4-11 loader     coalesced reads of the NEXT (tile, chunk) into registers while the MMAs
-//                         of the current one run; hi/lo split; st.shared in the UMMA layout
+// inputs, accumulating in the same TMEM columns.  Persistent CTAs, one per SM, 128-row tiles; a
+// "step" is one (tile, chunk) pair and both operands go through 2-stage rings:
+//   warps 0-3  epilogue   tcgen05.ld the 128 x 64 accumulator, add the bias, store rows
+//   warps 4-11 loader     coalesced reads of steps k+1 and k+2 sit in registers while step k is
+//                         split into TF32 hi/lo and stored in the UMMA layout of stage k & 1
 //   warp  12   W producer streams the pre-split, pre-swizzled 64x64 weight chunks (cp.async.bulk)
-//   warp  13   MMA issuer one elected lane; owns TMEM (2 stages x 2 row tiles x 64 columns)
+//   warp  13   MMA issuer one elected lane; owns TMEM (2 accumulator stages x 64 columns)
+// so the global loads, the split and the MMAs of consecutive steps overlap and the kernel runs
+// at the rate of its HBM stream (768 B read + 256 B written per bottom row).
 #include "common.cuh"
 #include "umma.cuh"
 
@@ -25,21 +28,21 @@ namespace isi {
 namespace proj {
 
 constexpr int kRowsPerMma = 128;
-constexpr int kMmaPerTile = 2;
-constexpr int kTileRows = kRowsPerMma * kMmaPerTile;   // 256
+constexpr int kTileRows = kRowsPerMma;                 // 128
 constexpr int kOut = 64;                               // output channels (UMMA N)
 constexpr int kChunk = 64;                             // input channels per contraction chunk
 constexpr int kSlabs = kChunk / 32;
-constexpr int kABytesPart = kSlabs * kRowsPerMma * 128;          // one (m, hi|lo) operand: 32 KB
-constexpr int kABytes = kMmaPerTile * 2 * kABytesPart;            // 128 KB
+constexpr int kABytesPart = kSlabs * kRowsPerMma * 128;          // one hi|lo operand: 32 KB
+constexpr int kAStageBytes = 2 * kABytesPart;                     // 64 KB
+constexpr int kAStages = 2;
 constexpr int kWBytesPart = kSlabs * kOut * 128;                 // one (hi|lo) weight chunk: 16 KB
 constexpr int kWStageBytes = 2 * kWBytesPart;                     // 32 KB
 constexpr int kAccStages = 2;
-constexpr int kTmemCols = kAccStages * kMmaPerTile * kOut;        // 256
+constexpr int kTmemCols = kAccStages * kOut;                      // 128
 constexpr int kFirstLoaderWarp = 4;
 constexpr int kLoaderWarps = 8;
 constexpr int kLoaderThreads = kLoaderWarps * 32;                                   // 256
-constexpr int kChunksPerThread = kTileRows * (kChunk / 4) / kLoaderThreads;         // 16
+constexpr int kChunksPerThread = kTileRows * (kChunk / 4) / kLoaderThreads;         // 8
 constexpr int kProducerWarp = kFirstLoaderWarp + kLoaderWarps;                      // 12
 constexpr int kMmaWarp = kProducerWarp + 1;                                         // 13
 constexpr int kThreads = (kMmaWarp + 1) * 32;                                       // 448
@@ -50,7 +53,7 @@ constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(kOu
 
 struct Smem {
   static constexpr int a = 0;                                   // 1024-aligned operand tiles
-  static constexpr int w = a + kABytes;
+  static constexpr int w = a + kAStages * kAStageBytes;
   static constexpr int bias = w + 2 * kWStageBytes;
   static constexpr int bars = bias + kOut * 4;
   static constexpr int total = bars + 128;
@@ -91,13 +94,17 @@ vq_project_tc_kernel(const float* __restrict__ src0, int chunks0, int64_t stride
   const uint32_t bar_w_empty = s32(bars + 2);    // [2]
   const uint32_t bar_acc_full = s32(bars + 4);   // [2]
   const uint32_t bar_acc_empty = s32(bars + 6);  // [2]
-  const uint32_t bar_a_full = s32(bars + 8);
-  const uint32_t bar_a_empty = s32(bars + 9);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  const uint32_t bar_a_full = s32(bars + 8);     // [2]
+  const uint32_t bar_a_empty = s32(bars + 10);   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_chunks = chunks0 + chunks1;
+  const uint32_t n_chunks = (uint32_t)(chunks0 + chunks1);
   const int64_t n_row_tiles = (n_rows + kTileRows - 1) / kTileRows;
+  // tiles blockIdx.x, blockIdx.x + gridDim.x, ...; step k = (k / n_chunks)-th of them, chunk k % n_chunks
+  const uint32_t my_tiles = (int64_t)blockIdx.x < n_row_tiles
+      ? (uint32_t)((n_row_tiles - 1 - blockIdx.x) / gridDim.x + 1) : 0u;
+  const uint32_t total_steps = my_tiles * n_chunks;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 2; ++i) {
@@ -105,9 +112,9 @@ vq_project_tc_kernel(const float* __restrict__ src0, int chunks0, int64_t stride
       mbar_init(bar_w_empty + 8 * i, 1);
       mbar_init(bar_acc_full + 8 * i, 1);
       mbar_init(bar_acc_empty + 8 * i, 128);
+      mbar_init(bar_a_full + 8 * i, kLoaderThreads);
+      mbar_init(bar_a_empty + 8 * i, 1);
     }
-    mbar_init(bar_a_full, kLoaderThreads);
-    mbar_init(bar_a_empty, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kMmaWarp) {
@@ -123,125 +130,121 @@ vq_project_tc_kernel(const float* __restrict__ src0, int chunks0, int64_t stride
 
   if (warp >= kFirstLoaderWarp && warp < kFirstLoaderWarp + kLoaderWarps) {
     // ===================== input loader / splitter =====================
-    // Thread t owns 16-byte piece c = t % 16 of rows t / 16 + 16 i: the 16 lanes of a row read
-    // its 256 contiguous bytes of the chunk.
+    // Thread t owns 16-byte piece c4 = t % 16 of rows t / 16 + 16 i: the 16 lanes of a row read
+    // its 256 contiguous bytes of the chunk.  Two register buffers: steps k+1 and k+2 are in
+    // flight while step k is split.
     const int t = threadIdx.x - kFirstLoaderWarp * 32;
     const int c4 = t % (kChunk / 4), r0 = t / (kChunk / 4);
-    float4 buf[kChunksPerThread];
-    auto fetch = [&](int64_t tile, int chunk) {
-      const bool first = chunk < chunks0;
+    constexpr int kRowStep = kLoaderThreads / (kChunk / 4);    // 16
+    auto fetch = [&](uint32_t step, float4* buf) {
+      if (step >= total_steps) return;
+      const uint32_t i_tile = step / n_chunks, chunk = step - i_tile * n_chunks;
+      const bool first = chunk < (uint32_t)chunks0;
       const float* base = first ? src0 + chunk * kChunk : src1 + (chunk - chunks0) * kChunk;
       const int64_t stride = first ? stride0 : stride1;
-      const int64_t row0 = tile * kTileRows;
+      const int64_t row0 = ((int64_t)blockIdx.x + (int64_t)i_tile * gridDim.x) * kTileRows;
 #pragma unroll
       for (int i = 0; i < kChunksPerThread; ++i) {
-        const int64_t row = row0 + r0 + i * (kLoaderThreads / (kChunk / 4));
+        const int64_t row = row0 + r0 + i * kRowStep;
         buf[i] = row < n_rows ? __ldg(reinterpret_cast<const float4*>(base + row * stride) + c4)
                               : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    uint32_t step = 0;
-    if ((int64_t)blockIdx.x < n_row_tiles) fetch(blockIdx.x, 0);
-    for (int64_t tile = blockIdx.x; tile < n_row_tiles; tile += gridDim.x) {
-      for (int chunk = 0; chunk < n_chunks; ++chunk, ++step) {
-        mbar_wait(bar_a_empty, (step & 1) ^ 1);            // MMAs of the previous step are done
+    auto split_store = [&](uint32_t step, uint32_t s, const float4* buf) {
+      mbar_wait(bar_a_empty + 8 * s, ((step >> 1) & 1) ^ 1);     // the MMAs of step - 2 are done
+      const uint32_t stage = Smem::a + s * kAStageBytes;
 #pragma unroll
-        for (int i = 0; i < kChunksPerThread; ++i) {
-          const int r = r0 + i * (kLoaderThreads / (kChunk / 4));
-          const float4 v = buf[i];
-          const float4 hi = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
-          const float4 lo = make_float4(to_tf32(v.x - hi.x), to_tf32(v.y - hi.y), to_tf32(v.z - hi.z),
-                                        to_tf32(v.w - hi.w));
-          const int m = r >> 7, rr = r & 127;
-          const uint32_t off = Smem::a + (uint32_t)(m * 2) * kABytesPart + operand_offset(kRowsPerMma, rr, 4 * c4);
-          *reinterpret_cast<float4*>(smem + off) = hi;
-          *reinterpret_cast<float4*>(smem + off + kABytesPart) = lo;
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy
-        mbar_arrive(bar_a_full);
-        if (chunk + 1 < n_chunks) fetch(tile, chunk + 1);
-        else if (tile + gridDim.x < n_row_tiles) fetch(tile + gridDim.x, 0);
+      for (int i = 0; i < kChunksPerThread; ++i) {
+        const int r = r0 + i * kRowStep;
+        const float4 v = buf[i];
+        const float4 hi = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+        const float4 lo = make_float4(to_tf32(v.x - hi.x), to_tf32(v.y - hi.y), to_tf32(v.z - hi.z),
+                                      to_tf32(v.w - hi.w));
+        const uint32_t off = stage + operand_offset(kRowsPerMma, r, 4 * c4);
+        *reinterpret_cast<float4*>(smem + off) = hi;
+        *reinterpret_cast<float4*>(smem + off + kABytesPart) = lo;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy
+      mbar_arrive(bar_a_full + 8 * s);
+    };
+    float4 buf0[kChunksPerThread], buf1[kChunksPerThread];
+    fetch(0, buf0);
+    fetch(1, buf1);
+    for (uint32_t step = 0; step < total_steps; step += 2) {
+      split_store(step, 0, buf0);
+      fetch(step + 2, buf0);
+      if (step + 1 < total_steps) {
+        split_store(step + 1, 1, buf1);
+        fetch(step + 3, buf1);
       }
     }
   } else if (warp == kProducerWarp) {
     // ===================== weight producer =====================
     if (lane == 0) {
-      uint32_t step = 0;
-      for (int64_t tile = blockIdx.x; tile < n_row_tiles; tile += gridDim.x) {
-        for (int chunk = 0; chunk < n_chunks; ++chunk, ++step) {
-          const uint32_t s = step & 1, ph = (step >> 1) & 1;
-          mbar_wait(bar_w_empty + 8 * s, ph ^ 1);
-          mbar_expect_tx(bar_w_full + 8 * s, kWStageBytes);
-          bulk_g2s(smem_base + Smem::w + s * kWStageBytes, w_tiles + (size_t)chunk * kWStageBytes,
-                   kWStageBytes, bar_w_full + 8 * s);
-        }
+      for (uint32_t step = 0; step < total_steps; ++step) {
+        const uint32_t s = step & 1, ph = (step >> 1) & 1, chunk = step % n_chunks;
+        mbar_wait(bar_w_empty + 8 * s, ph ^ 1);
+        mbar_expect_tx(bar_w_full + 8 * s, kWStageBytes);
+        bulk_g2s(smem_base + Smem::w + s * kWStageBytes, w_tiles + (size_t)chunk * kWStageBytes,
+                 kWStageBytes, bar_w_full + 8 * s);
       }
     }
   } else if (warp == kMmaWarp) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      uint32_t step = 0, it = 0;
-      for (int64_t tile = blockIdx.x; tile < n_row_tiles; tile += gridDim.x, ++it) {
-        const uint32_t sa = it & 1;
-        mbar_wait(bar_acc_empty + 8 * sa, ((it >> 1) & 1) ^ 1);   // the epilogue has drained this stage
-        for (int chunk = 0; chunk < n_chunks; ++chunk, ++step) {
-          const uint32_t s = step & 1, ph = (step >> 1) & 1;
-          mbar_wait(bar_a_full, step & 1);
-          mbar_wait(bar_w_full + 8 * s, ph);
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t w_base = smem_base + Smem::w + s * kWStageBytes;
+      for (uint32_t step = 0; step < total_steps; ++step) {
+        const uint32_t s = step & 1, ph = (step >> 1) & 1;
+        const uint32_t it = step / n_chunks, chunk = step - it * n_chunks, sa = it & 1;
+        if (chunk == 0) mbar_wait(bar_acc_empty + 8 * sa, ((it >> 1) & 1) ^ 1);   // epilogue drained it
+        mbar_wait(bar_a_full + 8 * s, ph);
+        mbar_wait(bar_w_full + 8 * s, ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t w_base = smem_base + Smem::w + s * kWStageBytes;
+        const uint32_t a_base = smem_base + Smem::a + s * kAStageBytes;
+        const uint32_t d_tmem = tmem_base + sa * kOut;
+        uint32_t acc = chunk > 0 ? 1u : 0u;
 #pragma unroll
-          for (int m = 0; m < kMmaPerTile; ++m) {
-            const uint32_t d_tmem = tmem_base + (uint32_t)((sa * kMmaPerTile + m) * kOut);
-            const uint32_t a_base = smem_base + Smem::a + (uint32_t)(m * 2) * kABytesPart;
-            uint32_t acc = chunk > 0 ? 1u : 0u;
+        for (int term = 0; term < 3; ++term) {
+          // (f_lo, w_hi), (f_hi, w_lo), (f_hi, w_hi): small terms first
+          const uint32_t a_part = a_base + (term == 0 ? kABytesPart : 0);
+          const uint32_t w_part = w_base + (term == 1 ? kWBytesPart : 0);
 #pragma unroll
-            for (int term = 0; term < 3; ++term) {
-              // (f_lo, w_hi), (f_hi, w_lo), (f_hi, w_hi): small terms first
-              const uint32_t a_part = a_base + (term == 0 ? kABytesPart : 0);
-              const uint32_t w_part = w_base + (term == 1 ? kWBytesPart : 0);
+          for (int slab = 0; slab < kSlabs; ++slab) {
 #pragma unroll
-              for (int slab = 0; slab < kSlabs; ++slab) {
-#pragma unroll
-                for (int kk = 0; kk < 4; ++kk) {
-                  const uint64_t ad = umma_desc(a_part + slab * (kRowsPerMma * 128) + kk * 32);
-                  const uint64_t wd = umma_desc(w_part + slab * (kOut * 128) + kk * 32);
-                  umma_tf32(d_tmem, ad, wd, kIdesc, acc);
-                  acc = 1;
-                }
-              }
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint64_t ad = umma_desc(a_part + slab * (kRowsPerMma * 128) + kk * 32);
+              const uint64_t wd = umma_desc(w_part + slab * (kOut * 128) + kk * 32);
+              umma_tf32(d_tmem, ad, wd, kIdesc, acc);
+              acc = 1;
             }
           }
-          umma_commit(bar_w_empty + 8 * s);       // the weight stage may be refilled
-          umma_commit(bar_a_empty);                // the input chunk may be overwritten
         }
-        umma_commit(bar_acc_full + 8 * sa);        // every chunk has been accumulated
+        umma_commit(bar_w_empty + 8 * s);          // the weight stage may be refilled
+        umma_commit(bar_a_empty + 8 * s);          // the input stage may be overwritten
+        if (chunk + 1 == n_chunks) umma_commit(bar_acc_full + 8 * sa);   // every chunk accumulated
       }
     }
   } else {
     // ===================== epilogue: bias, rows out =====================
-    uint32_t it = 0;
     const uint32_t lane_field = (uint32_t)(warp * 32) << 16;
-    for (int64_t tile = blockIdx.x; tile < n_row_tiles; tile += gridDim.x, ++it) {
+    for (uint32_t it = 0; it < my_tiles; ++it) {
       const uint32_t sa = it & 1;
+      const int64_t tile = (int64_t)blockIdx.x + (int64_t)it * gridDim.x;
       mbar_wait(bar_acc_full + 8 * sa, (it >> 1) & 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      float v[kOut];
+      tmem_ld64(tmem_base + lane_field + sa * kOut, v);
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(bar_acc_empty + 8 * sa);                 // the values are in registers
+      const int64_t row = tile * kTileRows + warp * 32 + lane;
+      if (row < n_rows) {
+        float4* dst = reinterpret_cast<float4*>(out + row * kOut);
 #pragma unroll
-      for (int m = 0; m < kMmaPerTile; ++m) {
-        float v[kOut];
-        tmem_ld64(tmem_base + lane_field + (uint32_t)((sa * kMmaPerTile + m) * kOut), v);
-        const int64_t row = tile * kTileRows + m * kRowsPerMma + warp * 32 + lane;
-        if (row < n_rows) {
-          float4* dst = reinterpret_cast<float4*>(out + row * kOut);
-#pragma unroll
-          for (int c = 0; c < kOut; c += 4) {
-            const float4 b = *reinterpret_cast<const float4*>(bias + c);
-            dst[c >> 2] = make_float4(v[c] + b.x, v[c + 1] + b.y, v[c + 2] + b.z, v[c + 3] + b.w);
-          }
+        for (int c = 0; c < kOut; c += 4) {
+          const float4 b = *reinterpret_cast<const float4*>(bias + c);
+          dst[c >> 2] = make_float4(v[c] + b.x, v[c + 1] + b.y, v[c + 2] + b.z, v[c + 3] + b.w);
         }
       }
-      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-      mbar_arrive(bar_acc_empty + 8 * sa);
     }
   }
 

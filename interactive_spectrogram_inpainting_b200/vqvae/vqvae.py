@@ -101,7 +101,7 @@ class PointwiseProjection:
     ``min_rows`` rows); ``usable`` says whether a call qualifies -- callers keep the stock modules
     otherwise."""
 
-    min_rows = 1024
+    min_rows = 128
 
     def __init__(self, conv: nn.Conv2d):
         self.conv = conv
