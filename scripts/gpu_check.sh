@@ -86,6 +86,15 @@ for s in $steps; do
     projection)
       timeout 240 python -m pytest tests/test_gpu_projection.py -x -q -s 2>&1 | tail -30 > gpurun_out/pytest_projection_$tag.log
       tail -12 gpurun_out/pytest_projection_$tag.log ;;
+    ncu_project)
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:vq_project_tc -s 5 -c 1 \
+        -o gpurun_out/project_$tag python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_project_$tag.log 2>&1
+      tail -1 gpurun_out/ncu_project_$tag.log | cut -c1-200 ;;
+    projection_sanitize)
+      for tool in memcheck racecheck; do
+        timeout 600 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_smoke.py projection > gpurun_out/sanitize_${tool}_projection_$tag.log 2>&1
+        echo "$tool projection rc=$? $(grep -c "=========     at\|========= Error\|========= Warning\|hazard" gpurun_out/sanitize_${tool}_projection_$tag.log) findings; $(grep "ERROR SUMMARY\|RACECHECK SUMMARY" gpurun_out/sanitize_${tool}_projection_$tag.log | tail -1)"
+      done ;;
     smoke)
       timeout 300 python __graft_entry__.py smoke 2>&1 | tail -2 ;;
     probe)

@@ -40,6 +40,21 @@ if which in ("all", "inverse"):
     torch.cuda.synchronize()
     print("inverse ok")
 
+if which in ("all", "projection"):
+    from interactive_spectrogram_inpainting_b200.vqvae.vqvae import PointwiseProjection
+    torch.manual_seed(0)
+    for c0, c1, shape in ((128, 0, (3, 32, 4)), (64, 128, (5, 37, 11)), (192, 64, (2, 150, 9))):
+        conv = torch.nn.Conv2d(c0 + c1, 64, 1).to(dev)
+        srcs = [torch.randn(shape[0], c, *shape[1:], device=dev).contiguous(memory_format=torch.channels_last)
+                for c in (c0, c1) if c]
+        proj = PointwiseProjection(conv)
+        proj.min_rows = 1
+        with torch.no_grad():
+            assert proj.usable(srcs)
+            proj(srcs)
+    torch.cuda.synchronize()
+    print("projection ok")
+
 if which in ("all", "quantizer"):
     embed = synthetic.synthetic_codebook(64, 512)
     for algo, rows, k in (("simt", 700, 512), ("tcgen05", 5000, 512), ("tcgen05_pair", 5000, 512),
