@@ -95,7 +95,7 @@ __host__ __device__ inline MelifSmem melif_smem_layout(int hop, int sample_bytes
 }
 
 template <int NFFT, int FB, int NT, bool MEL, typename S>
-__global__ void __launch_bounds__(NT, 3)
+__global__ void __launch_bounds__(NT, NT >= 512 ? 2 : 3)
 melif_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params p,
              float* __restrict__ out, int bulk_ok, int seg_frames, int n_segs) {
   using P = Plan<NFFT>;
@@ -306,10 +306,10 @@ melif_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params p,
 
 // Frames per CTA: whole notes when the batch fills the GPU on its own, else the split that
 // maximises (wave efficiency) x (useful / useful + look-back work).
-static void choose_segments(int64_t n_notes, int n_frames, int fb, int* seg_frames, int* n_segs) {
+static void choose_segments(int64_t n_notes, int n_frames, int fb, int ctas_per_sm, int* seg_frames, int* n_segs) {
   const int frames_padded = (n_frames + fb - 1) / fb * fb;
   const int max_segs = frames_padded / (4 * fb) > 1 ? frames_padded / (4 * fb) : 1;
-  const double slots = 3.0 * kNumSms;   // __launch_bounds__(NT, 3)
+  const double slots = 3.0 * kNumSms;   // __launch_bounds__(NT, NT >= 512 ? 2 : 3)
   double best = -1.0;
   *seg_frames = frames_padded; *n_segs = 1;
   for (int s = 1; s <= max_segs; ++s) {
@@ -335,7 +335,7 @@ static int launch_melif_t(const S* audio, int64_t n_notes, int64_t n_samples,
   const int bulk_ok = (n_samples % kPer16 == 0) && (p.hop % kPer16 == 0) &&
                       (p.pad_left % kPer16 == 0) && ((uintptr_t)audio % 16 == 0);
   int seg_frames, n_segs;
-  choose_segments(n_notes, p.n_frames, FB, &seg_frames, &n_segs);
+  choose_segments(n_notes, p.n_frames, FB, NT >= 512 ? 2 : 3, &seg_frames, &n_segs);
   if (n_notes * n_segs > 0x7fffffff) return ISI_ERR_SHAPE;
   melif_kernel<NFFT, FB, NT, MEL, S><<<(unsigned)(n_notes * n_segs), NT, L.total, stream>>>(
       audio, n_samples, p, out, bulk_ok, seg_frames, n_segs);
@@ -351,7 +351,7 @@ static int launch_melif_s(const S* audio, int64_t n_notes, int64_t n_samples,
     return p.use_mel ? launch_melif_t<N, FB, NT, true, S>(audio, n_notes, n_samples, p, out, stream) \
                      : launch_melif_t<N, FB, NT, false, S>(audio, n_notes, n_samples, p, out, stream);
   switch (p.n_fft) {
-    ISI_MELIF_CASE(2048, 4, 256)
+    ISI_MELIF_CASE(2048, 8, 512)
     ISI_MELIF_CASE(1024, 4, 128)
     ISI_MELIF_CASE(512, 4, 64)
     default: return ISI_ERR_UNSUPPORTED;

@@ -102,7 +102,7 @@ extern "C" int melif_emulate(const float* audio, int64_t n_notes, int64_t n_samp
   if (seg_frames <= 0) seg_frames = (n_frames + 3) / 4 * 4;
 #define CASE(N, FB, NT) case N: if (use_mel) emulate<N, FB, NT, true>(ARGS); else emulate<N, FB, NT, false>(ARGS); return 0;
   switch (n_fft) {
-    CASE(2048, 4, 256)
+    CASE(2048, 8, 512)
     CASE(1024, 4, 128)
     CASE(512, 4, 64)
     default: return -3;
