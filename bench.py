@@ -437,10 +437,10 @@ def b200_arm(args):
                      "peak": hbm_peak, "unit": "GB/s", "frac": melif_gbs / hbm_peak,
                      # dram__bytes_read + dram__bytes_write of one 444-note launch from the
                      # committed ncu captures of this kernel (channels_last output), scaled to
-                     # this batch: profiles/r01_melif_v6_pcm16_r02j_ncu_summary.csv (57.4 +
-                     # 414.8 MB) and profiles/r01_melif_v6_r02b_ncu_summary.csv (114.3 + 413.8 MB);
+                     # this batch: profiles/r01_melif_v8_512t_r05a_ncu_summary.csv (57.1 +
+                     # 413.6 MB) and profiles/r01_melif_v6_r02b_ncu_summary.csv (114.3 + 413.8 MB);
                      # ~50 MB of the last notes' output is still dirty in L2 when the kernel ends
-                     "traffic": ((57.426944e6 + 414.775296e6) if args.audio == "pcm16"
+                     "traffic": ((57.059840e6 + 413.562624e6) if args.audio == "pcm16"
                                  else (114.308608e6 + 413.754112e6)) / 444 * B if cl else None,
                      "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
                      "ms_per_launch": melif_ms, "algorithmic_bytes_per_launch": melif_bytes_per_note * B,
@@ -453,8 +453,8 @@ def b200_arm(args):
                          "achieved_ginst_per_s": per_note * B / (melif_ms * 1e-3) / 1e9,
                          "peak_ginst_per_s": 148 * 4 * mhz * 1e6 / 1e9,
                          "frac": per_note * B / (melif_ms * 1e-3) / (148 * 4 * mhz * 1e6),
-                         "source": "profiles/r01_melif_v7_s2d_pcm16_r03a_ncu_summary.csv"})(
-                             272791380 / 444 if args.audio == "pcm16" else 260017056 / 444,
+                         "source": "profiles/r01_melif_v8_512t_r05a_ncu_summary.csv"})(
+                             264092532 / 444 if args.audio == "pcm16" else 260017056 / 444,
                              clk["sm_mhz"] or 1965.0)},
         "rooflines_other": [
             {"kernel": f"vq_assign ({args.assign_algo})", "bound": "tensor",

@@ -309,7 +309,7 @@ melif_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params p,
 static void choose_segments(int64_t n_notes, int n_frames, int fb, int ctas_per_sm, int* seg_frames, int* n_segs) {
   const int frames_padded = (n_frames + fb - 1) / fb * fb;
   const int max_segs = frames_padded / (4 * fb) > 1 ? frames_padded / (4 * fb) : 1;
-  const double slots = 3.0 * kNumSms;   // __launch_bounds__(NT, NT >= 512 ? 2 : 3)
+  const double slots = (double)ctas_per_sm * kNumSms;   // resident CTAs: __launch_bounds__(NT, ctas_per_sm)
   double best = -1.0;
   *seg_frames = frames_padded; *n_segs = 1;
   for (int s = 1; s <= max_segs; ++s) {
