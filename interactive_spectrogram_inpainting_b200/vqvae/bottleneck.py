@@ -17,6 +17,8 @@ There is no CPU path: CPU tensors raise.
 import math
 from typing import List, Optional, Tuple
 
+import threading
+
 import torch
 from torch import nn
 
@@ -30,10 +32,15 @@ class _CodebookCache:
     def __init__(self):
         self.buffer = None
         self.key = None
+        self._lock = threading.Lock()     # request threads of the Flask server share the module
 
     def get(self, embed: torch.Tensor) -> torch.Tensor:
         key = (embed.data_ptr(), embed._version, embed.device, tuple(embed.shape))
-        if self.buffer is None or self.key != key:
+        if self.buffer is not None and self.key == key:
+            return self.buffer
+        with self._lock:
+            if self.buffer is not None and self.key == key:
+                return self.buffer
             lib = _lib.load()
             dim, n_embed = embed.shape
             nbytes = lib.isi_vq_prepared_bytes(dim, n_embed)
@@ -41,11 +48,11 @@ class _CodebookCache:
                     or self.buffer.device != embed.device):
                 self.buffer = torch.empty(nbytes, dtype=torch.uint8, device=embed.device)
             src = embed if embed.is_contiguous() else embed.contiguous()
-            _lib.invoke("isi_vq_prepare_codebook", 
-                src.data_ptr(), dim, n_embed, self.buffer.data_ptr(), self.buffer.numel(),
-                _lib.stream_ptr(embed.device))
+            _lib.invoke("isi_vq_prepare_codebook",
+                        src.data_ptr(), dim, n_embed, self.buffer.data_ptr(), self.buffer.numel(),
+                        _lib.stream_ptr(embed.device))
             self.key = key
-        return self.buffer
+            return self.buffer
 
     def invalidate(self):
         self.key = None

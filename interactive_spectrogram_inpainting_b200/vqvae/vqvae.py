@@ -14,6 +14,7 @@ the GANSynth data normaliser (all external to the reference tree) are not covere
 import json
 import math
 import pathlib
+import threading
 from typing import Mapping, Optional, Sequence, Type, Union
 
 import torch
@@ -108,6 +109,7 @@ class PointwiseProjection:
         self._key = None
         self._prepared = None
         self._bias = None
+        self._lock = threading.Lock()
 
     def usable(self, sources) -> bool:
         conv = self.conv
@@ -132,29 +134,39 @@ class PointwiseProjection:
         key = (w._version, w.data_ptr(), None if b is None else (b._version, b.data_ptr()),
                None if folded_bias is None else (folded_bias._version, folded_bias.data_ptr()), c0)
         if key == self._key:
-            return
+            return self._prepared, self._bias
+        with self._lock:
+            return self._prepare_locked(key, c0, folded_bias)
+
+    def _prepare_locked(self, key, c0: int, folded_bias):
+        if key == self._key:
+            return self._prepared, self._bias
+        conv = self.conv
+        w, b = conv.weight, conv.bias
         c_in = conv.in_channels
         w2 = w.detach().reshape(64, c_in).contiguous()
         nbytes = _lib.load().isi_vq_project_prepared_bytes(c_in)
-        self._prepared = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
-        _lib.invoke("isi_vq_project_prepare", w2.data_ptr(), c_in, 64, self._prepared.data_ptr(), nbytes,
+        prepared = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+        _lib.invoke("isi_vq_project_prepare", w2.data_ptr(), c_in, 64, prepared.data_ptr(), nbytes,
                     _lib.stream_ptr(w.device))
         bias = torch.zeros(64, device=w.device) if b is None else b.detach().clone()
         if folded_bias is not None:
             bias = bias + (w2[:, :c0].double() @ folded_bias.detach().double()).float()
-        self._bias = bias.contiguous()
+        # fresh tensors per weight version: a concurrent caller keeps using the pair it was handed
+        self._prepared, self._bias = prepared, bias.contiguous()
         self._key = key
+        return self._prepared, self._bias
 
     def __call__(self, sources, folded_bias=None) -> torch.Tensor:
         x0 = sources[0]
         x1 = sources[1] if len(sources) > 1 else None
-        self._prepare(x0.shape[1], folded_bias)
+        prepared, bias = self._prepare(x0.shape[1], folded_bias)
         b, _, h, w = x0.shape
         out = torch.empty(b, h, w, 64, dtype=torch.float32, device=x0.device)
         _lib.invoke("isi_vq_project", x0.data_ptr(), x0.shape[1], _as_rows(x0),
                     None if x1 is None else x1.data_ptr(), 0 if x1 is None else x1.shape[1],
-                    0 if x1 is None else _as_rows(x1), b * h * w, 64, self._prepared.data_ptr(),
-                    self._bias.data_ptr(), out.data_ptr(), _lib.stream_ptr(x0.device))
+                    0 if x1 is None else _as_rows(x1), b * h * w, 64, prepared.data_ptr(),
+                    bias.data_ptr(), out.data_ptr(), _lib.stream_ptr(x0.device))
         return out
 
 
