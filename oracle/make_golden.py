@@ -97,6 +97,18 @@ def frontend_fixture():
                         mel=mel[:, :, ::8, ::4].numpy(), lin=lin[:, :, ::8, ::4].numpy())
 
 
+def inverse_fixture():
+    """strided sample of the restated inverse (to_audio) of a seeded random mel / linear
+    spectrogram: 24 frames -> 10 752 samples."""
+    g = torch.Generator().manual_seed(20200117)
+    spec = torch.stack([torch.randn(2, 1024, 24, generator=g) * 2.0 - 3.0,
+                        torch.rand(2, 1024, 24, generator=g) * 2.0 - 1.0], 1)
+    mel = frontend_oracle.to_audio(spec.double(), frontend_oracle.FrontEndConfig())
+    lin = frontend_oracle.to_audio(spec.double(), frontend_oracle.FrontEndConfig(use_mel_scale=False))
+    np.savez_compressed(GOLDEN / "inverse_unpinned.npz", spec_corner=spec[:, :, :8, :8].numpy(),
+                        mel=mel[:, ::7].float().numpy(), lin=lin[:, ::7].float().numpy())
+
+
 def main():
     GOLDEN.mkdir(parents=True, exist_ok=True)
     torch.set_num_threads(1)             # fixed reduction order for the fixtures
@@ -104,6 +116,7 @@ def main():
     quantizer_train_fixture()
     quantizer_edge_fixture()
     frontend_fixture()
+    inverse_fixture()
     for p in sorted(GOLDEN.glob("*.npz")):
         print(p.name, p.stat().st_size)
 

@@ -55,3 +55,38 @@ def test_unwrap_matches_numpy():
     ph = (torch.rand(5, 40, generator=g, dtype=torch.float64) * 2 - 1) * math.pi
     np.testing.assert_allclose(fo.unwrap_time(ph).numpy(), np.unwrap(ph.numpy(), axis=-1),
                                atol=1e-12)
+
+
+def test_inverse_regression_fixture(golden_dir):
+    """``to_audio`` restatement (unpinned like the forward transform) against its fixture."""
+    g = np.load(golden_dir / "inverse_unpinned.npz")
+    gen = torch.Generator().manual_seed(20200117)
+    spec = torch.stack([torch.randn(2, 1024, 24, generator=gen) * 2.0 - 3.0,
+                        torch.rand(2, 1024, 24, generator=gen) * 2.0 - 1.0], 1)
+    np.testing.assert_array_equal(spec[:, :, :8, :8].numpy(), g["spec_corner"])
+    for mel, key in ((True, "mel"), (False, "lin")):
+        got = fo.to_audio(spec.double(), fo.FrontEndConfig(use_mel_scale=mel))[:, ::7].numpy()
+        assert got.shape == g[key].shape == (2, 1536)
+        assert np.abs(got - g[key]).max() <= 1e-5 * np.abs(g[key]).max()
+
+
+def test_inverse_of_forward_is_the_audio():
+    """Linear scale: forward then inverse returns the note up to the eps of log(|X| + eps) and
+    the dropped DC bin; the padded frames make every kept sample fully overlapped."""
+    cfg = fo.FrontEndConfig(use_mel_scale=False)
+    audio = synthetic.synthetic_notes(1).double()
+    back = fo.to_audio(fo.to_spectrogram(audio, cfg), cfg)
+    assert back.shape == audio.shape
+    assert (back - audio).abs().max() < 5e-3
+
+
+def test_mel_to_linear_matrix_undoes_the_filterbank_on_smooth_spectra():
+    cfg = fo.FrontEndConfig()
+    fwd, back = fo.linear_to_mel_matrix(cfg), fo.mel_to_linear_matrix(cfg)
+    assert back.shape == (1024, 1024) and (back >= 0).all()
+    flat = np.ones(1024)
+    flat[0] = 0.0                                              # the zeroed first linear row
+    rebuilt = (flat @ fwd) @ back                              # linear -> mel -> linear
+    # the column normalisation makes a flat spectrum come back exactly; the top bin sits on the
+    # upper band edge (8000 Hz = Nyquist) and receives no weight at all
+    assert np.abs(rebuilt[1:-1] - 1.0).max() < 1e-12 and rebuilt[-1] == 0.0 and rebuilt[0] == 0.0
