@@ -131,3 +131,15 @@ def test_decode_graph_continues_into_the_inverse_front_end():
         assert torch.allclose(spec, want_spec, rtol=1e-3, atol=1e-4)
         assert audio.shape == (2, 64000) and torch.isfinite(audio).all()
         assert torch.equal(audio, helper.to_audio(spec))      # same launch shape: bit-identical
+
+
+def test_committed_golden_vectors(golden_dir):
+    """tests/golden/inverse_unpinned.npz (oracle/make_golden.py::inverse_fixture)."""
+    import numpy as np
+    g = np.load(golden_dir / "inverse_unpinned.npz")
+    gen = torch.Generator().manual_seed(20200117)
+    spec = torch.stack([torch.randn(2, 1024, 24, generator=gen) * 2.0 - 3.0,
+                        torch.rand(2, 1024, 24, generator=gen) * 2.0 - 1.0], 1)
+    for mel, key in ((True, "mel"), (False, "lin")):
+        got = _helper(mel).to_audio(spec.to(DEV))[:, ::7].cpu().numpy()
+        assert np.abs(got - g[key]).max() <= 1e-4 * np.abs(g[key]).max()

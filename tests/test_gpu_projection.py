@@ -94,3 +94,29 @@ def test_encode_codes_with_and_without_the_projection_kernel():
     agree_b = (ref_b == id_b).float().mean().item()
     print(f"[projection] codes equal to the stock-module path: top {agree_t:.5f}, bottom {agree_b:.5f}")
     assert agree_t > 0.999 and agree_b > 0.995
+
+
+@pytest.mark.parametrize("factors", [{"bottom": 8, "top": 4}, {"bottom": 4, "top": 2}])
+def test_other_resolution_configs_use_the_kernel(factors):
+    """The in-tree configurations besides the deployed one: larger code maps,
+    same 128 / 64 + 128 channel projections."""
+    torch.manual_seed(0)
+    model = vq.VQVAE(in_channel=2, resolution_factors=factors,
+                     adapt_quantized_durations=False).to(DEV).eval().to(memory_format=torch.channels_last)
+    g = torch.Generator().manual_seed(3)
+    spec = torch.randn(8, 2, 256, 64, generator=g).to(DEV).contiguous(memory_format=torch.channels_last)
+    tf32, torch.backends.cudnn.allow_tf32 = torch.backends.cudnn.allow_tf32, False
+    try:
+        with torch.no_grad():
+            calls = vq._lib.launch_counts["isi_vq_project"]
+            id_t, id_b = model.encode_codes(spec)
+            assert vq._lib.launch_counts["isi_vq_project"] == calls + 2
+            vq.fused_inference = False
+            try:
+                ref_t, ref_b = model.encode_codes(spec)
+            finally:
+                vq.fused_inference = True
+    finally:
+        torch.backends.cudnn.allow_tf32 = tf32
+    assert id_t.shape == ref_t.shape and id_b.shape == ref_b.shape
+    assert (ref_t == id_t).float().mean() > 0.995 and (ref_b == id_b).float().mean() > 0.995
