@@ -278,9 +278,11 @@ def b200_arm(args):
 
     e2e_stamps = []
 
+    extractor = extract.CodeExtractor(helper, model, dev, cuda_graph=bool(args.e2e_cuda_graph))
+
     def e2e_run(n_batches, host):
-        loader = extract.SpectrogramBatches([(host, names)] * n_batches, helper, dev)
-        return extract.extract_codes(loader, model, sink=lambda rows: e2e_stamps.append(time.perf_counter()))
+        return extractor.run([(host, names)] * n_batches,
+                             sink=lambda rows: e2e_stamps.append(time.perf_counter()))
 
     def e2e_measure(host):
         e2e_run(W, host)
@@ -424,7 +426,9 @@ def b200_arm(args):
                 "h2d_bytes_per_step": host_audio.numel() * host_audio.element_size(),
                 "audio": args.audio,
                 "d2h_bytes_per_step": (host_codes[0].numel() + host_codes[1].numel()) * 8,
-                "api": "extract.extract_codes(extract.SpectrogramBatches(pinned host audio))",
+                "api": "extract.CodeExtractor(helper, model, device).run(pinned host audio batches)",
+                "cuda_graph": bool(args.e2e_cuda_graph) and not extractor.graph_failures,
+                "cuda_graph_failures": extractor.graph_failures[:2],
                 "ms_per_step": e2e_ms / K,
                 "host_ms_between_batches": {"median": statistics.median(e2e_gaps), "max": max(e2e_gaps)},
                 "other_audio_format": {"audio": other, "value": world * B * K / (other_ms * 1e-3),
@@ -521,6 +525,9 @@ def main():
                     help="sample format of the input notes: int16 PCM as the dataset stores them "
                          "(converted in the front-end kernel) or float32 as the reference uploads them")
     ap.add_argument("--cudnn-benchmark", type=int, default=1)
+    ap.add_argument("--e2e-cuda-graph", type=int, default=1,
+                    help="1: the e2e leg replays front end + encode from one CUDA graph per batch "
+                         "(extract.CodeExtractor); 0: the same calls eagerly")
     ap.add_argument("--space-to-depth", type=int, default=1,
                     help="front end writes 2x2 space-to-depth blocks; the first conv runs as 3x3 stride 1")
     ap.add_argument("--channels-last", type=int, default=1,

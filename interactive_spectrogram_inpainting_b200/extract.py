@@ -135,6 +135,141 @@ def extract_codes(loader: Iterable[Tuple[torch.Tensor, Sequence[str]]], model,
     return rows
 
 
+class _GraphedStep:
+    """Front end + ``encode_codes`` for one batch shape, captured in a CUDA graph: a step is ~30
+    kernel launches through Python and ctypes; replaying them costs the host one call, which is
+    what matters when eight ranks share a host's cores.  The graph holds the addresses of the
+    prepared codebooks and projection weights: eval mode, weights that no longer change."""
+
+    def __init__(self, helper, model, example: torch.Tensor, space_to_depth: bool, warmup: int = 3):
+        device = example.device
+        self.audio = torch.empty_like(example)
+        self.audio.copy_(example)
+
+        def run():
+            spec = helper.to_spectrogram(self.audio)
+            return model.encode_codes(spec, space_to_depth=True) if space_to_depth else model.encode_codes(spec)
+        stream = torch.cuda.Stream(device)
+        stream.wait_stream(torch.cuda.current_stream(device))
+        with torch.no_grad(), torch.cuda.stream(stream):
+            for _ in range(max(1, warmup)):      # cuDNN plan selection and cache fills stay outside
+                run()
+        torch.cuda.current_stream(device).wait_stream(stream)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.id_t, self.id_b = run()
+
+    def __call__(self, audio: torch.Tensor):
+        self.audio.copy_(audio, non_blocking=True)
+        self.graph.replay()
+        return self.id_t, self.id_b
+
+
+class CodeExtractor:
+    """``extract_code.py:62-79`` from audio batches to ``CodeRow``s as one pipeline:
+
+        pinned host audio --H2D (side stream, one batch ahead)--> front end + encode_codes
+        (one CUDA-graph replay per batch when ``cuda_graph``) --D2H--> rows
+
+    ``run(source)`` takes what ``SpectrogramBatches`` takes: an iterable of ``(audio [b, T],
+    names)``.  Graphs are captured per batch shape on first use and kept for later calls; a
+    shape whose capture fails (or ``cuda_graph=False``) runs the same calls eagerly.  The model
+    must be this repo's ``VQVAE`` in eval mode with fixed weights."""
+
+    def __init__(self, spectrograms_helper, model, device: torch.device, cuda_graph: bool = True):
+        if not hasattr(model, "encode_codes"):
+            raise TypeError("CodeExtractor needs this repo's VQVAE (encode_codes)")
+        self.helper, self.model, self.device = spectrograms_helper, model.eval(), device
+        self.cuda_graph = cuda_graph
+        self.space_to_depth = bool(getattr(spectrograms_helper, "space_to_depth", False))
+        self._graphs = {}
+        self._side = torch.cuda.Stream(device)
+        self._dev_audio = [None, None]
+        self._host_codes = [None, None]
+        self.graph_failures: List[str] = []
+
+    def _step(self, audio: torch.Tensor):
+        key = (tuple(audio.shape), audio.dtype)
+        graphed = self._graphs.get(key)
+        if graphed is None and self.cuda_graph:
+            try:
+                graphed = _GraphedStep(self.helper, self.model, audio, self.space_to_depth)
+            except Exception as exc:       # capture is an optimisation: the eager calls are the same work
+                self.graph_failures.append(f"{key}: {exc}")
+                graphed = False
+            self._graphs[key] = graphed
+        if graphed:
+            return graphed(audio)
+        spec = self.helper.to_spectrogram(audio)
+        return (self.model.encode_codes(spec, space_to_depth=True) if self.space_to_depth
+                else self.model.encode_codes(spec))
+
+    @torch.no_grad()
+    def run(self, source: Iterable[Tuple[torch.Tensor, Sequence[str]]],
+            sink: Optional[Callable[[List[CodeRow]], None]] = None) -> List[CodeRow]:
+        main, side = torch.cuda.current_stream(self.device), self._side
+        consumed = [None, None]          # per slot: the step that read the device copy is enqueued
+        rows: List[CodeRow] = []
+
+        def upload(item, slot):
+            audio, names = item
+            buf = self._dev_audio[slot]
+            if buf is None or buf.shape != audio.shape or buf.dtype != audio.dtype:
+                buf = torch.empty(audio.shape, dtype=audio.dtype, device=self.device)
+                self._dev_audio[slot] = buf
+            with torch.cuda.stream(side):
+                if consumed[slot] is not None:
+                    side.wait_event(consumed[slot])
+                buf.copy_(audio, non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(side)
+            return buf, list(names), ready
+
+        def host_pair(slot, id_t, id_b):
+            pair = self._host_codes[slot]
+            if pair is None or pair[0].shape != id_t.shape or pair[1].shape != id_b.shape:
+                pair = (torch.empty(id_t.shape, dtype=id_t.dtype, pin_memory=True),
+                        torch.empty(id_b.shape, dtype=id_b.dtype, pin_memory=True))
+                self._host_codes[slot] = pair
+            return pair
+
+        def flush(item):
+            host_t, host_b, names, done = item
+            done.synchronize()
+            tops, bottoms = host_t.numpy().copy(), host_b.numpy().copy()
+            batch_rows = [CodeRow(top=t, bottom=b, attributes={}, filename=n)
+                          for t, b, n in zip(tops, bottoms, names)]
+            if sink is not None:
+                sink(batch_rows)
+            rows.extend(batch_rows)
+
+        it = iter(source)
+        first = next(it, None)
+        uploaded = upload(first, 0) if first is not None else None
+        pending, step = None, 0
+        while uploaded is not None:
+            audio, names, ready = uploaded
+            slot = step % 2
+            nxt = next(it, None)
+            uploaded = upload(nxt, 1 - slot) if nxt is not None else None
+            main.wait_event(ready)
+            id_t, id_b = self._step(audio)
+            consumed[slot] = torch.cuda.Event()
+            consumed[slot].record(main)
+            host_t, host_b = host_pair(slot, id_t, id_b)
+            host_t.copy_(id_t, non_blocking=True)
+            host_b.copy_(id_b, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record(main)
+            if pending is not None:      # the previous batch's copy overlaps this batch's compute
+                flush(pending)
+            pending = (host_t, host_b, names, done)
+            step += 1
+        if pending is not None:
+            flush(pending)
+        return rows
+
+
 def save_shard(rows: Sequence[CodeRow], path) -> None:
     """One ``.npz`` per rank: names, top and bottom code maps (idempotent per note name,
     like the reference's ``dupsort=False`` LMDB keys, extract_code.py:47-50)."""

@@ -106,3 +106,35 @@ def test_space_to_depth_extraction_gives_the_same_codes(fp32_convs):
         blocks = MelSpectrogramsHelper(space_to_depth=True).to(DEV).to_spectrogram(audio.to(DEV))
         torch.testing.assert_close(model.enc_b(blocks, space_to_depth=True), model.enc_b(spec),
                                    rtol=1e-4, atol=1e-5)
+
+
+def test_code_extractor_graph_replay_equals_the_eager_pipeline():
+    """``CodeExtractor`` (H2D one batch ahead, one CUDA-graph replay per batch, D2H) returns the
+    rows of ``extract_codes`` over ``SpectrogramBatches``: same kernels, same order."""
+    from interactive_spectrogram_inpainting_b200 import extract
+    from interactive_spectrogram_inpainting_b200.utils.spectrograms_helper import MelSpectrogramsHelper
+    torch.manual_seed(7)
+    dev = torch.device(DEV)
+    model = (vq.VQVAE(in_channel=2, resolution_factors={"bottom": 16, "top": 2}, adapt_quantized_durations=False)
+             .to(dev).eval().to(memory_format=torch.channels_last))
+    helper = MelSpectrogramsHelper(space_to_depth=True).to(dev)
+    pcm = (synthetic.synthetic_notes(14) * 32767).round().to(torch.int16)
+    batches = [(pcm[0:4].pin_memory(), [f"n{i}" for i in range(0, 4)]),
+               (pcm[4:8].pin_memory(), [f"n{i}" for i in range(4, 8)]),
+               (pcm[8:12].pin_memory(), [f"n{i}" for i in range(8, 12)]),
+               (pcm[12:14].pin_memory(), [f"n{i}" for i in range(12, 14)])]      # ragged last batch
+    want = extract.extract_codes(extract.SpectrogramBatches(batches, helper, dev), model)
+    graphed = extract.CodeExtractor(helper, model, dev, cuda_graph=True)
+    eager = extract.CodeExtractor(helper, model, dev, cuda_graph=False)
+    streamed = []
+    for run in range(2):                                     # second run replays the cached graphs
+        got = graphed.run(batches, sink=streamed.extend)
+        assert graphed.graph_failures == [], graphed.graph_failures
+        assert [r.filename for r in got] == [r.filename for r in want]
+        for g, w in zip(got, want):
+            assert (g.top == w.top).all() and (g.bottom == w.bottom).all()
+    assert len(streamed) == 2 * len(want)
+    assert len(graphed._graphs) == 2 and all(graphed._graphs.values())     # one graph per batch shape
+    for g, w in zip(eager.run(batches), want):
+        assert (g.top == w.top).all() and (g.bottom == w.bottom).all()
+    assert graphed.run([]) == []
