@@ -156,7 +156,9 @@ class _GraphedStep:
                 run()
         torch.cuda.current_stream(device).wait_stream(stream)
         self.graph = torch.cuda.CUDAGraph()
-        with torch.no_grad(), torch.cuda.graph(self.graph):
+        # thread_local: other threads of the process (NCCL watchdog, loader workers) may call the
+        # CUDA runtime while this thread captures
+        with torch.no_grad(), torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
             self.id_t, self.id_b = run()
 
     def __call__(self, audio: torch.Tensor):

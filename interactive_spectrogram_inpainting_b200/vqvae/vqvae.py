@@ -456,7 +456,8 @@ class GraphedDecodeCode:
                 run()
         torch.cuda.current_stream(code_t.device).wait_stream(stream)
         self._graph = torch.cuda.CUDAGraph()
-        with torch.no_grad(), torch.cuda.graph(self._graph):
+        # thread_local: the server's other request threads keep using the CUDA runtime meanwhile
+        with torch.no_grad(), torch.cuda.graph(self._graph, capture_error_mode="thread_local"):
             self._out = run()
 
     def __call__(self, code_t: torch.Tensor, code_b: torch.Tensor):
