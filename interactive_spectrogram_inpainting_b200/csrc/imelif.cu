@@ -133,8 +133,10 @@ imelif_kernel(const float* __restrict__ spec, isi_imelif_params p, float* __rest
   if (fstart > 0) {
     // running phase before frame fstart: FP64 prefix sums of channel 1, projected per row
     double* sums = reinterpret_cast<double*>(zA);
-    for (int m = tid; m < M; m += NT)
-      sums[m] = lookback_row_sum(note1 + (int64_t)m * p.n_frames, fstart, p.in_scale[1], p.in_bias[1], vec_in != 0);
+    double row_sum[RPT];
+    lookback_rows_sum<RPT>(note1, p.n_frames, tid, NT, fstart, p.in_scale[1], p.in_bias[1], vec_in != 0, row_sum);
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) sums[tid + r * NT] = row_sum[r];
     __syncthreads();
 #pragma unroll
     for (int r = 0; r < RPT; ++r) phase[r] = lookback_phase<MEL>(sums, band_start[r], band_count[r], band_w[r]);

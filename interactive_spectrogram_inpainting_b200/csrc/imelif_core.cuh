@@ -134,19 +134,46 @@ ISI_HD void build_row(const float* slab, int M, int start, int count, int count_
 // ---- look-back (a segment that does not start at frame 0): the running phase before frame
 //      `f_end` is the projection of sum_{t < f_end} of channel 1; sums and projection in FP64
 //      (the sum reaches ~100 half-turns, where FP32 resolves 1e-5), folded, then FP32. ----
-ISI_HD double lookback_row_sum(const float* row /* channel-1 row */, int f_end, float s1, float b1, bool vec) {
+ISI_HD double lookback_row_sum(const float* row /* channel-1 row */, int f_end, float s1, float b1) {
   double acc = 0.0;
-  if (vec) {        // row 16-byte aligned, f_end a multiple of 4: independent 16-byte loads
-#pragma unroll 8
-    for (int t = 0; t < f_end; t += 4) {
-      const f4 q = *reinterpret_cast<const f4*>(row + t);
-      acc += (double)fmaf(q.x, s1, b1); acc += (double)fmaf(q.y, s1, b1);
-      acc += (double)fmaf(q.z, s1, b1); acc += (double)fmaf(q.w, s1, b1);
-    }
-    return acc;
-  }
   for (int t = 0; t < f_end; ++t) acc += (double)fmaf(row[t], s1, b1);
   return acc;
+}
+// The same sums for R rows at once (rows first_row + i * row_step of a [.., pitch] plane), frames
+// added in rising order per row.  `vec`: rows 16-byte aligned and f_end a multiple of 4 -- then
+// every round issues 4 independent 16-byte loads per row before the first add, so R x 4 loads
+// are in flight per thread instead of one row's.
+template <int R>
+ISI_HD void lookback_rows_sum(const float* plane, int64_t pitch, int first_row, int row_step, int f_end,
+                              float s1, float b1, bool vec, double* acc /* [R] */) {
+#pragma unroll
+  for (int i = 0; i < R; ++i) acc[i] = 0.0;
+  if (!vec) {
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+      acc[i] = lookback_row_sum(plane + (int64_t)(first_row + i * row_step) * pitch, f_end, s1, b1);
+    return;
+  }
+  for (int t = 0; t < f_end; t += 16) {
+    f4 q[R][4];
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+      const float* row = plane + (int64_t)(first_row + i * row_step) * pitch + t;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        q[i][j] = (t + 4 * j < f_end) ? *reinterpret_cast<const f4*>(row + 4 * j) : f4{0.f, 0.f, 0.f, 0.f};
+    }
+#pragma unroll
+    for (int i = 0; i < R; ++i) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (t + 4 * j < f_end) {
+          acc[i] += (double)fmaf(q[i][j].x, s1, b1); acc[i] += (double)fmaf(q[i][j].y, s1, b1);
+          acc[i] += (double)fmaf(q[i][j].z, s1, b1); acc[i] += (double)fmaf(q[i][j].w, s1, b1);
+        }
+      }
+    }
+  }
 }
 template <bool MEL>
 ISI_HD float lookback_phase(const double* sums, int start, int count, const float* w) {

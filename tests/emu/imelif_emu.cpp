@@ -51,7 +51,11 @@ static void emulate(const float* spec, int64_t n_notes, int hop, int pad_left, i
         }
       }
       if (fstart > 0) {
-        for (int m = 0; m < M; ++m) sums[m] = lookback_row_sum(note1 + (int64_t)m * n_frames, fstart, affine[2], affine[3], n_frames % 4 == 0);
+        for (int tid = 0; tid < NT; ++tid) {
+          double row_sum[RPT];
+          lookback_rows_sum<RPT>(note1, n_frames, tid, NT, fstart, affine[2], affine[3], n_frames % 4 == 0, row_sum);
+          for (int r = 0; r < RPT; ++r) sums[tid + r * NT] = row_sum[r];
+        }
         for (int tid = 0; tid < NT; ++tid)
           for (int r = 0; r < RPT; ++r) {
             const int row = tid + r * NT;
