@@ -5,11 +5,16 @@ extract_code.py:67) and without a host sync per note.
     audio batches --front end kernel--> spectrograms --VQVAE.encode_codes--> (top, bottom)
 
 Rows keep the reference's ``CodeRow(top, bottom, attributes, filename)`` shape
-(utils/datasets/lmdb_dataset.py:15); writing them to LMDB is left to the caller because
-``lmdb`` is not available in this image -- ``save_shard`` writes an ``.npz`` per rank instead.
+(utils/datasets/lmdb_dataset.py:15).  ``row_record`` serialises a row to exactly the key / value
+bytes the reference stores (extract_code.py:71-79), ``write_lmdb`` commits a batch of them in ONE
+transaction (the reference opens one per note) when the ``lmdb`` package is installed -- it is not
+in this image, where ``save_shard`` writes an ``.npz`` per rank instead.
 """
 from collections import namedtuple
 from typing import Callable, Iterable, Iterator, List, Optional, Sequence, Tuple
+
+import pickle
+import threading
 
 import numpy as np
 import torch
@@ -270,6 +275,63 @@ class CodeExtractor:
         if pending is not None:
             flush(pending)
         return rows
+
+
+# The reference pickles ``CodeRow`` instances of the class defined in its own module; its readers
+# (utils/datasets/lmdb_dataset.py:79-89, used by train_autoregressive_model.py:482-485 and
+# flask_server.py:273-279) unpickle through that import path.  Records written here name the
+# same path, so they load there without this package being importable.
+_REFERENCE_ROW_MODULE = "interactive_spectrogram_inpainting.utils.datasets.lmdb_dataset"
+_ReferenceCodeRow = namedtuple('CodeRow', ['top', 'bottom', 'attributes', 'filename'])
+_ReferenceCodeRow.__module__ = _REFERENCE_ROW_MODULE
+_ReferenceCodeRow.__qualname__ = 'CodeRow'
+
+
+_record_lock = threading.Lock()     # row_record lends sys.modules a placeholder while it pickles
+
+
+def row_record(row: CodeRow) -> Tuple[bytes, bytes]:
+    """``(key, value)`` as ``extract_code.py:71-79`` stores a note: key = the note name in UTF-8,
+    value = ``pickle.dumps`` of the reference's ``CodeRow`` (``top`` / ``bottom`` int64 arrays,
+    ``attributes`` dict, ``filename``)."""
+    import sys
+    import types
+    record = _ReferenceCodeRow(top=np.asarray(row.top), bottom=np.asarray(row.bottom),
+                               attributes=dict(row.attributes), filename=row.filename)
+    # pickle resolves the class by importing its module; lend it a placeholder module holding
+    # the class when the reference package is not importable here
+    with _record_lock:
+        lent = []
+        loaded = sys.modules.get(_REFERENCE_ROW_MODULE)
+        if loaded is None:
+            # pickle imports the module and its parent packages to verify the name: lend them
+            parts = _REFERENCE_ROW_MODULE.split(".")
+            for i in range(1, len(parts) + 1):
+                name = ".".join(parts[:i])
+                if name not in sys.modules:
+                    sys.modules[name] = types.ModuleType(name)
+                    lent.append(name)
+            sys.modules[_REFERENCE_ROW_MODULE].CodeRow = _ReferenceCodeRow
+        elif getattr(loaded, "CodeRow", None) is not _ReferenceCodeRow:
+            record = loaded.CodeRow(*record)          # the real reference module: pickle its own class
+        try:
+            value = pickle.dumps(record)
+        finally:
+            for name in lent:
+                del sys.modules[name]
+    return row.filename.encode('utf-8'), value
+
+
+def write_lmdb(rows: Sequence[CodeRow], env, db=None) -> int:
+    """Commit ``rows`` to an open ``lmdb.Environment`` in ONE write transaction (the reference
+    opens one per note, extract_code.py:76-78); ``db`` as returned by ``env.open_db(b'codes',
+    dupsort=False)``.  Existing keys are overwritten, like the reference's ``put``.  Returns the
+    number of records written.  Needs the ``lmdb`` package only through ``env``."""
+    records = [row_record(r) for r in rows]
+    with env.begin(db=db, write=True) as txn:
+        for key, value in records:
+            txn.put(key, value)
+    return len(records)
 
 
 def save_shard(rows: Sequence[CodeRow], path) -> None:

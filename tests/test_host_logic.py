@@ -105,3 +105,63 @@ def test_mel_to_audio_runs_and_is_close_in_level():
     assert rebuilt.shape == audio.shape and torch.isfinite(rebuilt).all()
     ratio = rebuilt.pow(2).mean().sqrt() / audio.pow(2).mean().sqrt()
     assert 0.3 < ratio < 3.0, ratio   # the mel pseudo-inverse is lossy; level must survive
+
+
+def test_row_records_unpickle_as_the_reference_code_row():
+    """extract.row_record writes the bytes extract_code.py:71-79 stores: key = note name, value =
+    a pickle naming the reference's own CodeRow class, so the reference's readers
+    (lmdb_dataset.py:79-89) load it without this package; write_lmdb commits a batch in one
+    transaction."""
+    import pickle
+    import sys
+    import types
+    import numpy as np
+    from interactive_spectrogram_inpainting_b200 import extract
+    row = extract.CodeRow(top=np.arange(128).reshape(32, 4), bottom=np.arange(512).reshape(64, 8),
+                          attributes={"pitch": 60}, filename="bass_synthetic_000-060-100")
+    key, value = extract.row_record(row)
+    assert key == b"bass_synthetic_000-060-100"
+    ref_path = "interactive_spectrogram_inpainting.utils.datasets.lmdb_dataset"
+    assert ref_path.encode() in value and b"interactive_spectrogram_inpainting_b200" not in value
+    assert ref_path not in sys.modules                     # the placeholder is gone again
+    # a reader that only has the reference's class (here: a stand-in module at its import path)
+    from collections import namedtuple
+    stand_in = types.ModuleType(ref_path)
+    stand_in.CodeRow = namedtuple('CodeRow', ['top', 'bottom', 'attributes', 'filename'])
+    stand_in.CodeRow.__module__ = ref_path
+    parents = []
+    parts = ref_path.split(".")
+    for i in range(1, len(parts)):
+        name = ".".join(parts[:i])
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+            parents.append(name)
+    sys.modules[ref_path] = stand_in
+    try:
+        loaded = pickle.loads(value)
+        assert type(loaded) is stand_in.CodeRow
+        assert (loaded.top == row.top).all() and (loaded.bottom == row.bottom).all()
+        assert loaded.attributes == {"pitch": 60} and loaded.filename == row.filename
+        assert loaded.top.dtype == np.int64
+        # with the reference module loaded, its own class is pickled
+        key2, value2 = extract.row_record(row)
+        assert type(pickle.loads(value2)) is stand_in.CodeRow
+    finally:
+        del sys.modules[ref_path]
+        for name in parents:
+            del sys.modules[name]
+
+    class Txn:
+        def __init__(self, store): self.store = store
+        def __enter__(self): self.store["begins"] += 1; return self
+        def __exit__(self, *exc): return False
+        def put(self, k, v): self.store[k] = v
+
+    class Env:
+        def __init__(self): self.store = {"begins": 0}
+        def begin(self, db=None, write=False): assert write; return Txn(self.store)
+
+    env = Env()
+    rows = [row, row._replace(filename="other")]
+    assert extract.write_lmdb(rows, env) == 2
+    assert env.store["begins"] == 1 and set(env.store) == {"begins", key, b"other"}
