@@ -90,3 +90,43 @@ def test_mel_to_linear_matrix_undoes_the_filterbank_on_smooth_spectra():
     # the column normalisation makes a flat spectrum come back exactly; the top bin sits on the
     # upper band edge (8000 Hz = Nyquist) and receives no weight at all
     assert np.abs(rebuilt[1:-1] - 1.0).max() < 1e-12 and rebuilt[-1] == 0.0 and rebuilt[0] == 0.0
+
+
+def test_stft_agrees_with_scipy():
+    """The restatement's framing / window / transform against an independent implementation
+    (scipy.signal.stft, no boundary extension, periodic Hann), FP64."""
+    import scipy.signal
+    cfg = fo.FrontEndConfig(use_mel_scale=False)
+    audio = synthetic.synthetic_notes(1, n_samples=16000).double()
+    ours = fo.stft(audio, cfg)[0].numpy()                                  # bins 1..1024
+    pad_l, pad_r, frames = fo.frame_geometry(cfg, 16000)
+    padded = np.pad(audio[0].numpy(), (pad_l, pad_r))
+    win = scipy.signal.get_window("hann", cfg.n_fft, fftbins=True)
+    _, _, z = scipy.signal.stft(padded, window=win, nperseg=cfg.n_fft, noverlap=cfg.n_fft - cfg.hop_length,
+                                boundary=None, padded=False, return_onesided=True)
+    z = z * win.sum()                                                      # scipy normalises by the window sum
+    assert z.shape == (cfg.n_fft // 2 + 1, frames)
+    assert np.abs(ours - z[1:]).max() <= 1e-9 * np.abs(z).max()
+
+
+def test_mel_matrix_agrees_with_a_direct_evaluation_of_the_published_formula():
+    """magenta ``linear_to_mel_weight_matrix`` written out bin by bin in plain Python for a few
+    columns: triangle between equally spaced mel edges, HTK-style mel with break frequency 700 Hz
+    and Q = 1127, narrow triangles widened to 1.5 linear bins (arcsinh re-centring)."""
+    cfg = fo.FrontEndConfig()
+    m = fo.linear_to_mel_matrix(cfg)
+    n, nyq, brk, q = 1024, 8000.0, 700.0, 1127.0
+    mel = lambda f: q * math.log(1.0 + f / brk)
+    hz = lambda v: brk * (math.exp(v / q) - 1.0)
+    edges = [mel(0.0) + (mel(8000.0) - mel(0.0)) * i / (n + 1) for i in range(n + 2)]
+    for j in (0, 3, 40, 300, 700, 1023):
+        lo, mid, hi = edges[j], edges[j + 1], edges[j + 2]
+        floor = 1.5 * nyq / n
+        if hz(hi) - hz(lo) < floor:
+            half = q * math.asinh(0.5 * floor / (hz(mid) + brk))
+            lo, hi = mid - half, mid + half
+        for k in range(1, n):
+            f = nyq * k / (n - 1)
+            want = max(0.0, min((f - hz(lo)) / (hz(mid) - hz(lo)), (hz(hi) - f) / (hz(hi) - hz(mid))))
+            assert abs(m[k, j] - want) < 1e-12, (k, j)
+        assert m[0, j] == 0.0
