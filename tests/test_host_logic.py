@@ -165,3 +165,22 @@ def test_row_records_unpickle_as_the_reference_code_row():
     rows = [row, row._replace(filename="other")]
     assert extract.write_lmdb(rows, env) == 2
     assert env.store["begins"] == 1 and set(env.store) == {"begins", key, b"other"}
+
+
+def test_helper_factory_takes_the_reference_parameter_dict():
+    """utils/misc.py:10-29: the dict train_vqvae.py dumps (every command-line parameter) selects
+    and configures the helper; unrelated keys are ignored, a missing one raises KeyError."""
+    from interactive_spectrogram_inpainting_b200.utils.misc import get_spectrograms_helper
+    params = dict(fs_hz=16000, n_fft=1024, hop_length=256, window_length=1024, use_mel_scale=True,
+                  mel_scale_lower_edge_hertz=20.0, mel_scale_upper_edge_hertz=7000.0,
+                  mel_scale_break_frequency_hertz=650.0, mel_scale_expand_resolution_factor=2.0,
+                  batch_size=64, lr=3e-4)
+    mel = get_spectrograms_helper(**params)
+    assert type(mel) is sh.MelSpectrogramsHelper
+    assert (mel.fs_hz, mel.n_fft, mel.hop_length, mel.window_length) == (16000, 1024, 256, 1024)
+    assert (mel.lower_edge_hertz, mel.upper_edge_hertz, mel.mel_break_frequency_hertz,
+            mel.mel_bin_width_threshold_factor) == (20.0, 7000.0, 650.0, 2.0)
+    lin = get_spectrograms_helper(**dict(params, use_mel_scale=False))
+    assert type(lin) is sh.SpectrogramsHelper and lin.n_fft == 1024
+    with pytest.raises(KeyError):
+        get_spectrograms_helper(fs_hz=16000, n_fft=1024, use_mel_scale=False)
