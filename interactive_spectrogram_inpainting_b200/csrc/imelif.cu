@@ -190,7 +190,7 @@ imelif_kernel(const float* __restrict__ spec, isi_imelif_params p, float* __rest
       asm volatile("bar.sync %0, 64;" ::"r"(group_bar) : "memory");
       fft_pass2<P>(tid & 63, twm, z);
       asm volatile("bar.sync %0, 64;" ::"r"(group_bar) : "memory");
-      Pass3Regs<P> regs;
+      Pass3Regs<P, cpx> regs;
       fft_pass3_load<P>(tid & 63, z, regs);
       asm volatile("bar.sync %0, 64;" ::"r"(group_bar) : "memory");
       fft_pass3_store<P>(tid & 63, regs, z);

@@ -76,41 +76,172 @@ __device__ __forceinline__ void st_stream4(float* p, float4 v) {
                :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+// ---- pieces shared by the two kernels below ----
+
+// Band constants of one output row (first bin incl. the dropped-DC offset, length, weights),
+// read from the L1/L2-resident tables.
+template <bool MEL>
+struct RowBand { int bin, cnt; float w[MEL ? kMaxMelWidth : 1]; };
+
+template <bool MEL>
+__device__ __forceinline__ RowBand<MEL> load_row_band(const isi_melif_params& p, int row, int dc, bool w_vec) {
+  RowBand<MEL> b;
+  b.bin = row + dc;
+  b.cnt = 0;
+  if (MEL) {
+    b.bin = ld_table(p.mel_start + row) + dc;
+    b.cnt = ld_table(p.mel_count + row);
+    if (w_vec) {
+      const float4* wt = reinterpret_cast<const float4*>(p.mel_weight) + (int64_t)row * 2;
+      const float4 a = ld_table4(wt), c = ld_table4(wt + 1);
+      b.w[0] = a.x; b.w[1] = a.y; b.w[2] = a.z; b.w[3] = a.w;
+      b.w[4 % (MEL ? 8 : 1)] = c.x; b.w[5 % (MEL ? 8 : 1)] = c.y;
+      b.w[6 % (MEL ? 8 : 1)] = c.z; b.w[7 % (MEL ? 8 : 1)] = c.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < kMaxMelWidth; ++i)
+        b.w[i % (MEL ? 8 : 1)] = (i < p.mel_width) ? __ldg(p.mel_weight + (int64_t)row * p.mel_width + i) : 0.f;
+    }
+  }
+  return b;
+}
+
+// One output row of a batch: projection, log / wrap, fused epilogue, and the stores of the FB
+// time steps in the requested layout.  v0 / v1 are produced per frame slot by scalar FFMAs, so
+// each 16-byte store finds its four values in consecutive registers.
+template <typename P, int FB, bool MEL>
+__device__ __forceinline__ void emit_row(const isi_melif_params& p, const cpx2* zA, const RowBand<MEL>& band,
+                                         int row, int note_idx, int f0, int nf, float eps, float* out) {
+  constexpr int M = P::M, NP = FB / 2;
+  f2 lg[NP], ph[NP];
+  if (MEL) {
+    const int cnt_warp = __reduce_max_sync(0xffffffffu, band.cnt);
+    emit_mel<NP>(zA, P::kPitchA, band.bin, cnt_warp, band.w, f0 == 0, eps, lg, ph);
+  } else {
+    emit_linear<NP>(zA, P::kPitchA, band.bin, lg, ph);
+  }
+  float v0[FB], v1[FB];      // frame-slot order
+  finish_row<NP>(lg, ph, p.mask_phase != 0, p.mask_threshold, p.out_scale[0], p.out_bias[0],
+                 p.out_scale[1], p.out_bias[1], v0, v1);
+  if (p.channels_last == ISI_SPEC_SPACE_TO_DEPTH) {
+    // [B, F/2, T'/2, (f&1, t&1, channel)]: 2x2 spectrogram blocks as 8 channels.  A row
+    // writes 16 bytes per block; the odd/even row pair (neighbouring lanes of the same
+    // instruction) completes each 32-byte sector.
+    float* d = out + ((((int64_t)note_idx * (M / 2) + (row >> 1)) * (p.n_frames >> 1) + (f0 >> 1)) * 8) +
+               (row & 1) * 4;
+    if (nf == FB) {
+#pragma unroll
+      for (int k = 0; k < FB / 2; ++k)
+        st_stream4(d + 8 * k, make_float4(v0[2 * k], v1[2 * k], v0[2 * k + 1], v1[2 * k + 1]));
+    } else {
+#pragma unroll
+      for (int s = 0; s < FB; ++s)
+        if (s < nf) {
+          float* e = d + (s >> 1) * 8 + (s & 1) * 2;
+          e[0] = v0[s]; e[1] = v1[s];
+        }
+    }
+    return;
+  }
+  if (p.channels_last) {
+    // [B, F, T', 2]: the FB time steps of both channels are one contiguous run
+    float* d = out + (((int64_t)note_idx * M + row) * p.n_frames + f0) * 2;
+    if (nf == FB && (p.n_frames % 2 == 0)) {
+#pragma unroll
+      for (int k = 0; k < FB / 2; ++k)
+        st_stream4(d + 4 * k, make_float4(v0[2 * k], v1[2 * k], v0[2 * k + 1], v1[2 * k + 1]));
+    } else {
+#pragma unroll
+      for (int s = 0; s < FB; ++s)
+        if (s < nf) { d[2 * s] = v0[s]; d[2 * s + 1] = v1[s]; }
+    }
+    return;
+  }
+  float* d0 = out + (int64_t)note_idx * 2 * M * p.n_frames + (int64_t)row * p.n_frames + f0;
+  float* d1 = d0 + (int64_t)M * p.n_frames;
+  if (nf == FB && (FB % 4 == 0) && (p.n_frames % 4 == 0)) {
+#pragma unroll
+    for (int k = 0; k < FB / 4; ++k) {
+      st_stream4(d0 + 4 * k, make_float4(v0[4 * k], v0[4 * k + 1], v0[4 * k + 2], v0[4 * k + 3]));
+      st_stream4(d1 + 4 * k, make_float4(v1[4 * k], v1[4 * k + 1], v1[4 * k + 2], v1[4 * k + 3]));
+    }
+  } else {
+#pragma unroll
+    for (int s = 0; s < FB; ++s)
+      if (s < nf) { d0[s] = v0[s]; d1[s] = v1[s]; }
+  }
+}
+
+// Stage the audio span of frames [frame, frame + nfr) of `note`: threads [t, nt) zero-fill what
+// lies outside the note, `issuer` sends one bulk copy for the rest (completion on `bar`).
+template <typename S>
+__device__ __forceinline__ void stage_span_bulk(S* stage, const S* note, int64_t n_samples, int hop, int pad_left,
+                                                int n_fft, int frame, int nfr, int t, int nt, bool issuer,
+                                                uint64_t* bar) {
+  const int span = (nfr - 1) * hop + n_fft;
+  const int64_t s0 = (int64_t)frame * hop - pad_left;
+  const int64_t lo = s0 < 0 ? -s0 : 0;                      // first valid index
+  int64_t hi = n_samples - s0;                              // one past the last valid index
+  hi = hi < 0 ? 0 : (hi > span ? span : hi);
+  const int64_t vlo = lo < hi ? lo : hi;
+  for (int i = t; i < vlo; i += nt) stage[i] = S(0);
+  for (int i = (int)hi + t; i < span; i += nt) stage[i] = S(0);
+  if (issuer) {
+    if (hi > lo) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      const uint32_t bytes = (uint32_t)(hi - lo) * (uint32_t)sizeof(S);
+      mbar_expect_tx(bar, bytes);
+      bulk_g2s(stage + lo, note + s0 + lo, bytes, bar);
+    } else {
+      mbar_arrive(bar);
+    }
+  }
+}
+
 struct MelifSmem {
   int tw, win, stage, za, bar, total;   // byte offsets into dynamic shared memory
 };
 
 template <int NFFT, int FB>
-__host__ __device__ inline MelifSmem melif_smem_layout(int hop, int sample_bytes) {
+__host__ __device__ inline MelifSmem melif_smem_layout(int hop, int sample_bytes, int n_buffers = 1) {
   using P = Plan<NFFT>;
   MelifSmem s;
   int off = 0;
   s.tw = off;    off += (NFFT / 2) * 8;                     // FFT twiddles (fft_table_source)
   s.win = off;   off += NFFT * 4;
   s.stage = off; off += (((FB - 1) * hop + NFFT) * sample_bytes + 15) / 16 * 16;
-  s.za = off;    off += FB * P::kPitchA * 8;                // FFT workspace, spectrum, polar values
-  s.bar = off;   off += 16;
+  s.za = off;    off += n_buffers * (FB / 2) * P::kPitchA * 16;   // FFT workspace, spectrum, polar values
+  s.bar = off;   off += 64;
   s.total = off;
   return s;
 }
 
+// CTAs per SM each instantiation is built for (registers: 65536 / (NT * CTAS))
+__host__ __device__ constexpr int melif_ctas_per_sm(int nt) { return nt >= 256 ? 2 : (nt >= 128 ? 4 : 8); }
+
+// ------------------------------------------------------------------------------------------
+// Generic kernel: every thread runs every phase (n_fft 512 / 1024 / 2048, any hop, any
+// alignment; the synchronous staging path when the audio is not 16-byte copyable).
+// ------------------------------------------------------------------------------------------
 template <int NFFT, int FB, int NT, bool MEL, typename S>
-__global__ void __launch_bounds__(NT, NT >= 512 ? 2 : 3)
+__global__ void __launch_bounds__(NT, melif_ctas_per_sm(NT))
 melif_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params p,
              float* __restrict__ out, int bulk_ok, int seg_frames, int n_segs) {
   using P = Plan<NFFT>;
   constexpr int M = P::M;
+  constexpr int NP = FB / 2;                  // frame pairs per batch: pair q = slots q, q + NP
   constexpr int IPT = (M / 2) / NT;           // polar work items per thread
   constexpr int RPT = M / NT;                 // output rows per thread
-  constexpr int kGroups = NT / 64;            // frames transformed concurrently
+  constexpr int kGroups = NT / 64;            // pairs transformed concurrently
+  static_assert(FB % 2 == 0 && NP >= 2, "frames are processed in pairs");
   static_assert(IPT >= 1 && (M / 2) % NT == 0 && NT % 64 == 0, "bad thread count");
-  static_assert(P::kPitchA >= M + 1, "a frame region must hold bins 0..M");
+  static_assert(P::kPitchA >= M + kMaxMelWidth, "a pair's region must hold bins 0..M and the band overrun");
   extern __shared__ __align__(128) unsigned char smem[];
   const MelifSmem L = melif_smem_layout<NFFT, FB>(p.hop, (int)sizeof(S));
   cpx* twm = reinterpret_cast<cpx*>(smem + L.tw);
   float* win = reinterpret_cast<float*>(smem + L.win);
   S* stage = reinterpret_cast<S*>(smem + L.stage);
-  cpx* zA = reinterpret_cast<cpx*>(smem + L.za);
+  cpx2* zA = reinterpret_cast<cpx2*>(smem + L.za);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.bar);
 
   const int tid = threadIdx.x;
@@ -118,8 +249,6 @@ melif_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params p,
   const int fs = seg * seg_frames;                          // first frame of this CTA
   const int fe = min(p.n_frames, fs + seg_frames);          // one past its last frame
   const S* note = audio + (int64_t)note_idx * n_samples;
-  float* out0 = out + (int64_t)note_idx * 2 * M * p.n_frames;
-  float* out1 = out0 + (int64_t)M * p.n_frames;
   const int dc = p.drop_dc ? 1 : 0;
   const float eps = p.safelog_eps;
   const bool pairs_aligned = (p.hop % 2) == 0;   // a frame starts on a sample-pair boundary
@@ -127,7 +256,13 @@ melif_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params p,
   // ---- one-time setup: tables to shared memory, per-thread constants to registers ----
   const cpx* tw_global = reinterpret_cast<const cpx*>(p.twiddle);     // W_N^j, j < N
   for (int i = tid; i < M; i += NT) twm[i] = tw_global[fft_table_source<P>(i)];
-  for (int i = tid; i < NFFT; i += NT) win[i] = p.window[i];
+  // the window carries the untangle's 1/2 and, for PCM input, a power-of-two sample scale
+  const bool fold_scale = sizeof(S) == 2 && is_pow2_scale(p.pcm_scale);
+  const float win_scale = 0.5f * (fold_scale ? p.pcm_scale : 1.f);
+  const float sample_scale = (sizeof(S) == 2 && !fold_scale) ? p.pcm_scale : 1.f;
+  for (int i = tid; i < NFFT; i += NT) win[i] = p.window[i] * win_scale;
+  // band reads may run past a band into never-written padding: make it finite once
+  for (int i = tid; i < NP * P::kPitchA; i += NT) { zA[i].re = bc(0.f); zA[i].im = bc(0.f); }
   if (tid == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -135,40 +270,18 @@ melif_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params p,
   cpx w_item[IPT];
 #pragma unroll
   for (int i = 0; i < IPT; ++i) w_item[i] = tw_global[tid + i * NT];
-  // Per-row band constants (first bin, length, weights) are NOT kept in registers across the
-  // transform (they would spill): each batch re-reads them from the L1-resident tables ahead
-  // of the barrier that precedes emit.
   const bool w_vec = MEL && p.mel_width == kMaxMelWidth && (reinterpret_cast<uintptr_t>(p.mel_weight) & 15) == 0;
-  BinState sa[IPT], sb[IPT];
+  BinState st[IPT];
 #pragma unroll
-  for (int i = 0; i < IPT; ++i) { sa[i] = BinState{1.f, 0.f}; sb[i] = BinState{1.f, 0.f}; }
+  for (int i = 0; i < IPT; ++i) st[i] = bin_state_init();
   __syncthreads();
 
-  // Stage the audio span of frames [frame, frame + nfr): zero-fill what lies outside the
-  // note, one bulk copy for the rest (thread 0), completion signalled on `bar`.
   auto stage_span = [&](int frame, int nfr) {
-    const int span = (nfr - 1) * p.hop + NFFT;
-    const int64_t s0 = (int64_t)frame * p.hop - p.pad_left;
     if (!bulk_ok) {
-      stage_fill(tid, NT, stage, span, note, n_samples, s0);
+      stage_fill(tid, NT, stage, (nfr - 1) * p.hop + NFFT, note, n_samples, (int64_t)frame * p.hop - p.pad_left);
       return;
     }
-    const int64_t lo = s0 < 0 ? -s0 : 0;                      // first valid index
-    int64_t hi = n_samples - s0;                              // one past the last valid index
-    hi = hi < 0 ? 0 : (hi > span ? span : hi);
-    const int64_t vlo = lo < hi ? lo : hi;
-    for (int i = tid; i < vlo; i += NT) stage[i] = S(0);
-    for (int i = (int)hi + tid; i < span; i += NT) stage[i] = S(0);
-    if (tid == 0) {
-      if (hi > lo) {
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        const uint32_t bytes = (uint32_t)(hi - lo) * (uint32_t)sizeof(S);
-        mbar_expect_tx(bar, bytes);
-        bulk_g2s(stage + lo, note + s0 + lo, bytes, bar);
-      } else {
-        mbar_arrive(bar);
-      }
-    }
+    stage_span_bulk(stage, note, n_samples, p.hop, p.pad_left, NFFT, frame, nfr, tid, NT, tid == 0, bar);
   };
 
   // Batch -1 is the look-back transform of frame fs-1: it only seeds the phase-step state.
@@ -187,120 +300,187 @@ melif_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params p,
     if (bulk_ok) { mbar_wait(bar, stage_phase & 1); ++stage_phase; }
     __syncthreads();       // zero-filled pads / synchronous fills come from other threads;
                            // also fences the previous batch's emit from this pass 1
-    // The three FFT passes of a frame only involve the 64 threads of its group: they meet
-    // on a named barrier of their own instead of stalling the whole CTA.
+    // The three FFT passes of a pair only involve the 64 threads of its group: they meet
+    // on a named barrier of their own instead of stalling the whole CTA.  Slots >= nf of a
+    // ragged last batch transform whatever the stage holds (finite; never emitted).  The
+    // look-back frame is transformed as lane y of the last pair, where the state lives.
     const uint32_t group_bar = 1 + (tid >> 6);
-    for (int fb = tid / 64; fb < nf; fb += kGroups)
-      fft_pass1<P>(tid & 63, stage + fb * p.hop, pairs_aligned, p.pcm_scale, win, twm, zA + fb * P::kPitchA);
-    asm volatile("bar.sync %0, 64;" ::"r"(group_bar) : "memory");
-    for (int fb = tid / 64; fb < nf; fb += kGroups) fft_pass2<P>(tid & 63, twm, zA + fb * P::kPitchA);
-    asm volatile("bar.sync %0, 64;" ::"r"(group_bar) : "memory");
-    for (int fb = tid / 64; fb < nf; fb += kGroups) {
-      Pass3Regs<P> regs;
-      fft_pass3_load<P>(tid & 63, zA + fb * P::kPitchA, regs);
+    for (int q = tid / 64; q < NP; q += kGroups) {
+      if (lookback ? (q != NP - 1) : (q >= nf)) continue;
+      const S* fa = stage + (lookback ? 0 : q * p.hop);
+      const S* fb = stage + (lookback ? 0 : (q + NP) * p.hop);
+      cpx2* z = zA + q * P::kPitchA;
+      fft_pass1_pair<P>(tid & 63, fa, fb, pairs_aligned, sample_scale, win, twm, z);
       asm volatile("bar.sync %0, 64;" ::"r"(group_bar) : "memory");
-      fft_pass3_store<P>(tid & 63, regs, zA + fb * P::kPitchA);
+      fft_pass2<P>(tid & 63, twm, z);
+      asm volatile("bar.sync %0, 64;" ::"r"(group_bar) : "memory");
+      Pass3Regs<P, cpx2> regs;
+      fft_pass3_load<P>(tid & 63, z, regs);
+      asm volatile("bar.sync %0, 64;" ::"r"(group_bar) : "memory");
+      fft_pass3_store<P>(tid & 63, regs, z);
     }
     __syncthreads();
     if (next_nf > 0 && bulk_ok) stage_span(next_f0, next_nf);   // every group is done with the stage
-    // polar: frames in order, previous spectrum value in registers, in place
-#pragma unroll 2
-    for (int fb = 0; fb < nf; ++fb) {
+    // polar: the whole batch of a work item, previous phasors in registers, in place
 #pragma unroll
-      for (int i = 0; i < IPT; ++i)
-        if (i == 0)
-          polar_item<P, MEL, true>(tid, zA + fb * P::kPitchA, w_item[0], dc ? M : 0,
-                                   lookback || (f0 + fb == 0), eps, sa[0], sb[0]);
-        else
-          polar_item<P, MEL, false>(tid + i * NT, zA + fb * P::kPitchA, w_item[i], 0,
-                                    lookback || (f0 + fb == 0), eps, sa[i], sb[i]);
-    }
+    for (int i = 0; i < IPT; ++i)
+      if (i == 0)
+        polar_item<P, MEL, NP, true>(tid, zA, P::kPitchA, w_item[0], dc ? M : 0, lookback, eps, st[0]);
+      else
+        polar_item<P, MEL, NP, false>(tid + i * NT, zA, P::kPitchA, w_item[i], 0, lookback, eps, st[i]);
     if (!lookback) {
-      float row_w[RPT][MEL ? kMaxMelWidth : 1];
-      int row_bin[RPT], row_cnt[RPT];
+      // Per-row band constants are NOT kept in registers across the transform and polar
+      // (they would spill): each batch re-reads them from the L1-resident tables just
+      // before the barrier that precedes emit.
+      RowBand<MEL> band[RPT];
 #pragma unroll
-      for (int r = 0; r < RPT; ++r) {
-        const int row = tid + r * NT;
-        row_bin[r] = row + dc;
-        row_cnt[r] = 0;
-        if (MEL) {
-          row_bin[r] = ld_table(p.mel_start + row) + dc;
-          row_cnt[r] = ld_table(p.mel_count + row);
-          if (w_vec) {
-            const float4* wt = reinterpret_cast<const float4*>(p.mel_weight) + (int64_t)row * 2;
-            const float4 a = ld_table4(wt), c = ld_table4(wt + 1);
-            row_w[r][0] = a.x; row_w[r][1] = a.y; row_w[r][2] = a.z; row_w[r][3] = a.w;
-            row_w[r][4] = c.x; row_w[r][5] = c.y; row_w[r][6] = c.z; row_w[r][7] = c.w;
-          } else {
-#pragma unroll
-            for (int i = 0; i < kMaxMelWidth; ++i)
-              row_w[r][i] = (i < p.mel_width) ? __ldg(p.mel_weight + (int64_t)row * p.mel_width + i) : 0.f;
-          }
-        }
-      }
+      for (int r = 0; r < RPT; ++r) band[r] = load_row_band<MEL>(p, tid + r * NT, dc, w_vec);
       __syncthreads();
       // emit: all FB time steps of a row at once
 #pragma unroll
-      for (int r = 0; r < RPT; ++r) {
-        const int row = tid + r * NT;
-        const int row_cnt_warp = MEL ? __reduce_max_sync(0xffffffffu, row_cnt[r]) : 0;
-        float v0[FB], v1[FB];
-        if (MEL)
-          emit_mel<FB>(zA, P::kPitchA, row_bin[r], row_cnt[r], row_cnt_warp, row_w[r], f0 == 0, eps, v0, v1);
-        else
-          emit_linear<FB>(zA, P::kPitchA, row_bin[r], v0, v1);
-        apply_epilogue<FB>(v0, v1, p.mask_phase != 0, p.mask_threshold, p.out_scale[0], p.out_bias[0],
-                           p.out_scale[1], p.out_bias[1]);
-        if (p.channels_last == ISI_SPEC_SPACE_TO_DEPTH) {
-          // [B, F/2, T'/2, (f&1, t&1, channel)]: 2x2 spectrogram blocks as 8 channels.  A row
-          // writes 16 bytes per block; the odd/even row pair (neighbouring lanes of the same
-          // instruction) completes each 32-byte sector.
-          float* d = out + ((((int64_t)note_idx * (M / 2) + (row >> 1)) * (p.n_frames >> 1) + (f0 >> 1)) * 8) +
-                     (row & 1) * 4;
-          if (nf == FB && (FB % 2 == 0)) {
-#pragma unroll
-            for (int q = 0; q < FB / 2; ++q)
-              st_stream4(d + 8 * q, make_float4(v0[2 * q], v1[2 * q], v0[2 * q + 1], v1[2 * q + 1]));
-          } else {
-#pragma unroll
-            for (int fb = 0; fb < FB; ++fb)
-              if (fb < nf) {
-                float* e = d + (fb >> 1) * 8 + (fb & 1) * 2;
-                e[0] = v0[fb]; e[1] = v1[fb];
-              }
-          }
-          continue;
-        }
-        if (p.channels_last) {
-          // [B, F, T', 2]: the FB time steps of both channels are one contiguous run
-          float* d = out + (((int64_t)note_idx * M + row) * p.n_frames + f0) * 2;
-          if (nf == FB && (FB % 2 == 0) && (p.n_frames % 2 == 0)) {
-#pragma unroll
-            for (int q = 0; q < FB / 2; ++q)
-              st_stream4(d + 4 * q, make_float4(v0[2 * q], v1[2 * q], v0[2 * q + 1], v1[2 * q + 1]));
-          } else {
-#pragma unroll
-            for (int fb = 0; fb < FB; ++fb)
-              if (fb < nf) { d[2 * fb] = v0[fb]; d[2 * fb + 1] = v1[fb]; }
-          }
-          continue;
-        }
-        float* d0 = out0 + (int64_t)row * p.n_frames + f0;
-        float* d1 = out1 + (int64_t)row * p.n_frames + f0;
-        if (nf == FB && (FB % 4 == 0) && (p.n_frames % 4 == 0)) {
-#pragma unroll
-          for (int q = 0; q < FB / 4; ++q) {
-            st_stream4(d0 + 4 * q, make_float4(v0[4 * q], v0[4 * q + 1], v0[4 * q + 2], v0[4 * q + 3]));
-            st_stream4(d1 + 4 * q, make_float4(v1[4 * q], v1[4 * q + 1], v1[4 * q + 2], v1[4 * q + 3]));
-          }
-        } else {
-#pragma unroll
-          for (int fb = 0; fb < FB; ++fb)
-            if (fb < nf) { d0[fb] = v0[fb]; d1[fb] = v1[fb]; }
-        }
-      }
+      for (int r = 0; r < RPT; ++r)
+        emit_row<P, FB, MEL>(p, zA, band[r], tid + r * NT, note_idx, f0, nf, eps, out);
     }
     if (!bulk_ok && next_nf > 0) { __syncthreads(); stage_span(next_f0, next_nf); }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Warp-specialised kernel (n_fft 2048, bulk-copyable audio, even hop): the NSynth shape.
+//
+// One CTA per SM, 24 warps in two roles that run CONCURRENTLY on consecutive batches of
+// FB = 8 frames through a double-buffered workspace:
+//   * 8 transform warps (4 groups of 64 threads, one frame pair each): stage wait, the three
+//     FFT passes; ~110 registers (setmaxnreg.inc) for the 16-point butterflies of a pair;
+//   * 16 polar/emit warps (512 threads, one untangle item and two output rows each): polar
+//     of the batch the transform warps finished last, then the mel projection, log / wrap,
+//     epilogue and stores; ~72 registers (setmaxnreg.dec).
+// The generic kernel gives every thread the transform's register budget, which caps an SM at
+// 16 warps; here the register file is split by need (8 x 32 x 112 + 16 x 32 x 72 = 64 Ki), so
+// 24 warps are resident, and the FMA-heavy transform overlaps the LDS / MUFU / store-heavy
+// emit instead of alternating with it.  Hand-off: full[buf] / empty[buf] mbarriers
+// (transform -> polar/emit -> transform); role-wide named barriers inside each role.
+// ------------------------------------------------------------------------------------------
+constexpr int kWsFftThreads = 256, kWsPeThreads = 512, kWsThreads = kWsFftThreads + kWsPeThreads;
+constexpr int kWsFftRegs = 112, kWsPeRegs = 72;
+
+template <int FB, bool MEL, typename S>
+__global__ void __launch_bounds__(kWsThreads, 1)
+melif_ws_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params p,
+                float* __restrict__ out, int seg_frames, int n_segs) {
+  constexpr int NFFT = 2048;
+  using P = Plan<NFFT>;
+  constexpr int M = P::M, NP = FB / 2;
+  static_assert(NP == kWsFftThreads / 64, "one transform group per frame pair");
+  static_assert(M / 2 == kWsPeThreads, "one untangle item per polar/emit thread");
+  constexpr int RPT = M / kWsPeThreads;
+  extern __shared__ __align__(128) unsigned char smem[];
+  const MelifSmem L = melif_smem_layout<NFFT, FB>(p.hop, (int)sizeof(S), 2);
+  cpx* twm = reinterpret_cast<cpx*>(smem + L.tw);
+  float* win = reinterpret_cast<float*>(smem + L.win);
+  S* stage = reinterpret_cast<S*>(smem + L.stage);
+  cpx2* zA = reinterpret_cast<cpx2*>(smem + L.za);         // [2][NP][kPitchA]
+  uint64_t* bar_stage = reinterpret_cast<uint64_t*>(smem + L.bar);
+  uint64_t* bar_full = bar_stage + 1;                      // [2] transform -> polar/emit
+  uint64_t* bar_empty = bar_stage + 3;                     // [2] polar/emit -> transform
+  constexpr int kBufElems = NP * P::kPitchA;
+
+  const int tid = threadIdx.x;
+  const int note_idx = blockIdx.x / n_segs, seg = blockIdx.x - note_idx * n_segs;
+  const int fs = seg * seg_frames;
+  const int fe = min(p.n_frames, fs + seg_frames);
+  const S* note = audio + (int64_t)note_idx * n_samples;
+  const int dc = p.drop_dc ? 1 : 0;
+  const float eps = p.safelog_eps;
+
+  const cpx* tw_global = reinterpret_cast<const cpx*>(p.twiddle);
+  for (int i = tid; i < M; i += kWsThreads) twm[i] = tw_global[fft_table_source<P>(i)];
+  const bool fold_scale = sizeof(S) == 2 && is_pow2_scale(p.pcm_scale);
+  const float win_scale = 0.5f * (fold_scale ? p.pcm_scale : 1.f);
+  const float sample_scale = (sizeof(S) == 2 && !fold_scale) ? p.pcm_scale : 1.f;
+  for (int i = tid; i < NFFT; i += kWsThreads) win[i] = p.window[i] * win_scale;
+  for (int i = tid; i < 2 * kBufElems; i += kWsThreads) { zA[i].re = bc(0.f); zA[i].im = bc(0.f); }
+  if (tid == 0) {
+    mbar_init(bar_stage, 1);
+    mbar_init(bar_full + 0, kWsFftThreads);
+    mbar_init(bar_full + 1, kWsFftThreads);
+    mbar_init(bar_empty + 0, kWsPeThreads);
+    mbar_init(bar_empty + 1, kWsPeThreads);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const int n_batches = (fe - fs + FB - 1) / FB;
+  const int b_begin = fs > 0 ? -1 : 0;
+
+  if (tid < kWsFftThreads) {
+    // =========================== transform warps ===========================
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kWsFftRegs));
+    const int q = tid >> 6, j = tid & 63;                  // frame pair of this group, lane in it
+    const uint32_t group_bar = 3 + q;
+    stage_span_bulk(stage, note, n_samples, p.hop, p.pad_left, NFFT, fs > 0 ? fs - 1 : fs,
+                    fs > 0 ? 1 : min(FB, fe - fs), tid, kWsFftThreads, tid == 0, bar_stage);
+    uint32_t it = 0;
+    for (int b = b_begin; b < n_batches; ++b, ++it) {
+      const bool lookback = b < 0;
+      const int f0 = lookback ? fs - 1 : fs + b * FB;
+      const int nf = lookback ? 1 : min(FB, fe - f0);
+      const int next_f0 = fs + (b + 1) * FB;
+      const int next_nf = (b + 1 < n_batches) ? min(FB, fe - next_f0) : 0;
+      const uint32_t buf = it & 1, use = it >> 1;
+      cpx2* z = zA + buf * kBufElems + q * P::kPitchA;
+      const bool active = lookback ? (q == NP - 1) : (q < nf);
+
+      mbar_wait(bar_stage, it & 1);                        // this batch's audio has landed
+      mbar_wait(bar_empty + buf, (use & 1) ^ 1);           // polar/emit released the buffer
+      asm volatile("bar.sync 1, %0;" ::"n"(kWsFftThreads) : "memory");   // zero-filled pads are visible
+      if (active)
+        fft_pass1_pair<P>(j, stage + (lookback ? 0 : q * p.hop), stage + (lookback ? 0 : (q + NP) * p.hop),
+                          true, sample_scale, win, twm, z);
+      asm volatile("bar.sync 1, %0;" ::"n"(kWsFftThreads) : "memory");   // every group is done with the stage
+      if (next_nf > 0)
+        stage_span_bulk(stage, note, n_samples, p.hop, p.pad_left, NFFT, next_f0, next_nf, tid,
+                        kWsFftThreads, tid == 0, bar_stage);
+      if (active) {
+        fft_pass2<P>(j, twm, z);
+        asm volatile("bar.sync %0, 64;" ::"r"(group_bar) : "memory");
+        Pass3Regs<P, cpx2> regs;
+        fft_pass3_load<P>(j, z, regs);
+        asm volatile("bar.sync %0, 64;" ::"r"(group_bar) : "memory");
+        fft_pass3_store<P>(j, regs, z);
+      }
+      mbar_arrive(bar_full + buf);                         // release: the spectrum is in place
+    }
+  } else {
+    // =========================== polar / emit warps ===========================
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kWsPeRegs));
+    const int t = tid - kWsFftThreads;                     // 0 .. 511: untangle item and first row
+    const cpx w_item = tw_global[t];
+    const bool w_vec = MEL && p.mel_width == kMaxMelWidth && (reinterpret_cast<uintptr_t>(p.mel_weight) & 15) == 0;
+    BinState st = bin_state_init();
+    uint32_t it = 0;
+    for (int b = b_begin; b < n_batches; ++b, ++it) {
+      const bool lookback = b < 0;
+      const int f0 = lookback ? fs - 1 : fs + b * FB;
+      const int nf = lookback ? 1 : min(FB, fe - f0);
+      const uint32_t buf = it & 1, use = it >> 1;
+      cpx2* z = zA + buf * kBufElems;
+      // band constants first: their L1/L2 latency hides behind the wait and polar
+      RowBand<MEL> band[RPT];
+      if (!lookback) {
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) band[r] = load_row_band<MEL>(p, t + r * kWsPeThreads, dc, w_vec);
+      }
+      mbar_wait(bar_full + buf, use & 1);
+      polar_item<P, MEL, NP, true>(t, z, P::kPitchA, w_item, dc ? M : 0, lookback, eps, st);
+      if (!lookback) {
+        asm volatile("bar.sync 2, %0;" ::"n"(kWsPeThreads) : "memory");  // every bin of the batch is polar
+#pragma unroll
+        for (int r = 0; r < RPT; ++r)
+          emit_row<P, FB, MEL>(p, z, band[r], t + r * kWsPeThreads, note_idx, f0, nf, eps, out);
+      }
+      mbar_arrive(bar_empty + buf);                        // release: the buffer may be overwritten
+    }
   }
 }
 
@@ -324,18 +504,14 @@ static void choose_segments(int64_t n_notes, int n_frames, int fb, int ctas_per_
 
 template <int NFFT, int FB, int NT, bool MEL, typename S>
 static int launch_melif_t(const S* audio, int64_t n_notes, int64_t n_samples,
-                          const isi_melif_params& p, float* out, cudaStream_t stream) {
+                          const isi_melif_params& p, float* out, cudaStream_t stream, int bulk_ok) {
   const MelifSmem L = melif_smem_layout<NFFT, FB>(p.hop, (int)sizeof(S));
   if (L.total > 227 * 1024) return ISI_ERR_UNSUPPORTED;
   cudaError_t e = cudaFuncSetAttribute(melif_kernel<NFFT, FB, NT, MEL, S>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
   if (e != cudaSuccess) return (int)e;
-  // the bulk copy needs 16-byte aligned global addresses and sizes
-  constexpr int kPer16 = 16 / (int)sizeof(S);
-  const int bulk_ok = (n_samples % kPer16 == 0) && (p.hop % kPer16 == 0) &&
-                      (p.pad_left % kPer16 == 0) && ((uintptr_t)audio % 16 == 0);
   int seg_frames, n_segs;
-  choose_segments(n_notes, p.n_frames, FB, NT >= 512 ? 2 : 3, &seg_frames, &n_segs);
+  choose_segments(n_notes, p.n_frames, FB, melif_ctas_per_sm(NT), &seg_frames, &n_segs);
   if (n_notes * n_segs > 0x7fffffff) return ISI_ERR_SHAPE;
   melif_kernel<NFFT, FB, NT, MEL, S><<<(unsigned)(n_notes * n_segs), NT, L.total, stream>>>(
       audio, n_samples, p, out, bulk_ok, seg_frames, n_segs);
@@ -343,15 +519,40 @@ static int launch_melif_t(const S* audio, int64_t n_notes, int64_t n_samples,
   return ISI_OK;
 }
 
+template <bool MEL, typename S>
+static int launch_melif_ws(const S* audio, int64_t n_notes, int64_t n_samples,
+                           const isi_melif_params& p, float* out, cudaStream_t stream) {
+  constexpr int FB = 8;
+  const MelifSmem L = melif_smem_layout<2048, FB>(p.hop, (int)sizeof(S), 2);
+  cudaError_t e = cudaFuncSetAttribute(melif_ws_kernel<FB, MEL, S>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
+  if (e != cudaSuccess) return (int)e;
+  int seg_frames, n_segs;
+  choose_segments(n_notes, p.n_frames, FB, 1, &seg_frames, &n_segs);
+  if (n_notes * n_segs > 0x7fffffff) return ISI_ERR_SHAPE;
+  melif_ws_kernel<FB, MEL, S><<<(unsigned)(n_notes * n_segs), kWsThreads, L.total, stream>>>(
+      audio, n_samples, p, out, seg_frames, n_segs);
+  ISI_LAUNCH_CHECK();
+  return ISI_OK;
+}
+
 template <typename S>
 static int launch_melif_s(const S* audio, int64_t n_notes, int64_t n_samples,
                           const isi_melif_params& p, float* out, cudaStream_t stream) {
+  // the bulk copy needs 16-byte aligned global addresses and sizes
+  constexpr int kPer16 = 16 / (int)sizeof(S);
+  const int bulk_ok = (n_samples % kPer16 == 0) && (p.hop % kPer16 == 0) &&
+                      (p.pad_left % kPer16 == 0) && ((uintptr_t)audio % 16 == 0);
+  if (p.n_fft == 2048 && bulk_ok && p.hop % 2 == 0 && p.hop <= 2048 &&
+      melif_smem_layout<2048, 8>(p.hop, (int)sizeof(S), 2).total <= 227 * 1024)
+    return p.use_mel ? launch_melif_ws<true, S>(audio, n_notes, n_samples, p, out, stream)
+                     : launch_melif_ws<false, S>(audio, n_notes, n_samples, p, out, stream);
 #define ISI_MELIF_CASE(N, FB, NT)                                                               \
   case N:                                                                                     \
-    return p.use_mel ? launch_melif_t<N, FB, NT, true, S>(audio, n_notes, n_samples, p, out, stream) \
-                     : launch_melif_t<N, FB, NT, false, S>(audio, n_notes, n_samples, p, out, stream);
+    return p.use_mel ? launch_melif_t<N, FB, NT, true, S>(audio, n_notes, n_samples, p, out, stream, bulk_ok) \
+                     : launch_melif_t<N, FB, NT, false, S>(audio, n_notes, n_samples, p, out, stream, bulk_ok);
   switch (p.n_fft) {
-    ISI_MELIF_CASE(2048, 8, 512)
+    ISI_MELIF_CASE(2048, 8, 256)
     ISI_MELIF_CASE(1024, 4, 128)
     ISI_MELIF_CASE(512, 4, 64)
     default: return ISI_ERR_UNSUPPORTED;

@@ -93,7 +93,7 @@ static void emulate(const float* spec, int64_t n_notes, int hop, int pad_left, i
           for (int j = 0; j < 64; ++j) ifft_pass1_load<P>(j, z, &v[j * P::R1]);
           for (int j = 0; j < 64; ++j) ifft_pass1_store<P>(j, &v[j * P::R1], twm.data(), z);
           for (int j = 0; j < 64; ++j) fft_pass2<P>(j, twm.data(), z);
-          std::vector<Pass3Regs<P>> regs(64);
+          std::vector<Pass3Regs<P, cpx>> regs(64);
           for (int j = 0; j < 64; ++j) fft_pass3_load<P>(j, z, regs[j]);
           for (int j = 0; j < 64; ++j) fft_pass3_store<P>(j, regs[j], z);
         }
