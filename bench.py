@@ -133,21 +133,35 @@ def pcm_to_float(pcm: torch.Tensor) -> torch.Tensor:
 
 
 # --------------------------------------------------------------------------- reference arm
-def cpu_encode_path(threads: int):
-    """The oracle port of the path: torch-CPU front-end restatement, the same conv wiring on
-    the CPU, the oracle quantiser.  Returns fn(audio[B,T]) -> (id_t, id_b)."""
-    from interactive_spectrogram_inpainting_b200.vqvae.vqvae import VQVAE
+def cpu_encode_path(threads: int, state_dict=None):
+    """The reference's CPU implementation of the path: the front-end restatement (torch CPU;
+    the reference's own front end lives in GANsynth_pytorch, which is not installable here) ->
+    the UNMODIFIED reference ``VQVAE.encode`` + ``QuantizedBottleneck`` (vqvae.py:251-278,
+    bottleneck.py:53-104) imported from /root/reference or its staged copy baseline/_ref.  If
+    neither exists, this repo's CPU wiring with the oracle quantiser (kind "port").
+    Returns (fn(audio[B,T]) -> (id_t, id_b), model, kind)."""
     from oracle import frontend_oracle as fo
-    from oracle import quantizer_oracle as qo
+    from oracle import parity
     torch.set_num_threads(threads)
-    torch.manual_seed(0)
-    model = VQVAE(**MODEL_KW, bottleneck_cls=qo.OracleBottleneck).eval()
+    if state_dict is None:
+        from interactive_spectrogram_inpainting_b200.vqvae.vqvae import VQVAE
+        torch.manual_seed(0)
+        state_dict = VQVAE(**MODEL_KW).state_dict()
+    model, kind = parity.reference_or_port_model(state_dict, MODEL_KW)
     cfg = fo.FrontEndConfig()
 
     def run(audio):
         with torch.no_grad():
-            return model.encode_codes(fo.to_spectrogram(audio, cfg))
-    return run, model
+            out = model.encode(fo.to_spectrogram(audio, cfg))
+            return out[3], out[4]
+    return run, model, kind
+
+
+def cpu_baseline_description(kind: str, cores: int) -> str:
+    enc = ("the unmodified reference VQVAE.encode + QuantizedBottleneck (vqvae.py:251-278, bottleneck.py:53-104)"
+           if kind == "reference" else "this repo's CPU wiring of the conv encoder + the oracle quantiser")
+    return (f"torch-CPU front-end restatement (GANsynth_pytorch, the reference's own, is absent) + {enc}, "
+            f"{cores} threads")
 
 
 def time_cpu(run, audio, steps, warmup):
@@ -165,7 +179,7 @@ def reference_arm(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    run, _ = cpu_encode_path(cores)
+    run, _, kind = cpu_encode_path(cores)
     sample = 16
     audio = pcm_to_float(to_pcm16(make_audio(sample)))     # the values the B200 arm sees
     value, per_step = time_cpu(run, audio, args.steps, args.warmup)
@@ -177,10 +191,9 @@ def reference_arm(args):
         "config": {"workload": "extract_code cfg2: 4 s/16 kHz notes -> mel-IF -> VQ-VAE-2 "
                                "encode (bottom 16 / top 2, K=512, D=64) -> top+bottom codes",
                    "notes_per_step": sample},
-        "cpu_baseline": {"value": value, "unit": "notes/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample} notes per step x {args.steps} steps, torch-CPU "
-                                   f"oracle port (front-end restatement + conv encoder + "
-                                   f"oracle quantiser), {cores} threads"},
+        "cpu_baseline": {"value": value, "unit": "notes/s", "cores": cores, "kind": kind,
+                         "sample": f"{sample} notes per step x {args.steps} steps: "
+                                   + cpu_baseline_description(kind, cores)},
         "e2e": {"value": value, "unit": "notes/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -494,18 +507,17 @@ def b200_arm(args):
 
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        run, cpu_model = cpu_encode_path(cores)
-        cpu_model.load_state_dict(model.state_dict())
+        run, _, kind = cpu_encode_path(cores, {k: v.detach().cpu().contiguous()
+                                               for k, v in model.state_dict().items()})
         sample = 16
         cpu_audio = host_by_format["f32"][:sample].clone()
         # size the sample to ~10-20 s of CPU work
         v1, per = time_cpu(run, cpu_audio, 1, 1)
         reps = max(2, min(50, int(12.0 / max(per, 1e-3))))
         v, per = time_cpu(run, cpu_audio, reps, 0)
-        line["cpu_baseline"] = {"value": v, "unit": "notes/s", "cores": cores, "kind": "port",
-                                "sample": f"{sample} notes x {reps} passes of the torch-CPU oracle "
-                                          f"port (front-end restatement + conv encoder + oracle "
-                                          f"quantiser), {cores} threads"}
+        line["cpu_baseline"] = {"value": v, "unit": "notes/s", "cores": cores, "kind": kind,
+                                "sample": f"{sample} notes x {reps} passes: "
+                                          + cpu_baseline_description(kind, cores)}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -105,7 +105,9 @@ vq_assign_simt_kernel(const float* __restrict__ x, isi_rows_layout lay, int64_t 
     }
     int64_t row = row0 + 4 * rg + i;
     if (cg == 0 && row < n_rows) {
-      out_index[row] = best_i[i];
+      // a row of NaN / Inf never wins a comparison: code 0, like torch's (-dist).max(1) on an
+      // all-NaN row (bottleneck.py:61), never an out-of-range index
+      out_index[row] = best_i[i] == 0x7fffffff ? 0 : best_i[i];
       if (out_score) out_score[row] = best_s[i];
     }
   }

@@ -11,6 +11,7 @@ transaction (the reference opens one per note) when the ``lmdb`` package is inst
 in this image, where ``save_shard`` writes an ``.npz`` per rank instead.
 """
 from collections import namedtuple
+from collections.abc import Mapping
 from typing import Callable, Iterable, Iterator, List, Optional, Sequence, Tuple
 
 import pickle
@@ -24,29 +25,67 @@ from .utils import distributed as dist_utils
 CodeRow = namedtuple('CodeRow', ['top', 'bottom', 'attributes', 'filename'])
 
 
+def _split_item(item):
+    """A source item is ``(audio, names)`` or ``(audio, names, attributes)`` with ``attributes``
+    a mapping {attribute name: per-note values} -- the label-encoded categorical fields the
+    reference's loader yields next to each batch (extract_code.py:62-63,
+    ``--categorical_fields`` :104-105)."""
+    if len(item) == 2:
+        return item[0], item[1], None
+    audio, names, attributes = item
+    return audio, names, (attributes if attributes else None)
+
+
+def _row_attributes(attributes, index: int) -> dict:
+    """``dict(zip(attribute_names, attributes))`` of extract_code.py:73-74 for one note: 0-dim
+    int64 tensors, because the reference's reader calls ``.view(1)`` on them
+    (utils/datasets/lmdb_dataset.py:84-86)."""
+    if attributes is None:
+        return {}
+    return {name: torch.as_tensor(values[index]).detach().cpu().reshape(()).clone()
+            for name, values in attributes.items()}
+
+
+def _unpack_batch(batch):
+    """A loader batch is ``(spec, names)``, ``(spec, names, attributes)`` or the reference
+    loader's ``(spec, *categorical, attributes_batch)`` with ``attributes_batch['note_str']``
+    the names and ``attributes_batch['categorical_fields']`` (ours) the field names."""
+    if isinstance(batch[-1], Mapping) and 'note_str' in batch[-1]:
+        info = batch[-1]
+        fields = list(info.get('categorical_fields', range(len(batch) - 2)))
+        return batch[0], info['note_str'], dict(zip(fields, batch[1:-1])) or None
+    return _split_item(batch)
+
+
 class SpectrogramBatches:
     """On-GPU wav -> spectrogram batching with the call shape of the reference's
     ``WavToSpectrogramDataLoader`` (extract_code.py:199-206): iterating yields
     ``(spectrogram_batch, names)`` with the spectrograms computed on the helper's device.
 
-    ``source`` yields ``(audio [b, T] float tensor on any device, names)``."""
+    ``source`` yields ``(audio [b, T] float tensor on any device, names)`` or ``(audio, names,
+    attributes)`` (see ``_split_item``).  With ``reference_protocol`` a batch comes out as the
+    reference's loader yields it (extract_code.py:62-63): ``(spectrogram_batch,
+    *categorical_attribute_tensors, attributes_batch)`` with ``attributes_batch['note_str']`` the
+    names; otherwise ``(spectrogram_batch, names[, attributes])``."""
 
     def __init__(self, source: Iterable[Tuple[torch.Tensor, Sequence[str]]], spectrograms_helper,
-                 device: torch.device, transform: Optional[Callable] = None, prefetch: bool = True):
+                 device: torch.device, transform: Optional[Callable] = None, prefetch: bool = True,
+                 reference_protocol: bool = False):
         self.source, self.helper, self.device, self.transform = source, spectrograms_helper, device, transform
         self.prefetch = prefetch
+        self.reference_protocol = reference_protocol
         self._side = None        # one copy stream per loader, so its allocator pool is reused
         # the helper may write 2x2 space-to-depth blocks (see SpectrogramsHelper); the encoder
         # has to be told (extract_codes reads this attribute)
         self.space_to_depth = bool(getattr(spectrograms_helper, "space_to_depth", False))
 
     def _upload(self, item, stream):
-        audio, names = item
+        audio, names, attributes = _split_item(item)
         with torch.cuda.stream(stream):
             dev_audio = audio.to(self.device, non_blocking=True)
             ready = torch.cuda.Event()
             ready.record(stream)
-        return dev_audio, names, ready
+        return dev_audio, names, attributes, ready
 
     def __iter__(self) -> Iterator[Tuple[torch.Tensor, Sequence[str]]]:
         """With ``prefetch`` the host->device copy of batch i+1 (pinned source memory) runs
@@ -61,7 +100,7 @@ class SpectrogramBatches:
             pending = self._upload(item, side)
             break
         while pending is not None:
-            dev_audio, names, ready = pending
+            dev_audio, names, attributes, ready = pending
             pending = None
             for item in it:
                 pending = self._upload(item, side)
@@ -71,7 +110,14 @@ class SpectrogramBatches:
             spec = self.helper.to_spectrogram(dev_audio)
             if self.transform is not None:
                 spec = self.transform(spec)
-            yield spec, names
+            if self.reference_protocol:
+                fields = list(attributes) if attributes else []
+                yield (spec, *[torch.as_tensor(attributes[f]) for f in fields],
+                       {'note_str': list(names), 'categorical_fields': fields})
+            elif attributes is None:
+                yield spec, names
+            else:
+                yield spec, names, attributes
 
 
 def synthetic_source(n_notes: int, batch: int, rank: int = 0, world_size: int = 1,
@@ -108,18 +154,19 @@ def extract_codes(loader: Iterable[Tuple[torch.Tensor, Sequence[str]]], model,
         return (pair[0][:id_t.numel()].view(id_t.shape), pair[1][:id_b.numel()].view(id_b.shape))
 
     def flush(item):
-        host_t, host_b, names, done = item
+        host_t, host_b, names, attributes, done = item
         done.synchronize()
         tops, bottoms = host_t.numpy().copy(), host_b.numpy().copy()
-        batch_rows = [CodeRow(top=t, bottom=b, attributes={}, filename=n)
-                      for t, b, n in zip(tops, bottoms, names)]
+        batch_rows = [CodeRow(top=t, bottom=b, attributes=_row_attributes(attributes, i), filename=n)
+                      for i, (t, b, n) in enumerate(zip(tops, bottoms, names))]
         if sink is not None:
             sink(batch_rows)
         rows.extend(batch_rows)
 
     model.eval()
     s2d = bool(getattr(loader, "space_to_depth", False))
-    for step, (spec, names) in enumerate(loader):
+    for step, batch in enumerate(loader):
+        spec, names, attributes = _unpack_batch(batch)
         if hasattr(model, "encode_codes"):
             id_t, id_b = model.encode_codes(spec, space_to_depth=True) if s2d else model.encode_codes(spec)
         else:
@@ -134,7 +181,7 @@ def extract_codes(loader: Iterable[Tuple[torch.Tensor, Sequence[str]]], model,
         done.record()
         if pending is not None:          # the previous batch's copy overlaps this batch's compute
             flush(pending)
-        pending = (host_t, host_b, list(names), done)
+        pending = (host_t, host_b, list(names), attributes, done)
     if pending is not None:
         flush(pending)
     return rows
@@ -179,7 +226,7 @@ class CodeExtractor:
         (one CUDA-graph replay per batch when ``cuda_graph``) --D2H--> rows
 
     ``run(source)`` takes what ``SpectrogramBatches`` takes: an iterable of ``(audio [b, T],
-    names)``.  Graphs are captured per batch shape on first use and kept for later calls; a
+    names)`` or ``(audio, names, attributes)``.  Graphs are captured per batch shape on first use and kept for later calls; a
     shape whose capture fails (or ``cuda_graph=False``) runs the same calls eagerly.  The model
     must be this repo's ``VQVAE`` in eval mode with fixed weights."""
 
@@ -219,18 +266,22 @@ class CodeExtractor:
         rows: List[CodeRow] = []
 
         def upload(item, slot):
-            audio, names = item
+            audio, names, attributes = _split_item(item)
             buf = self._dev_audio[slot]
-            if buf is None or buf.shape != audio.shape or buf.dtype != audio.dtype:
-                buf = torch.empty(audio.shape, dtype=audio.dtype, device=self.device)
-                self._dev_audio[slot] = buf
             with torch.cuda.stream(side):
+                if buf is None or buf.shape != audio.shape or buf.dtype != audio.dtype:
+                    # a new block may be memory the main stream's previous step has just freed
+                    # and is still reading: the copy below must not overtake that step
+                    side.wait_stream(main)
+                    buf = torch.empty(audio.shape, dtype=audio.dtype, device=self.device)
+                    buf.record_stream(main)
+                    self._dev_audio[slot] = buf
                 if consumed[slot] is not None:
                     side.wait_event(consumed[slot])
                 buf.copy_(audio, non_blocking=True)
                 ready = torch.cuda.Event()
                 ready.record(side)
-            return buf, list(names), ready
+            return buf, list(names), attributes, ready
 
         def host_pair(slot, id_t, id_b):
             pair = self._host_codes[slot]
@@ -241,11 +292,11 @@ class CodeExtractor:
             return pair
 
         def flush(item):
-            host_t, host_b, names, done = item
+            host_t, host_b, names, attributes, done = item
             done.synchronize()
             tops, bottoms = host_t.numpy().copy(), host_b.numpy().copy()
-            batch_rows = [CodeRow(top=t, bottom=b, attributes={}, filename=n)
-                          for t, b, n in zip(tops, bottoms, names)]
+            batch_rows = [CodeRow(top=t, bottom=b, attributes=_row_attributes(attributes, i), filename=n)
+                          for i, (t, b, n) in enumerate(zip(tops, bottoms, names))]
             if sink is not None:
                 sink(batch_rows)
             rows.extend(batch_rows)
@@ -255,7 +306,7 @@ class CodeExtractor:
         uploaded = upload(first, 0) if first is not None else None
         pending, step = None, 0
         while uploaded is not None:
-            audio, names, ready = uploaded
+            audio, names, attributes, ready = uploaded
             slot = step % 2
             nxt = next(it, None)
             uploaded = upload(nxt, 1 - slot) if nxt is not None else None
@@ -270,7 +321,7 @@ class CodeExtractor:
             done.record(main)
             if pending is not None:      # the previous batch's copy overlaps this batch's compute
                 flush(pending)
-            pending = (host_t, host_b, names, done)
+            pending = (host_t, host_b, names, attributes, done)
             step += 1
         if pending is not None:
             flush(pending)
@@ -332,6 +383,15 @@ def write_lmdb(rows: Sequence[CodeRow], env, db=None) -> int:
         for key, value in records:
             txn.put(key, value)
     return len(records)
+
+
+def write_label_encoders(env, label_encoders) -> None:
+    """``extract_code.py:52-57``: the label encoders ride along in the database's unnamed
+    default table under the key ``label_encoders`` (master process only, like the reference)."""
+    if not dist_utils.is_master_process():
+        return
+    with env.begin(write=True) as txn:
+        txn.put('label_encoders'.encode('utf-8'), pickle.dumps(label_encoders))
 
 
 def save_shard(rows: Sequence[CodeRow], path) -> None:

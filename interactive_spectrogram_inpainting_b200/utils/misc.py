@@ -19,3 +19,10 @@ def get_spectrograms_helper(**kwargs) -> SpectrogramsHelper:
         return SpectrogramsHelper(**args)
     args.update({ctor: kwargs[key] for key, ctor in _MEL.items()})
     return MelSpectrogramsHelper(**args)
+
+
+def expand_path(p):
+    """``utils/misc.py:32-33`` of the reference: user-expanded absolute path (the reference's
+    scripts import it from this module)."""
+    import pathlib
+    return pathlib.Path(p).expanduser().absolute()

@@ -250,3 +250,20 @@ class QuantizedBottleneck(nn.Module):
             self.embed.data_ptr(), self.dim, self.n_embed, float(self.decay), float(self.eps),
             _lib.stream_ptr(stats.device))
         self._cache.invalidate()
+
+
+class UnquantizedBottleneck(QuantizedBottleneck):
+    """``bottleneck.py:107-119`` of the reference (selected by ``disable_quantization``,
+    vqvae.py:159-160): the features pass through unquantised; no indices, infinite perplexity,
+    zero commitment term.  Keeps the codebook buffers so that checkpoints interchange."""
+
+    def forward(self, input: torch.Tensor):
+        diff = torch.zeros((1,), dtype=input.dtype, device=input.device)
+        perplexity = torch.as_tensor([math.inf], device=input.device)
+        return input, diff, None, perplexity
+
+    def assign(self, input: torch.Tensor):
+        raise NotImplementedError("an unquantised bottleneck has no codes")
+
+    def embed_code(self, embed_ind):
+        raise NotImplementedError

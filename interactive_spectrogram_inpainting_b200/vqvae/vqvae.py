@@ -21,7 +21,7 @@ import torch
 from torch import nn
 
 from .. import _lib
-from .bottleneck import QuantizedBottleneck
+from .bottleneck import QuantizedBottleneck, UnquantizedBottleneck
 
 # channel plan of the strided stages in quarters of `channel` (encoder_decoder.py:52-116)
 _DOWN_PLAN = {16: (1, 2, 3, 4), 8: (2, 2, 4), 4: (2, 4), 2: (2,)}
@@ -290,10 +290,53 @@ class VQVAE(nn.Module):
                  corruption_weights: Mapping[str, Optional[Sequence[float]]] = {'top': None,
                                                                              'bottom': None},
                  adapt_quantized_durations: bool = True,
-                 bottleneck_cls: Type[nn.Module] = QuantizedBottleneck, **unused):
+                 output_activation_type: Optional[str] = None,
+                 output_spectrogram_min_magnitude: Optional[float] = None,
+                 decoder_output_activation: Optional[nn.Module] = None,
+                 normalizer_statistics: Optional[Mapping[str, float]] = None,
+                 disable_quantization: bool = False,
+                 restarts_usage_threshold: float = 1.,
+                 encoders=None, decoders=None,
+                 bottleneck_cls: Optional[Type[nn.Module]] = None):
+        """Every keyword of the reference constructor (vqvae.py:66-98) is named; the ones this
+        wiring cannot honour raise instead of being dropped:
+
+        * ``normalizer_statistics`` (vqvae.py:218-226): GANSynth's per-channel affine,
+          ``{'s_a','s_b','p_a','p_b'}`` with ``normalised = x * a + b`` (``DataNormalizer`` lives
+          in GANsynth_pytorch, which the reference does not vendor -- any other key set raises).
+          ``encode`` normalises (vqvae.py:254-255), ``decode`` denormalises (vqvae.py:297-299).
+        * ``output_spectrogram_min_magnitude`` (vqvae.py:238-241): the masked-phase output
+          transform, IF := 0 where the log-magnitude is below the threshold (vqvae.py:300-301).
+        * ``output_activation_type='threshold_gelu'`` (vqvae.py:228-236) only builds a module the
+          reference never calls; accepted (with the reference's assert) and equally unused.
+        * ``disable_quantization`` selects ``UnquantizedBottleneck`` (vqvae.py:159-160).
+        * ``restarts_usage_threshold != 1`` (``QuantizedBottleneckWithRestarts``, built on the
+          un-vendored ``discretization`` package), custom ``encoders`` / ``decoders`` (fastai /
+          xresnet stacks), ``decoder_output_activation`` and ``groups != 1``: NotImplementedError.
+        """
         super().__init__()
         if groups != 1:
             raise NotImplementedError("groups != 1")
+        if decoder_output_activation is not None:
+            raise NotImplementedError("decoder_output_activation (vqvae.py:99-100 raises too)")
+        if encoders is not None or decoders is not None:
+            raise NotImplementedError("custom encoders / decoders (fastai stacks) are out of scope")
+        if restarts_usage_threshold != 1.:
+            raise NotImplementedError("QuantizedBottleneckWithRestarts needs the un-vendored "
+                                      "`discretization` package; restarts_usage_threshold must be 1")
+        if output_activation_type not in (None, 'threshold_gelu'):
+            raise AssertionError("Unexpected output activation type")          # vqvae.py:235-236
+        if output_activation_type == 'threshold_gelu':
+            assert output_spectrogram_min_magnitude is not None                  # vqvae.py:229
+        if normalizer_statistics is not None:
+            normalizer_statistics = dict(getattr(normalizer_statistics, '__dict__', normalizer_statistics))
+            if set(normalizer_statistics) != {'s_a', 's_b', 'p_a', 'p_b'}:
+                raise NotImplementedError(
+                    "normalizer_statistics keys %s: only GANSynth's {'s_a','s_b','p_a','p_b'} affine "
+                    "is implemented (GANsynth_pytorch.normalizer is not vendored by the reference)"
+                    % sorted(normalizer_statistics))
+        if bottleneck_cls is None:
+            bottleneck_cls = UnquantizedBottleneck if disable_quantization else QuantizedBottleneck
         self._instantiation_parameters = dict(
             in_channel=in_channel, num_hidden_channels=num_hidden_channels,
             n_res_block=n_res_block, num_residual_channels=num_residual_channels,
@@ -301,7 +344,21 @@ class VQVAE(nn.Module):
             use_local_kernels=use_local_kernels, resolution_factors=dict(resolution_factors),
             embeddings_initial_variance=embeddings_initial_variance,
             corruption_weights=dict(corruption_weights),
-            adapt_quantized_durations=adapt_quantized_durations)
+            adapt_quantized_durations=adapt_quantized_durations,
+            output_activation_type=output_activation_type,
+            output_spectrogram_min_magnitude=output_spectrogram_min_magnitude,
+            decoder_output_activation=None, normalizer_statistics=normalizer_statistics,
+            disable_quantization=disable_quantization, restarts_usage_threshold=restarts_usage_threshold)
+        self.output_activation_type = output_activation_type
+        self.output_spectrogram_min_magnitude = output_spectrogram_min_magnitude
+        self.normalizer_statistics = normalizer_statistics
+        self.use_gansynth_normalization = normalizer_statistics is not None      # vqvae.py:215-216
+        if normalizer_statistics is not None:
+            st = normalizer_statistics
+            self.register_buffer("_norm_scale", torch.tensor([st['s_a'], st['p_a']], dtype=torch.float32)
+                                 .view(1, 2, 1, 1), persistent=False)
+            self.register_buffer("_norm_bias", torch.tensor([st['s_b'], st['p_b']], dtype=torch.float32)
+                                 .view(1, 2, 1, 1), persistent=False)
         self.in_channel, self.embed_dim = in_channel, embed_dim
         self.resolution_factors = dict(resolution_factors)
         self.adapt_quantized_durations = adapt_quantized_durations
@@ -361,6 +418,7 @@ class VQVAE(nn.Module):
     def encode(self, input: torch.Tensor, space_to_depth: bool = False):
         """``space_to_depth``: ``input`` is the 2x2-blocked spectrogram ``[B, 4C, F/2, T/2]`` that
         ``SpectrogramsHelper(space_to_depth=True)`` writes; same result, faster first conv."""
+        input = self._normalize(input, space_to_depth)
         enc_b = self.enc_b(input, space_to_depth=space_to_depth)
         enc_t = self.enc_t(enc_b)
 
@@ -379,15 +437,55 @@ class VQVAE(nn.Module):
         if self.training or not hasattr(self.quantize_b, "assign"):
             out = self.encode(input, space_to_depth=space_to_depth)
             return out[3], out[4]
+        input = self._normalize(input, space_to_depth)
         enc_b = self.enc_b(input, space_to_depth=space_to_depth)
         enc_t = self.enc_t(enc_b)
         quant_t, _, id_t, _ = self.quantize_t(self._prequant_top(enc_t))
         id_b = self.quantize_b.assign(self._prequant_bottom(quant_t.permute(0, 3, 1, 2), enc_b))
         return id_t, id_b
 
-    # -- vqvae.py:280-295 --
+    # -- vqvae.py:254-255: DataNormalizer.normalize, unless the front end already applied it --
+    normalizes_input = True
+
+    def _normalize(self, input: torch.Tensor, space_to_depth: bool = False) -> torch.Tensor:
+        if not (self.use_gansynth_normalization and self.normalizes_input):
+            return input
+        if space_to_depth:
+            raise ValueError("space-to-depth input: let the front end apply the normaliser "
+                             "(front_end_knobs()) and set model.normalizes_input = False")
+        return input * self._norm_scale + self._norm_bias
+
+    def front_end_knobs(self) -> dict:
+        """The per-channel affine of ``encode`` as ``SpectrogramsHelper`` keywords: constructing the
+        helper with ``output_affine=knobs['output_affine']`` fuses the normaliser into the front-end
+        kernel's epilogue (then set ``model.normalizes_input = False``)."""
+        if not self.use_gansynth_normalization:
+            return {}
+        st = self.normalizer_statistics
+        return {"output_affine": ((st['s_a'], st['s_b']), (st['p_a'], st['p_b']))}
+
+    def inverse_front_end_knobs(self) -> dict:
+        """``post_process`` as keywords of the inverse front end (``to_audio``'s fused input
+        affine): spectrogram = (decoder output - b) / a."""
+        if not self.use_gansynth_normalization:
+            return {}
+        st = self.normalizer_statistics
+        return {"input_affine": ((1.0 / st['s_a'], -st['s_b'] / st['s_a']),
+                                 (1.0 / st['p_a'], -st['p_b'] / st['p_a']))}
+
+    # -- vqvae.py:280-302 --
     def decode(self, quant_t: torch.Tensor, quant_b: torch.Tensor):
-        return self.dec(torch.cat([self.upsample_top_to_bottom(quant_t), quant_b], 1))
+        dec = self.dec(torch.cat([self.upsample_top_to_bottom(quant_t), quant_b], 1))
+        return self.post_process(dec)
+
+    def post_process(self, dec: torch.Tensor) -> torch.Tensor:
+        """vqvae.py:297-302: denormalise, then the masked-phase output transform."""
+        if self.use_gansynth_normalization:
+            dec = (dec - self._norm_bias) / self._norm_scale
+        if self.output_spectrogram_min_magnitude is not None:
+            keep = (dec[:, :1] >= self.output_spectrogram_min_magnitude).to(dec.dtype)
+            dec = torch.cat([dec[:, :1], dec[:, 1:2] * keep, dec[:, 2:]], 1)
+        return dec
 
     def decode_code(self, code_t: torch.Tensor, code_b: torch.Tensor):
         quant_t = self.quantize_t.embed_code(code_t).permute(0, 3, 1, 2)

@@ -99,6 +99,9 @@ for s in $steps; do
       timeout 300 python __graft_entry__.py smoke 2>&1 | tail -2 ;;
     probe)
       timeout 120 ./tools/umma_probe.bin 2>&1 | tee gpurun_out/umma_probe_$tag.log ;;
+    e2e_parity)
+      timeout 600 python -m pytest tests/test_gpu_e2e_parity.py -x -q -s 2>&1 | tail -30 > gpurun_out/pytest_e2e_parity_$tag.log
+      tail -12 gpurun_out/pytest_e2e_parity_$tag.log ;;
     all_tests)
       timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -40 > gpurun_out/pytest_all_$tag.log
       tail -5 gpurun_out/pytest_all_$tag.log ;;

@@ -1,0 +1,87 @@
+"""End-to-end GPU parity of the extracted code maps against the CPU checker, bottom level
+included (reference path: extract_code.py:62-69 -> vqvae.py:251-278 -> bottleneck.py:55-61).
+
+The product path is the one bench.py's e2e leg times: ``extract.CodeExtractor`` over pinned
+int16 PCM batches, front end writing 2x2 space-to-depth blocks, channels_last conv stack, the
+tensor-core projection and search kernels, one CUDA-graph replay per batch.  The checker is
+the FP64-evaluated front-end oracle -> the UNMODIFIED reference ``VQVAE`` on the CPU (from
+/root/reference or the staged baseline/_ref copy; this repo's CPU wiring with the oracle
+quantiser if neither exists) with identical weights.
+
+No agreement percentage is asserted: every differing code must be explained by the FP64
+distances on the checker's features and the measured feature difference
+(oracle/parity.py::explain_differences); the counts are printed."""
+import pytest
+import torch
+
+from interactive_spectrogram_inpainting_b200 import extract
+from interactive_spectrogram_inpainting_b200.utils import synthetic
+from interactive_spectrogram_inpainting_b200.utils.spectrograms_helper import MelSpectrogramsHelper
+from interactive_spectrogram_inpainting_b200.vqvae import vqvae as vq
+from oracle import frontend_oracle as fo
+from oracle import parity
+
+pytestmark = pytest.mark.gpu
+DEV = torch.device("cuda:0")
+MODEL_KW = dict(in_channel=2, resolution_factors={"bottom": 16, "top": 2}, adapt_quantized_durations=False)
+PCM_SCALE = 1.0 / 32768.0
+
+
+@pytest.fixture
+def fp32_convs():
+    old = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32 = old
+
+
+def test_extracted_codes_match_the_cpu_reference_with_near_tie_accounting(fp32_convs, capsys):
+    n_notes = 32       # 4096 top rows: isi_vq_assign dispatches the tcgen05 pair kernel
+    torch.manual_seed(11)
+    model = vq.VQVAE(**MODEL_KW).to(DEV).eval().to(memory_format=torch.channels_last)
+    pcm = (synthetic.synthetic_notes(n_notes) * 32767.0).round().clamp(-32768, 32767).to(torch.int16)
+    audio = pcm.float() * PCM_SCALE                     # the values both sides see
+
+    # ---- product path ----
+    helper = MelSpectrogramsHelper(space_to_depth=True).to(DEV)
+    helper.pcm_scale = PCM_SCALE
+    names = [f"n{i:03d}" for i in range(n_notes)]
+    batches = [(pcm[i:i + 16].pin_memory(), names[i:i + 16]) for i in range(0, n_notes, 16)]
+    extractor = extract.CodeExtractor(helper, model, DEV, cuda_graph=True)
+    rows = extractor.run(batches)
+    assert extractor.graph_failures == [] and [r.filename for r in rows] == names
+    got_t = torch.stack([torch.from_numpy(r.top) for r in rows])
+    got_b = torch.stack([torch.from_numpy(r.bottom) for r in rows])
+    assert got_t.shape == (n_notes, 32, 4) and got_b.shape == (n_notes, 64, 8)
+
+    # ---- checker: FP64 front-end oracle -> reference VQVAE on the CPU ----
+    state = {k: v.detach().cpu().contiguous() for k, v in model.state_dict().items()}
+    cpu_model, kind = parity.reference_or_port_model(state, MODEL_KW)
+    spec_cpu = fo.to_spectrogram(audio.double(), fo.FrontEndConfig()).float()
+    with torch.no_grad():
+        feat_t, want_t, feat_b, want_b = parity.encode_with_features(cpu_model, spec_cpu)
+
+    # ---- the product's own pre-quantiser features, for the feature difference ----
+    plain = MelSpectrogramsHelper().to(DEV)
+    with torch.no_grad():
+        spec_gpu = plain.to_spectrogram(audio.to(DEV))
+        gfeat_t, gid_t, gfeat_b, gid_b = parity.encode_with_features(model, spec_gpu.contiguous(
+            memory_format=torch.channels_last))
+    embed_t, embed_b = model.quantize_t.embed.cpu(), model.quantize_b.embed.cpu()
+
+    rep_t = parity.explain_differences(feat_t, got_t, want_t, embed_t, gfeat_t.cpu() - feat_t)
+    # bottom features depend on the top codes through dec_t: compare the bottom maps of the
+    # notes whose top map is identical (a top near-tie flip legitimately changes what follows)
+    same_top = ((got_t == want_t) & (gid_t.cpu() == want_t)).reshape(n_notes, -1).all(1)
+    rep_b = parity.explain_differences(feat_b[same_top], got_b[same_top], want_b[same_top], embed_b,
+                                       (gfeat_b.cpu() - feat_b)[same_top])
+    with capsys.disabled():
+        print(f"\n[e2e parity, checker = {kind} VQVAE] top: {rep_t}")
+        print(f"[e2e parity] bottom ({int(same_top.sum())}/{n_notes} notes with identical top maps): {rep_b}")
+        print(f"[e2e parity] max |feature difference| top {float((gfeat_t.cpu() - feat_t).abs().max()):.3g} "
+              f"bottom {float((gfeat_b.cpu() - feat_b)[same_top].abs().max()):.3g}")
+    assert rep_t.unexplained == 0, str(rep_t)
+    assert rep_b.unexplained == 0, str(rep_b)
+    assert int(same_top.sum()) >= n_notes // 2       # top flips are rare events, not the rule
+    # and the feature difference itself is small: the front end + conv stack agree to FP32 noise
+    assert float((gfeat_t.cpu() - feat_t).abs().max()) < 5e-2 * float(feat_t.abs().max())

@@ -93,3 +93,92 @@ def test_space_to_depth_first_conv_is_the_same_convolution():
     assert torch.equal(a[3], b[3]) and torch.equal(a[4], b[4])
     with pytest.raises(ValueError):
         mod.Encoder(2, 16, 0, 4, 4, use_local_kernels=True)(x, space_to_depth=True)
+
+
+def test_every_reference_constructor_keyword_is_named_or_refused():
+    """vqvae.py:66-98: nothing the reference dumps into model_parameters.json is dropped
+    silently -- it is honoured, or the constructor raises."""
+    import inspect
+    ours = set(inspect.signature(VQVAE.__init__).parameters)
+    reference_kwargs = {"encoders", "decoders", "in_channel", "num_hidden_channels", "n_res_block",
+                        "num_residual_channels", "embed_dim", "num_embeddings", "decay", "groups",
+                        "use_local_kernels", "output_activation_type", "output_spectrogram_min_magnitude",
+                        "resolution_factors", "embeddings_initial_variance", "decoder_output_activation",
+                        "normalizer_statistics", "corruption_weights", "adapt_quantized_durations",
+                        "disable_quantization", "restarts_usage_threshold"}
+    assert reference_kwargs <= ours
+    assert not any(p.kind is inspect.Parameter.VAR_KEYWORD
+                   for p in inspect.signature(VQVAE.__init__).parameters.values())
+    kw = dict(in_channel=2, resolution_factors={'bottom': 16, 'top': 2}, bottleneck_cls=OracleBottleneck)
+    for bad in (dict(restarts_usage_threshold=0.5), dict(groups=2), dict(encoders={'top': None, 'bottom': None}),
+                dict(decoder_output_activation=torch.nn.ReLU()), dict(normalizer_statistics={'mean': 0., 'std': 1.})):
+        with pytest.raises(NotImplementedError):
+            VQVAE(**kw, **bad)
+    with pytest.raises(AssertionError):
+        VQVAE(**kw, output_activation_type='relu')
+    with pytest.raises(TypeError):
+        VQVAE(**kw, no_such_parameter=1)
+
+
+def test_normaliser_and_masked_phase_output_transform(tmp_path):
+    """vqvae.py:254-255 (normalise in ``encode``) and :297-302 (denormalise + masked-phase
+    transform in ``decode``), with GANSynth's affine statistics; parameters survive the
+    model_parameters.json round trip (vqvae.py:304-342)."""
+    stats = {'s_a': 0.09, 's_b': 0.4, 'p_a': 0.8, 'p_b': 0.05}
+    kw = dict(in_channel=2, resolution_factors={'bottom': 16, 'top': 2}, adapt_quantized_durations=False,
+              bottleneck_cls=OracleBottleneck)
+    torch.manual_seed(1)
+    plain = VQVAE(**kw).eval()
+    model = VQVAE(**kw, normalizer_statistics=stats, output_spectrogram_min_magnitude=-3.0).eval()
+    model.load_state_dict(plain.state_dict())
+    x = torch.randn(1, 2, 256, 32) * 3 - 4
+    scale = torch.tensor([stats['s_a'], stats['p_a']]).view(1, 2, 1, 1)
+    bias = torch.tensor([stats['s_b'], stats['p_b']]).view(1, 2, 1, 1)
+    with torch.no_grad():
+        got = model.encode(x)
+        want = plain.encode(x * scale + bias)
+        assert torch.equal(got[3], want[3]) and torch.equal(got[4], want[4])
+        assert torch.equal(model.encode_codes(x)[1], want[4])
+        raw = plain.decode(want[0], want[1])
+        dec = model.decode(got[0], got[1])
+        expect = (raw - bias) / scale
+        expect[:, 1][expect[:, 0] < -3.0] = 0
+        torch.testing.assert_close(dec, expect)
+        assert (dec[:, 1][dec[:, 0] < -3.0] == 0).all() and (dec[:, 0] < -3.0).any()
+        # the same affine as front-end knobs: helper applies it, the model must not re-apply it
+        knobs = model.front_end_knobs()
+        assert knobs["output_affine"] == ((0.09, 0.4), (0.8, 0.05))
+        model.normalizes_input = False
+        assert torch.equal(model.encode(x * scale + bias)[4], want[4])
+        model.normalizes_input = True
+        inv = model.inverse_front_end_knobs()["input_affine"]
+        torch.testing.assert_close(raw[:, 0] * inv[0][0] + inv[0][1], expect[:, 0])
+    path = tmp_path / "model_parameters.json"
+    model.store_instantiation_parameters(path)
+    import json
+    params = json.loads(path.read_text())
+    assert params["normalizer_statistics"] == stats and params["output_spectrogram_min_magnitude"] == -3.0
+    again = VQVAE(**params, bottleneck_cls=OracleBottleneck)
+    assert again.normalizer_statistics == stats and again.use_gansynth_normalization
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="reference checkout not present")
+def test_unquantized_bottleneck_matches_reference():
+    """bottleneck.py:107-119 / vqvae.py:159-160: ``disable_quantization`` passes the features
+    through; runs on the CPU (no kernel involved), so the whole model is compared."""
+    RefVQVAE = ref_loader.load_reference_vqvae_class()
+    torch.manual_seed(2)
+    kw = dict(in_channel=2, resolution_factors={'bottom': 16, 'top': 2}, adapt_quantized_durations=False,
+              disable_quantization=True)
+    ref = RefVQVAE(**kw).eval()
+    ours = VQVAE(**kw).eval()
+    ours.load_state_dict(ref.state_dict(), strict=True)
+    x = torch.randn(1, 2, 256, 32)
+    with torch.no_grad():
+        r, o = ref.encode(x), ours.encode(x)
+    torch.testing.assert_close(r[0], o[0])
+    torch.testing.assert_close(r[1], o[1])
+    assert r[3] is None and o[3] is None and o[4] is None
+    assert torch.isinf(o[5]).all() and float(o[2].sum()) == 0.0
+    with pytest.raises(NotImplementedError):
+        ours.quantize_t.embed_code(torch.zeros(1, 2, 2, dtype=torch.long))
