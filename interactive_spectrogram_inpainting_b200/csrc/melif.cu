@@ -351,18 +351,24 @@ melif_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params p,
 // One CTA per SM, 24 warps in two roles that run CONCURRENTLY on consecutive batches of
 // FB = 8 frames through a double-buffered workspace:
 //   * 8 transform warps (4 groups of 64 threads, one frame pair each): stage wait, the three
-//     FFT passes; ~110 registers (setmaxnreg.inc) for the 16-point butterflies of a pair;
+//     FFT passes; 112 registers (setmaxnreg.inc) for the 16-point butterflies of a pair;
 //   * 16 polar/emit warps (512 threads, one untangle item and two output rows each): polar
 //     of the batch the transform warps finished last, then the mel projection, log / wrap,
-//     epilogue and stores; ~72 registers (setmaxnreg.dec).
+//     epilogue and stores; 64 registers (setmaxnreg.dec).
 // The generic kernel gives every thread the transform's register budget, which caps an SM at
-// 16 warps; here the register file is split by need (8 x 32 x 112 + 16 x 32 x 72 = 64 Ki), so
-// 24 warps are resident, and the FMA-heavy transform overlaps the LDS / MUFU / store-heavy
-// emit instead of alternating with it.  Hand-off: full[buf] / empty[buf] mbarriers
+// 16 warps; here the registers are split by need, so 24 warps are resident, and the FMA-heavy
+// transform overlaps the LDS / MUFU / store-heavy emit instead of alternating with it.  The
+// split must CONSERVE the CTA's launch allocation (768 threads x 80 registers = 60 Ki): the
+// transform warps' setmaxnreg.inc spins until the pool holds what the polar/emit warps'
+// setmaxnreg.dec released, 8 x 32 x (112 - 80) = 16 x 32 x (80 - 64).  Hand-off: full[buf] / empty[buf] mbarriers
 // (transform -> polar/emit -> transform); role-wide named barriers inside each role.
 // ------------------------------------------------------------------------------------------
 constexpr int kWsFftThreads = 256, kWsPeThreads = 512, kWsThreads = kWsFftThreads + kWsPeThreads;
-constexpr int kWsFftRegs = 112, kWsPeRegs = 72;
+constexpr int kWsFftRegs = 112, kWsPeRegs = 64, kWsLaunchRegs = 80;
+static_assert(kWsFftThreads * (kWsFftRegs - kWsLaunchRegs) <= kWsPeThreads * (kWsLaunchRegs - kWsPeRegs),
+              "setmaxnreg.inc would wait forever for registers nobody releases");
+static_assert(kWsThreads * kWsLaunchRegs <= 65536 && kWsThreads * (kWsLaunchRegs + 8) > 65536,
+              "kWsLaunchRegs must be what __launch_bounds__(kWsThreads, 1) gives");
 
 template <int FB, bool MEL, typename S>
 __global__ void __launch_bounds__(kWsThreads, 1)

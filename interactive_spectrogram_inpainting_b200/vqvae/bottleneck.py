@@ -15,7 +15,7 @@ arithmetic runs in ``libisi_b200.so``:
 There is no CPU path: CPU tensors raise.
 """
 import math
-from typing import List, Optional, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import threading
 
@@ -97,6 +97,90 @@ class _QuantizeFunction(torch.autograd.Function):
         return None, grad
 
 
+class EmaExchange:
+    """The training path's one exchange step: the EMA statistics of SEVERAL
+    quantisers (the VQ-VAE's top and bottom) live in ONE packed buffer
+
+        [counts_t (K_t) | embed_sum_t (K_t*D) | counts_b (K_b) | embed_sum_b (K_b*D)]      266 KB
+
+    which is summed over the ranks by a single ``all_reduce(async_op=True)`` issued right after
+    the last quantiser ran -- NCCL over NVLink on its own stream -- and waited for only when the
+    codebook updates are applied, i.e. after whatever the caller enqueued in between (the
+    decoder's forward in ``VQVAE.forward``).  Every rank then runs the identical
+    ``isi_vq_ema_update`` on identical sums, so the codebooks stay bit-identical across ranks.
+
+    Protocol (driven by the owner): ``begin()`` -> each member quantiser's training forward
+    writes its statistics into ``slot(member)`` and defers its update -> ``launch()`` ->
+    ... -> ``finish()``.  Inactive (members update immediately, as a lone quantiser does) unless
+    torch.distributed is initialised with more than one rank and every member syncs."""
+
+    def __init__(self, members: Sequence["QuantizedBottleneck"], process_group=None):
+        self.members = list(members)
+        self.process_group = process_group
+        self.offsets, off = [], 0
+        for m in self.members:
+            self.offsets.append(off)
+            off += m.n_embed * (1 + m.dim)
+        self.numel = off
+        self.pack: Optional[torch.Tensor] = None
+        self.open = False
+        self._pending: List["QuantizedBottleneck"] = []
+        self._work = None
+        self.last_allreduce_events = None      # (start, end) CUDA events of the last collective, if timed
+        self.time_collective = False
+
+    def enabled(self) -> bool:
+        import torch.distributed as dist
+        return (dist.is_available() and dist.is_initialized()
+                and dist.get_world_size(self.process_group) > 1
+                and all(m.sync_ema_stats and m.training for m in self.members))
+
+    def begin(self, device: torch.device) -> bool:
+        if not self.enabled():
+            return False
+        if self.pack is None or self.pack.device != device:
+            self.pack = torch.zeros(self.numel, dtype=torch.float32, device=device)
+        else:
+            self.pack.zero_()
+        self.open, self._pending, self._work = True, [], None
+        for m in self.members:
+            m._exchange = self
+        return True
+
+    def slot(self, member: "QuantizedBottleneck") -> torch.Tensor:
+        i = next(k for k, m in enumerate(self.members) if m is member)
+        return self.pack[self.offsets[i]: self.offsets[i] + member.n_embed * (1 + member.dim)]
+
+    def defer(self, member: "QuantizedBottleneck") -> None:
+        self._pending.append(member)
+
+    def launch(self) -> None:
+        import torch.distributed as dist
+        if not self.open:
+            return
+        if self.time_collective:
+            start = torch.cuda.Event(enable_timing=True)
+            start.record()
+        self._work = dist.all_reduce(self.pack, op=dist.ReduceOp.SUM, group=self.process_group, async_op=True)
+        if self.time_collective:
+            self._start = start
+
+    def finish(self) -> None:
+        if not self.open:
+            return
+        if self._work is not None:
+            self._work.wait()                  # the current stream waits for the collective
+            if self.time_collective:
+                end = torch.cuda.Event(enable_timing=True)
+                end.record()
+                self.last_allreduce_events = (self._start, end)
+        for m in self._pending:
+            m._apply_ema(self.slot(m))
+        self.open, self._pending, self._work = False, [], None
+        for m in self.members:
+            m._exchange = None
+
+
 class QuantizedBottleneck(nn.Module):
     cluster_size: torch.Tensor
 
@@ -122,6 +206,7 @@ class QuantizedBottleneck(nn.Module):
         self.stats_process_group = None
         self.embed_code_channels_first = True  # 3-D ids -> NCHW storage (vqvae.py:289-292)
         self._cache = _CodebookCache()
+        self._exchange: Optional[EmaExchange] = None   # set by an open EmaExchange for one step
 
     # -- nn.Module plumbing: any re-materialisation of the buffers drops the cache --
     def _apply(self, fn, *args, **kwargs):
@@ -207,7 +292,9 @@ class QuantizedBottleneck(nn.Module):
         quantize = _empty_like_strided(x)
         q_layout = _lib.rows_layout(quantize)
         n_stats = self.n_embed * (1 + self.dim) if self.training else self.n_embed
-        stats = torch.zeros(n_stats, dtype=torch.float32, device=dev)
+        deferred = self.training and self._exchange is not None and self._exchange.open
+        # an open exchange lends (zeroed) room in its packed buffer; the update is its job
+        stats = self._exchange.slot(self) if deferred else torch.zeros(n_stats, dtype=torch.float32, device=dev)
         ws_bytes = lib.isi_vq_gather_workspace_bytes(n_rows, self.dim)
         workspace = torch.empty((ws_bytes + 7) // 8, dtype=torch.float64, device=dev)
         _lib.invoke("isi_vq_gather_stats", 
@@ -220,7 +307,9 @@ class QuantizedBottleneck(nn.Module):
                                      stats.data_ptr(), scalars.data_ptr(),
                                      scalars.data_ptr() + 4, stream)
 
-        if self.training:
+        if deferred:
+            self._exchange.defer(self)
+        elif self.training:
             self._ema_update(stats)
         if quantize.dtype != input.dtype:
             quantize = quantize.to(input.dtype)
@@ -242,6 +331,10 @@ class QuantizedBottleneck(nn.Module):
         one process on the concatenated batch (the reference itself never
         reduces these and lets DDP broadcast rank 0's buffers instead)."""
         self.reduce_ema_stats(stats)
+        self._apply_ema(stats)
+
+    def _apply_ema(self, stats: torch.Tensor) -> None:
+        """``isi_vq_ema_update`` on (already reduced) packed statistics."""
         for buf in (self.cluster_size, self.embed_avg, self.embed):
             if not buf.is_contiguous():
                 raise RuntimeError("codebook buffers must be contiguous")

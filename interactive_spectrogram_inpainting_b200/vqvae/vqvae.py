@@ -21,7 +21,7 @@ import torch
 from torch import nn
 
 from .. import _lib
-from .bottleneck import QuantizedBottleneck, UnquantizedBottleneck
+from .bottleneck import EmaExchange, QuantizedBottleneck, UnquantizedBottleneck
 
 # channel plan of the strided stages in quarters of `channel` (encoder_decoder.py:52-116)
 _DOWN_PLAN = {16: (1, 2, 3, 4), 8: (2, 2, 4), 4: (2, 4), 2: (2,)}
@@ -389,6 +389,11 @@ class VQVAE(nn.Module):
                            use_local_kernels)
         self._project_t = PointwiseProjection(self.quantize_conv_t)
         self._project_b = PointwiseProjection(self.quantize_conv_b)
+        # data-parallel training: ONE packed all-reduce of both quantisers' EMA statistics,
+        # overlapped with the decoder; inert outside torch.distributed
+        self.ema_exchange = (EmaExchange([self.quantize_t, self.quantize_b])
+                             if isinstance(self.quantize_t, QuantizedBottleneck)
+                             and type(self.quantize_t) is not UnquantizedBottleneck else None)
 
     # -- the two pre-quantiser 1x1 convolutions (vqvae.py:260 and :271-272), as ``[B, H, W, D]`` --
     def _prequant_top(self, enc_t: torch.Tensor) -> torch.Tensor:
@@ -415,9 +420,12 @@ class VQVAE(nn.Module):
         return self.quantize_conv_b(torch.cat([dec_t, enc_b], 1)).permute(0, 2, 3, 1)
 
     # -- vqvae.py:251-278 --
-    def encode(self, input: torch.Tensor, space_to_depth: bool = False):
+    def encode(self, input: torch.Tensor, space_to_depth: bool = False, _exchange_open: bool = False):
         """``space_to_depth``: ``input`` is the 2x2-blocked spectrogram ``[B, 4C, F/2, T/2]`` that
         ``SpectrogramsHelper(space_to_depth=True)`` writes; same result, faster first conv."""
+        ex = self.ema_exchange
+        own_exchange = (self.training and ex is not None and not _exchange_open and input.is_cuda
+                        and ex.begin(input.device))
         input = self._normalize(input, space_to_depth)
         enc_b = self.enc_b(input, space_to_depth=space_to_depth)
         enc_t = self.enc_t(enc_b)
@@ -427,6 +435,9 @@ class VQVAE(nn.Module):
 
         quant_b, diff_b, id_b, perplexity_b = self.quantize_b(self._prequant_bottom(quant_t, enc_b))
         quant_b = quant_b.permute(0, 3, 1, 2)
+        if own_exchange:        # a bare encode() in training: exchange and update right away
+            ex.launch()
+            ex.finish()
         return (quant_t, quant_b, diff_t.unsqueeze(0) + diff_b.unsqueeze(0), id_t, id_b,
                 perplexity_t, perplexity_b)
 
@@ -493,8 +504,18 @@ class VQVAE(nn.Module):
         return self.decode(quant_t, quant_b)
 
     def forward(self, input):
-        quant_t, quant_b, diff, id_t, id_b, perplexity_t, perplexity_b = self.encode(input)
-        return self.decode(quant_t, quant_b), diff, perplexity_t, perplexity_b, id_t, id_b
+        """vqvae.py:245-249.  In data-parallel training the packed EMA statistics of both
+        quantisers are all-reduced while the decoder runs (``EmaExchange``)."""
+        ex = self.ema_exchange
+        exchanging = self.training and ex is not None and input.is_cuda and ex.begin(input.device)
+        quant_t, quant_b, diff, id_t, id_b, perplexity_t, perplexity_b = self.encode(
+            input, _exchange_open=exchanging)
+        if exchanging:
+            ex.launch()
+        dec = self.decode(quant_t, quant_b)
+        if exchanging:
+            ex.finish()
+        return dec, diff, perplexity_t, perplexity_b, id_t, id_b
 
     # -- vqvae.py:304-342 --
     @classmethod

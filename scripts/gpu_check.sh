@@ -8,8 +8,20 @@ steps="$*"
 [ -z "$steps" ] && steps="frontend quant tc bench"
 for s in $steps; do
   case $s in
+    quick)
+      # a hang here (e.g. a kernel deadlock) must not burn the GPU budget: stop the whole script
+      timeout 150 python -c "
+import torch
+from interactive_spectrogram_inpainting_b200.utils import synthetic
+from interactive_spectrogram_inpainting_b200.utils.spectrograms_helper import MelSpectrogramsHelper
+h = MelSpectrogramsHelper().to('cuda:0')
+for n in (1, 4, 300):
+    s = h.to_spectrogram(synthetic.synthetic_notes(min(n, 8)).repeat((n + 7) // 8, 1)[:n].to('cuda:0'))
+    torch.cuda.synchronize(); print('quick ok', n, tuple(s.shape), float(s.abs().mean()))
+" 2>&1 | tail -4
+      if [ "${PIPESTATUS[0]}" != "0" ]; then echo "quick check FAILED or hung: stopping"; exit 1; fi ;;
     frontend)
-      timeout 900 python -m pytest tests/test_gpu_frontend.py -q 2>&1 | tail -40 > gpurun_out/pytest_frontend_$tag.log
+      timeout 300 python -m pytest tests/test_gpu_frontend.py -q 2>&1 | tail -40 > gpurun_out/pytest_frontend_$tag.log
       tail -3 gpurun_out/pytest_frontend_$tag.log ;;
     extraction)
       timeout 900 python -m pytest tests/test_gpu_extraction.py -q 2>&1 | tail -40 > gpurun_out/pytest_extraction_$tag.log
