@@ -201,6 +201,190 @@ def reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def pin_to_gpu_numa_node(index: int):
+    """Run this rank on the cores NVML reports as local to its GPU (pinned host buffers are then
+    allocated on that NUMA node by first touch): eight ranks sharing one host otherwise pull
+    their uploads across the socket interconnect.  Returns the number of cores, or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+        handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        n_words = (os.cpu_count() + 63) // 64
+        words = pynvml.nvmlDeviceGetCpuAffinity(handle, n_words)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return len(cpus)
+    except Exception:
+        pass
+    return None
+
+
+# --------------------------------------------------------------------------- other configs
+def source_hash(*names) -> str:
+    """SHA-256 over the kernel sources a recorded ncu fact belongs to (first 16 hex digits)."""
+    import hashlib
+    h = hashlib.sha256()
+    for name in names:
+        h.update((ROOT / "interactive_spectrogram_inpainting_b200" / "csrc" / name).read_bytes())
+    return h.hexdigest()[:16]
+
+
+def recorded_ncu_facts(kernel: str):
+    """Counters of the dominant kernel from a committed ncu capture (profiles/ncu_facts.json):
+    used ONLY when the sources the capture was taken on are the sources in the tree (hash);
+    otherwise the fields are null -- a stale constant must not survive a kernel change."""
+    path = ROOT / "profiles" / "ncu_facts.json"
+    if not path.exists():
+        return None
+    facts = json.loads(path.read_text()).get(kernel)
+    if not facts or facts.get("source_sha16") != source_hash(*facts.get("sources", [])):
+        return None
+    return facts
+
+
+def train_step_leg(dev, rank, world, local, steps=8, warmup=3, batch=64):
+    """BASELINE config 3: train_vqvae.py:169-192 -- front end, VQ-VAE-2 forward (this repo's
+    quantisers inside the torch conv stacks), reconstruction + commitment loss, backward, Adam;
+    batch 64 per GPU; under N>1 DDP for the conv gradients and ONE packed EMA-statistics
+    all-reduce per step overlapped with the decoder (EmaExchange)."""
+    import torch.distributed as dist
+    import torch.nn.functional as F
+    from interactive_spectrogram_inpainting_b200 import _lib
+    from interactive_spectrogram_inpainting_b200.utils import synthetic
+    from interactive_spectrogram_inpainting_b200.utils.spectrograms_helper import MelSpectrogramsHelper
+    from interactive_spectrogram_inpainting_b200.vqvae.vqvae import VQVAE
+    torch.manual_seed(0)
+    helper = MelSpectrogramsHelper(channels_last=True).to(dev)
+    model = VQVAE(**MODEL_KW).to(dev).to(memory_format=torch.channels_last).train()
+    net = model
+    if world > 1:       # the quantisers keep their own buffers in sync: no per-forward broadcast
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], broadcast_buffers=False)
+    opt = torch.optim.Adam(net.parameters(), lr=3e-4)
+    audio = synthetic.synthetic_notes(batch, seed=synthetic.AUDIO_SEED + 1000 + rank).to(dev)
+    model.ema_exchange.time_collective = True
+    reduce_ms = []
+
+    def step():
+        spec = helper.to_spectrogram(audio)
+        recon, diff, *_ = net(spec)
+        loss = F.mse_loss(recon, spec) + 0.25 * diff.mean()
+        opt.zero_grad(set_to_none=True)
+        loss.backward()
+        opt.step()
+        if model.ema_exchange.last_allreduce_events is not None:
+            reduce_ms.append(model.ema_exchange.last_allreduce_events)
+            model.ema_exchange.last_allreduce_events = None
+        return loss
+
+    for _ in range(warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    reduce_ms.clear()
+    _lib.event_log = []
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(steps):
+        loss = step()
+    t1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    calls, _lib.event_log = _lib.event_log, None
+    ms = torch.tensor([t0.elapsed_time(t1) / steps], device=dev)
+    same = True
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        flags = []
+        for q in (model.quantize_t, model.quantize_b):
+            for buf in (q.embed, q.cluster_size, q.embed_avg):
+                ref = buf.clone()
+                dist.broadcast(ref, 0)
+                flags.append(float(torch.equal(ref, buf)))
+        flag = torch.tensor([min(flags)], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        same = bool(flag.item())
+    per_call = {}
+    for name, a, b in calls:
+        per_call[name] = per_call.get(name, 0.0) + a.elapsed_time(b) / steps
+    # launch -> wait-complete span of the collective on the main stream: it contains the decoder
+    # work it overlaps with, so it is an upper bound of the collective's own time
+    span = [a.elapsed_time(b) for a, b in reduce_ms]
+    del net, opt, model
+    torch.cuda.empty_cache()
+    return {"what": "cfg3: VQ-VAE-2 training step (front end + forward + loss + backward + Adam), "
+                    f"batch {batch} per GPU" + (", DDP + one packed async EMA all-reduce per step" if world > 1 else ""),
+            "ms_per_step": ms.item(), "notes_per_s": world * batch / (ms.item() * 1e-3), "steps": steps,
+            "loss": float(loss), "isi_kernels_ms_per_step": round(sum(per_call.values()), 4),
+            "ema_allreduces_per_step": (len(span) / steps) if world > 1 else 0,
+            "ema_allreduce_bytes": 4 * 2 * N_EMBED * (1 + DIM) if world > 1 else 0,
+            "ema_allreduce_launch_to_wait_ms": (sum(span) / max(1, len(span))) if span else 0.0,
+            "codebooks_identical_across_ranks": same}
+
+
+def large_codebook_leg(dev, rows=1 << 20, dim=128, n_embed=4096, iters=3):
+    """BASELINE config 4: 4096 x 128 codebook, nearest-code search over 1 Mi rows
+    (vq_assign_pstream_kernel<128>: CTA pair, streamed codebook)."""
+    from interactive_spectrogram_inpainting_b200.utils import synthetic
+    from interactive_spectrogram_inpainting_b200.vqvae.bottleneck import QuantizedBottleneck
+    embed = synthetic.synthetic_codebook(dim, n_embed)
+    m = QuantizedBottleneck(dim, n_embed).to(dev).eval()
+    m.embed.copy_(embed)
+    x = synthetic.synthetic_features(rows, embed, 5).to(dev)
+    for _ in range(2):
+        m.assign(x)
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(iters):
+        m.assign(x)
+    t1.record()
+    torch.cuda.synchronize()
+    ms = t0.elapsed_time(t1) / iters
+    del m, x
+    return ms, 2.0 * rows * n_embed * dim / (ms * 1e-3) / 1e12
+
+
+def decode_leg(dev, batches=(1, 16)):
+    """BASELINE config 5: embed_code lookup of edited top/bottom code maps feeding the decoder
+    (VQVAE.decode_code, vqvae.py:288-295) at the server's batch sizes, eager and replayed from
+    one CUDA graph."""
+    from interactive_spectrogram_inpainting_b200.utils import synthetic
+    from interactive_spectrogram_inpainting_b200.vqvae.vqvae import VQVAE, GraphedDecodeCode
+    torch.manual_seed(0)
+    model = VQVAE(**MODEL_KW).to(dev).eval()
+    out = []
+
+    def timed(fn, iters=20):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters
+    with torch.no_grad():
+        for b in batches:
+            top, bottom = synthetic.synthetic_codemaps(b)
+            top, bottom = top.to(dev), bottom.to(dev)
+            lookup = timed(lambda: (model.quantize_t.embed_code(top), model.quantize_b.embed_code(bottom)))
+            eager = timed(lambda: model.decode_code(top, bottom))
+            graphed = GraphedDecodeCode(model, top, bottom)
+            replay = timed(lambda: graphed(top, bottom))
+            out.append({"batch": b, "embed_code_top_plus_bottom_ms": lookup, "decode_code_eager_ms": eager,
+                        "decode_code_cuda_graph_ms": replay})
+    del model
+    return out
+
+
 # --------------------------------------------------------------------------- B200 arm
 def b200_arm(args):
     import torch.distributed as dist
@@ -217,6 +401,7 @@ def b200_arm(args):
         raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback for the product path")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    affinity = pin_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
@@ -272,11 +457,21 @@ def b200_arm(args):
         step(audio)
     t1.record()
     barrier()
-    clocks.stop()
     step_events, _lib.event_log = _lib.event_log, None
     launches = _lib.total_launches() - launches0
     ms_total = max_over_ranks(t0.elapsed_time(t1))
     value = world * B * K / (ms_total * 1e-3)
+    # the same loop again for >= 1 s (K steps are a ~50 ms window: too short for a steady clock
+    # record); `value` stays the K-step number the contract asks for, both are reported
+    reps = max(1, int(1000.0 / max(ms_total, 1e-3)) + 1)
+    s0, s1 = ev(), ev()
+    s0.record()
+    for _ in range(reps * K):
+        step(audio)
+    s1.record()
+    barrier()
+    clocks.stop()
+    sustained_ms = max_over_ranks(s0.elapsed_time(s1))
     per_call = {}
     for name, a, b in step_events:
         per_call.setdefault(name, []).append(a.elapsed_time(b))
@@ -310,6 +505,17 @@ def b200_arm(args):
         ms = max_over_ranks(t0.elapsed_time(t1))
         gaps = [(b - a) * 1e3 for a, b in zip(e2e_stamps[:-1], e2e_stamps[1:])] or [ms / K]
         return ms, gaps
+    # raw upload rate of this rank's pinned audio batch (all ranks at once: they share the host)
+    probe = torch.empty_like(audio)
+    barrier()
+    h0, h1 = ev(), ev()
+    h0.record()
+    for _ in range(5):
+        probe.copy_(host_audio, non_blocking=True)
+    h1.record()
+    barrier()
+    h2d_gbs = 5 * host_audio.numel() * host_audio.element_size() / (max_over_ranks(h0.elapsed_time(h1)) * 1e-3) / 1e9
+    del probe
     e2e_ms, e2e_gaps = e2e_measure(host_audio)
     e2e_value = world * B * K / (e2e_ms * 1e-3)
     other = "f32" if args.audio == "pcm16" else "pcm16"
@@ -406,7 +612,16 @@ def b200_arm(args):
         torch.backends.cuda.matmul.allow_tf32 = False
         del ma, mb
 
-    hbm_peak, peak_kind, _ = measured_peaks()
+    with torch.no_grad():
+        pstream_ms, pstream_tflops = large_codebook_leg(dev)
+        decode_rows = decode_leg(dev)
+    train = train_step_leg(dev, rank, world, local)
+
+    hbm_peak, peak_kind, peaks = measured_peaks()
+    # 3xTF32 rooflines from the driver's measurement (bf16 cuBLAS / 2 = TF32 dense, / 3 for the split)
+    tf32x3_burst = peaks["bf16_tflops"] / 2 / 3 if "bf16_tflops" in peaks else None
+    tf32x3_sustained = peaks["bf16_tflops_sustained"] / 2 / 3 if "bf16_tflops_sustained" in peaks else None
+    facts = recorded_ncu_facts("melif_ws_kernel")
     project_bytes = B * (128 * (4 * 128 + 256) + 512 * (4 * 192 + 256))
     # algorithmic bytes per note: the samples as uploaded + the FP32 spectrogram
     melif_bytes_per_note = MELIF_BYTES_PER_NOTE - (4 - host_audio.element_size()) * N_SAMPLES
@@ -442,7 +657,7 @@ def b200_arm(args):
                 "api": "extract.CodeExtractor(helper, model, device).run(pinned host audio batches)",
                 "cuda_graph": bool(args.e2e_cuda_graph) and not extractor.graph_failures,
                 "cuda_graph_failures": extractor.graph_failures[:2],
-                "ms_per_step": e2e_ms / K,
+                "ms_per_step": e2e_ms / K, "h2d_gbs": h2d_gbs,
                 "host_ms_between_batches": {"median": statistics.median(e2e_gaps), "max": max(e2e_gaps)},
                 "other_audio_format": {"audio": other, "value": world * B * K / (other_ms * 1e-3),
                                        "h2d_bytes_per_step": host_by_format[other].numel()
@@ -450,35 +665,49 @@ def b200_arm(args):
         "gpu_launches": launches,
         "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"],
                    "reasons": clk["reasons"], "samples": clk["samples"]},
-        "roofline": {"kernel": "melif_kernel<2048,8,512>", "bound": "hbm", "achieved": melif_gbs,
+        "roofline": {"kernel": "melif_ws_kernel<8,mel> (warp-specialised front end: 8 transform + 16 polar/emit warps)",
+                     "bound": "hbm", "achieved": melif_gbs,
                      "peak": hbm_peak, "unit": "GB/s", "frac": melif_gbs / hbm_peak,
-                     # dram__bytes_read + dram__bytes_write of one 444-note launch from the
-                     # committed ncu captures of this kernel (channels_last output), scaled to
-                     # this batch: profiles/r01_melif_v8_512t_r05a_ncu_summary.csv (57.1 +
-                     # 413.6 MB) and profiles/r01_melif_v6_r02b_ncu_summary.csv (114.3 + 413.8 MB);
-                     # ~50 MB of the last notes' output is still dirty in L2 when the kernel ends
-                     "traffic": ((57.059840e6 + 413.562624e6) if args.audio == "pcm16"
-                                 else (114.308608e6 + 413.754112e6)) / 444 * B if cl else None,
                      "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
                      "ms_per_launch": melif_ms, "algorithmic_bytes_per_launch": melif_bytes_per_note * B,
-                     # what actually bounds this kernel: instruction issue.  Warp instructions
-                     # per note from the committed ncu capture of this variant
-                     # (smsp__inst_executed.sum / 444 notes), against 148 SMs x 4 issue slots
-                     # at the SM clock sampled during the timed region
-                     "issue_bound": (lambda per_note, mhz: {
-                         "warp_instructions_per_note": per_note,
-                         "achieved_ginst_per_s": per_note * B / (melif_ms * 1e-3) / 1e9,
-                         "peak_ginst_per_s": 148 * 4 * mhz * 1e6 / 1e9,
-                         "frac": per_note * B / (melif_ms * 1e-3) / (148 * 4 * mhz * 1e6),
-                         "source": "profiles/r01_melif_v8_512t_r05a_ncu_summary.csv"})(
-                             264092532 / 444 if args.audio == "pcm16" else 260017056 / 444,
-                             clk["sm_mhz"] or 1965.0)},
+                     # dram__bytes_read + dram__bytes_write of one launch from the committed ncu
+                     # capture of THESE sources (profiles/ncu_facts.json, checked by hash), scaled
+                     # to this batch; null when the kernel changed since the capture
+                     "traffic": (facts["dram_bytes_per_note"] * B if facts else None),
+                     "traffic_source": (facts["profile"] if facts else
+                                        "null: no ncu capture of the current kernel sources (profiles/ncu_facts.json)"),
+                     # what bounds this kernel besides bytes: issue slots and shared-memory
+                     # wavefronts, per note, from the same capture
+                     "issue_bound": ({
+                         "warp_instructions_per_note": facts["warp_instructions_per_note"],
+                         "achieved_ginst_per_s": facts["warp_instructions_per_note"] * B / (melif_ms * 1e-3) / 1e9,
+                         "peak_ginst_per_s": 148 * 4 * (clk["sm_mhz"] or 1965.0) * 1e6 / 1e9,
+                         "frac": facts["warp_instructions_per_note"] * B / (melif_ms * 1e-3)
+                                 / (148 * 4 * (clk["sm_mhz"] or 1965.0) * 1e6),
+                         "shared_wavefronts_per_note": facts.get("shared_wavefronts_per_note"),
+                         "shared_wavefront_frac": (facts["shared_wavefronts_per_note"] * B / (melif_ms * 1e-3)
+                                                   / (148 * (clk["sm_mhz"] or 1965.0) * 1e6)
+                                                   if facts.get("shared_wavefronts_per_note") else None),
+                         "source": facts["profile"]} if facts else None),
+                     "parity": "front end parity is UNPINNED (GANsynth_pytorch absent): the oracle is a "
+                               "restatement of the published GANSynth recipe; 1e-4 holds at >= 99.9 % of "
+                               "log-magnitude positions and >= 99.95 % of the well-conditioned IF positions "
+                               "(60-90 % of all positions), 1e-3 at 99.97 % everywhere (tests/test_melif_emulation.py)"},
         "rooflines_other": [
-            {"kernel": f"vq_assign ({args.assign_algo})", "bound": "tensor",
-             "achieved": assign_tflops, "peak": tf32_tflops / 3.0, "unit": "TFLOP/s",
-             "frac": assign_tflops / (tf32_tflops / 3.0), "ms_per_launch": assign_ms,
-             "rows": qn, "note": "2*N*K*D algorithmic FLOP over the 3xTF32 roofline = TF32 dense "
-                                 f"cuBLAS peak measured on this box ({tf32_tflops:.0f} TFLOP/s) / 3"},
+            {"kernel": f"vq_assign_pair_kernel ({args.assign_algo}; K=512, D=64)", "bound": "tensor",
+             "achieved": assign_tflops, "peak": tf32x3_burst or tf32_tflops / 3.0, "unit": "TFLOP/s",
+             "frac": assign_tflops / (tf32x3_burst or tf32_tflops / 3.0), "ms_per_launch": assign_ms,
+             "frac_of_sustained": (assign_tflops / tf32x3_sustained) if tf32x3_sustained else None,
+             "frac_of_in_run_cublas_tf32": assign_tflops / (tf32_tflops / 3.0),
+             "rows": qn, "note": "2*N*K*D algorithmic FLOP over the 3xTF32 roofline; peak = MEASURED_PEAKS.json "
+                                 "bf16 burst / 2 (TF32 dense) / 3 (the kernel is timed in isolation); also against "
+                                 f"the sustained figure and against TF32 cuBLAS timed in this run ({tf32_tflops:.0f} TFLOP/s)"},
+            {"kernel": "vq_assign_pstream_kernel<128> (cfg 4: K=4096, D=128, CTA pair, streamed codebook)",
+             "bound": "tensor", "achieved": pstream_tflops, "peak": tf32x3_burst or tf32_tflops / 3.0,
+             "unit": "TFLOP/s", "frac": pstream_tflops / (tf32x3_burst or tf32_tflops / 3.0),
+             "frac_of_sustained": (pstream_tflops / tf32x3_sustained) if tf32x3_sustained else None,
+             "frac_of_in_run_cublas_tf32": pstream_tflops / (tf32_tflops / 3.0),
+             "ms_per_launch": pstream_ms, "rows": 1 << 20},
             {"kernel": "vq_gather_stats (training: lookup + (q-x)^2 + EMA sums)", "bound": "hbm",
              "achieved": gather_bytes / (gather_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
              "frac": gather_bytes / (gather_ms * 1e-3) / 1e9 / hbm_peak, "ms_per_launch": gather_ms,
@@ -500,6 +729,12 @@ def b200_arm(args):
              "ms_per_launch": inverse_ms, "notes": B,
              "note": "4*2*F*T' read + 4*T written per note; issue/latency bound like the forward kernel"}],
         "kernel_ms_per_step": kernel_ms_per_step,
+        "sustained": {"steps": reps * K, "seconds": sustained_ms * 1e-3,
+                      "value": world * B * reps * K / (sustained_ms * 1e-3), "unit": "notes/s",
+                      "what": "the timed loop repeated for >= 1 s; `value` above is the K-step region"},
+        "train_step": train,
+        "decode_code": decode_rows,
+        "host": {"cpu_affinity_cores": affinity, "h2d_gbs_all_ranks_at_once": h2d_gbs},
         "hot_path_only": {"value": world * B * K / (hot_ms * 1e-3), "unit": "notes/s",
                           "ms_per_step": hot_ms / K,
                           "what": "front end + top/bottom quantiser kernels, conv features precomputed"},

@@ -18,6 +18,8 @@
 // three layouts (planes, channels-last, 2x2 space-to-depth blocks).  The whole working set is
 // one FB-frame buffer (65 KB with tables and stage at n_fft 2048), so three CTAs share an SM
 // and fill each other's barrier and latency stalls.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "melif_core.cuh"
 
@@ -471,15 +473,14 @@ melif_ws_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params
       const int nf = lookback ? 1 : min(FB, fe - f0);
       const uint32_t buf = it & 1, use = it >> 1;
       cpx2* z = zA + buf * kBufElems;
-      // band constants first: their L1/L2 latency hides behind the wait and polar
-      RowBand<MEL> band[RPT];
-      if (!lookback) {
-#pragma unroll
-        for (int r = 0; r < RPT; ++r) band[r] = load_row_band<MEL>(p, t + r * kWsPeThreads, dc, w_vec);
-      }
       mbar_wait(bar_full + buf, use & 1);
       polar_item<P, MEL, NP, true>(t, z, P::kPitchA, w_item, dc ? M : 0, lookback, eps, st);
       if (!lookback) {
+        // band constants after polar (held across it they spill): their L1/L2 latency hides
+        // behind the role's barrier
+        RowBand<MEL> band[RPT];
+#pragma unroll
+        for (int r = 0; r < RPT; ++r) band[r] = load_row_band<MEL>(p, t + r * kWsPeThreads, dc, w_vec);
         asm volatile("bar.sync 2, %0;" ::"n"(kWsPeThreads) : "memory");  // every bin of the batch is polar
 #pragma unroll
         for (int r = 0; r < RPT; ++r)
@@ -549,7 +550,13 @@ static int launch_melif_s(const S* audio, int64_t n_notes, int64_t n_samples,
   constexpr int kPer16 = 16 / (int)sizeof(S);
   const int bulk_ok = (n_samples % kPer16 == 0) && (p.hop % kPer16 == 0) &&
                       (p.pad_left % kPer16 == 0) && ((uintptr_t)audio % 16 == 0);
-  if (p.n_fft == 2048 && bulk_ok && p.hop % 2 == 0 && p.hop <= 2048 &&
+  // ISI_MELIF_GENERIC=1 (testing / profiling): keep the NSynth shape on the generic kernel too.
+  // The choice must not depend on the sample format -- PCM and FP32 input of the same notes give
+  // bit-identical spectrograms only through the same kernel (ptxas contracts differently in
+  // different instantiations) -- so the geometry has to be bulk-copyable in BOTH formats.
+  static const bool force_generic = getenv("ISI_MELIF_GENERIC") != nullptr;
+  const bool geometry_ok = (n_samples % 8 == 0) && (p.hop % 8 == 0) && (p.pad_left % 8 == 0);
+  if (!force_generic && p.n_fft == 2048 && bulk_ok && geometry_ok && p.hop <= 2048 &&
       melif_smem_layout<2048, 8>(p.hop, (int)sizeof(S), 2).total <= 227 * 1024)
     return p.use_mel ? launch_melif_ws<true, S>(audio, n_notes, n_samples, p, out, stream)
                      : launch_melif_ws<false, S>(audio, n_notes, n_samples, p, out, stream);

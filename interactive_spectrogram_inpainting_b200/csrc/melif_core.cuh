@@ -93,6 +93,30 @@ ISI_HD cpx2 cadd(cpx2 a, cpx2 b) { cpx2 r; r.re = add2(a.re, b.re); r.im = add2(
 ISI_HD cpx2 csub(cpx2 a, cpx2 b) { cpx2 r; r.re = sub2(a.re, b.re); r.im = sub2(a.im, b.im); return r; }
 ISI_HD cpx2 mul_neg_i(cpx2 a) { cpx2 r; r.re = a.im; r.im = neg2(a.re); return r; }
 
+// Storing a cpx2: ptxas fuses two adjacent 8-byte stores into one STS.128 and then spends up to
+// four MOVs lining the halves up in consecutive registers (the packed instructions leave their
+// results in arbitrary aligned pairs; loads have no such cost, LDS.128 writes a fresh quad).  An
+// offset the assembler cannot see through -- 8, read from constant memory at run time -- keeps
+// the two STS.64, straight from the registers the results were produced in.
+#ifdef __CUDACC__
+static __constant__ int kOpaqueEight = 8;
+#endif
+struct SplitPtr { f2* re; f2* im; };        // element k of the cpx2 array: re[2k], im[2k]
+ISI_HD SplitPtr split_ptr(cpx2* p) {
+  SplitPtr s;
+  s.re = reinterpret_cast<f2*>(p);
+#ifdef __CUDA_ARCH__
+  s.im = reinterpret_cast<f2*>(reinterpret_cast<char*>(p) + kOpaqueEight);
+#else
+  s.im = s.re + 1;
+#endif
+  return s;
+}
+ISI_HD void put(SplitPtr s, int k, cpx2 v) { s.re[2 * k] = v.re; s.im[2 * k] = v.im; }
+// the scalar complex type stores as one 8-byte value
+ISI_HD cpx* split_ptr(cpx* p) { return p; }
+ISI_HD void put(cpx* s, int k, cpx v) { s[k] = v; }
+
 constexpr float kPi = 3.14159265358979323846f;
 constexpr float kHalfPi = 1.57079632679489661923f;
 constexpr float kTwoPi = 6.28318530717958647692f;
@@ -274,8 +298,9 @@ ISI_HD void fft_pass1_finish(int j, C* v, const cpx* tws, C* zA) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) if (p0 + i < P::R1) v[p0 + i] = cmul(v[p0 + i], t[i]);
   }
+  auto o = split_ptr(zA + j);
 #pragma unroll
-  for (int p = 0; p < P::R1; ++p) zA[j + P::kBlockPitch * p] = v[p];
+  for (int p = 0; p < P::R1; ++p) put(o, P::kBlockPitch * p, v[p]);
 }
 
 // Forward kernel: window + pack the two frames of a pair (frame_a / frame_b point at their
@@ -339,8 +364,9 @@ ISI_HD void fft_pass2(int t, const cpx* tws, C* zA) {
         for (int i = 0; i < 4; ++i) if (p0 + i < 16) v[p0 + i] = cmul(v[p0 + i], t[i]);
       }
     }
+    auto ob = split_ptr(blk + j);
 #pragma unroll
-    for (int p = 0; p < 16; ++p) blk[j + 4 * p] = v[p];
+    for (int p = 0; p < 16; ++p) put(ob, 4 * p, v[p]);
   }
 }
 
@@ -371,8 +397,8 @@ ISI_HD void fft_pass3_store(int t, const Pass3Regs<P, C>& r, C* z) {
 #pragma unroll
   for (int i = 0; i < P::R1 / 4; ++i) {
     const int p2 = t / P::R1 + kStep * i;
-    C* o = z + p1 + P::R1 * p2;
-    o[0] = r.q[i][0]; o[16 * P::R1] = r.q[i][1]; o[32 * P::R1] = r.q[i][2]; o[48 * P::R1] = r.q[i][3];
+    auto o = split_ptr(z + p1 + P::R1 * p2);
+    put(o, 0, r.q[i][0]); put(o, 16 * P::R1, r.q[i][1]); put(o, 32 * P::R1, r.q[i][2]); put(o, 48 * P::R1, r.q[i][3]);
   }
 }
 
@@ -396,14 +422,19 @@ constexpr float kMinNorm2 = 4.70197740328915e-38f;      // 2^-124
 
 struct Unit2 { f2 re, im; };                            // unit phasors of one bin, both frames
 
-ISI_HD void unit_mag(cpx2 x, Unit2& u, f2& mag) {
+// |X| is left as its two factors (|X|^2 clamped, 1/|X|): the consumer adds eps with one FFMA2.
+// (ptxas contracts a packed multiply feeding a packed add into FFMA2 when it likes -- even
+// mul.rn.f32x2 + add.rn.f32x2 -- so every such pair in this file is an explicit fma2: results
+// then do not depend on which instantiation the code was inlined into.)
+struct Mag2 { f2 m2, rs; };
+ISI_HD void unit_mag(cpx2 x, Unit2& u, Mag2& mag) {
   const f2 re = add2(x.re, bc(kZeroBias));
   f2 m2 = fma2(re, re, mul2(x.im, x.im));
   m2 = mk2(fmaxf(m2.x, kMinNorm2), fmaxf(m2.y, kMinNorm2));
   const f2 rs = mk2(fast_rsqrt(m2.x), fast_rsqrt(m2.y));
   u.re = mul2(re, rs);
   u.im = mul2(x.im, rs);
-  mag = mul2(m2, rs);
+  mag.m2 = m2; mag.rs = rs;
 }
 
 // arg(u conj p) for unit phasors: (c, s) = (cos, sin) of the angle; the smaller of |c|, |s| is
@@ -459,9 +490,9 @@ ISI_HD void untangle(int it, const cpx2* z, cpx w /* W_N^it */, int real_bin, cp
 // What polar leaves per bin for emit: mel mode (|X|+eps)^2 and the phase step; linear mode
 // log2(|X|+eps) and the phase step (finish_row turns log2 into log and radians into half-turns).
 template <bool MEL>
-ISI_HD cpx2 polar_value(f2 mag, f2 step, float eps) {
+ISI_HD cpx2 polar_value(Mag2 mag, f2 step, float eps) {
   cpx2 r;
-  const f2 a = add2(mag, bc(eps));
+  const f2 a = fma2(mag.m2, mag.rs, bc(eps));          // |X| + eps
   if (MEL) r.re = mul2(a, a);
   else r.re = mk2(fast_log2(a.x), fast_log2(a.y));
   r.im = step;
@@ -493,7 +524,7 @@ ISI_HD void polar_item(int it, cpx2* z, int pitch, cpx w, int real_bin, bool see
   const int ka = special ? M / 2 : it, kb = special ? real_bin : M - it;
   cpx2 xa, xb;
   Unit2 la, lb;          // last pair
-  f2 mla, mlb;
+  Mag2 mla, mlb;
   untangle<P, MAYBE_ZERO>(it, z + (NP - 1) * pitch, w, real_bin, xa, xb);
   unit_mag(xa, la, mla);
   unit_mag(xb, lb, mlb);
@@ -504,16 +535,16 @@ ISI_HD void polar_item(int it, cpx2* z, int pitch, cpx w, int real_bin, bool see
 #pragma unroll
     for (int q = 0; q < NP - 1; ++q) {
       Unit2 ua, ub;
-      f2 ma, mb;
+      Mag2 ma, mb;
       untangle<P, MAYBE_ZERO>(it, z + q * pitch, w, real_bin, xa, xb);
       unit_mag(xa, ua, ma);
       unit_mag(xb, ub, mb);
-      z[q * pitch + ka] = polar_value<MEL>(ma, unit_step(ua, pa), eps);
-      z[q * pitch + kb] = polar_value<MEL>(mb, unit_step(ub, pb), eps);
+      put(split_ptr(z + q * pitch + ka), 0, polar_value<MEL>(ma, unit_step(ua, pa), eps));
+      put(split_ptr(z + q * pitch + kb), 0, polar_value<MEL>(mb, unit_step(ub, pb), eps));
       pa = ua; pb = ub;
     }
-    z[(NP - 1) * pitch + ka] = polar_value<MEL>(mla, unit_step(la, pa), eps);
-    z[(NP - 1) * pitch + kb] = polar_value<MEL>(mlb, unit_step(lb, pb), eps);
+    put(split_ptr(z + (NP - 1) * pitch + ka), 0, polar_value<MEL>(mla, unit_step(la, pa), eps));
+    put(split_ptr(z + (NP - 1) * pitch + kb), 0, polar_value<MEL>(mlb, unit_step(lb, pb), eps));
   }
   st.a = la; st.b = lb;
 }
@@ -539,10 +570,11 @@ ISI_HD void emit_mel(const cpx2* z, int pitch, int bin0, int count_uniform, cons
   f2 m2[NP], mp[NP];
 #pragma unroll
   for (int q = 0; q < NP; ++q) { m2[q] = bc(0.f); mp[q] = bc(0.f); }
-  // two taps per (warp-uniform) step: all 2*NP loads are issued before the first use
+  // two taps per (warp-uniform) step: all 2*NP loads are issued before the first use; an odd
+  // longest band ends with a single tap
 #pragma unroll
   for (int i = 0; i < kMaxMelWidth; i += 2) {
-    if (i < count_uniform) {
+    if (i + 1 < count_uniform) {
       cpx2 va[NP], vb[NP];
 #pragma unroll
       for (int q = 0; q < NP; ++q) { va[q] = z[q * pitch + bin0 + i]; vb[q] = z[q * pitch + bin0 + i + 1]; }
@@ -550,6 +582,15 @@ ISI_HD void emit_mel(const cpx2* z, int pitch, int bin0, int count_uniform, cons
       for (int q = 0; q < NP; ++q) {
         m2[q] = fma2(vb[q].re, bc(w[i + 1]), fma2(va[q].re, bc(w[i]), m2[q]));
         mp[q] = fma2(vb[q].im, bc(w[i + 1]), fma2(va[q].im, bc(w[i]), mp[q]));
+      }
+    } else if (i < count_uniform) {
+      cpx2 va[NP];
+#pragma unroll
+      for (int q = 0; q < NP; ++q) va[q] = z[q * pitch + bin0 + i];
+#pragma unroll
+      for (int q = 0; q < NP; ++q) {
+        m2[q] = fma2(va[q].re, bc(w[i]), m2[q]);
+        mp[q] = fma2(va[q].im, bc(w[i]), mp[q]);
       }
     }
   }

@@ -230,7 +230,8 @@ class CodeExtractor:
     shape whose capture fails (or ``cuda_graph=False``) runs the same calls eagerly.  The model
     must be this repo's ``VQVAE`` in eval mode with fixed weights."""
 
-    def __init__(self, spectrograms_helper, model, device: torch.device, cuda_graph: bool = True):
+    def __init__(self, spectrograms_helper, model, device: torch.device, cuda_graph: bool = True,
+                 prefetch_depth: int = 2):
         if not hasattr(model, "encode_codes"):
             raise TypeError("CodeExtractor needs this repo's VQVAE (encode_codes)")
         self.helper, self.model, self.device = spectrograms_helper, model.eval(), device
@@ -238,7 +239,10 @@ class CodeExtractor:
         self.space_to_depth = bool(getattr(spectrograms_helper, "space_to_depth", False))
         self._graphs = {}
         self._side = torch.cuda.Stream(device)
-        self._dev_audio = [None, None]
+        # uploads run `prefetch_depth` batches ahead of the compute (two: a slow copy -- eight
+        # ranks share one host's memory and PCIe switches -- does not stall the next step)
+        self.prefetch_depth = max(1, int(prefetch_depth))
+        self._dev_audio = [None] * (self.prefetch_depth + 1)
         self._host_codes = [None, None]
         self.graph_failures: List[str] = []
 
@@ -262,7 +266,8 @@ class CodeExtractor:
     def run(self, source: Iterable[Tuple[torch.Tensor, Sequence[str]]],
             sink: Optional[Callable[[List[CodeRow]], None]] = None) -> List[CodeRow]:
         main, side = torch.cuda.current_stream(self.device), self._side
-        consumed = [None, None]          # per slot: the step that read the device copy is enqueued
+        n_slots = self.prefetch_depth + 1
+        consumed = [None] * n_slots      # per slot: the step that read the device copy is enqueued
         rows: List[CodeRow] = []
 
         def upload(item, slot):
@@ -301,20 +306,31 @@ class CodeExtractor:
                 sink(batch_rows)
             rows.extend(batch_rows)
 
+        from collections import deque
         it = iter(source)
-        first = next(it, None)
-        uploaded = upload(first, 0) if first is not None else None
+        uploads, next_slot = deque(), 0
+
+        def top_up():
+            # a new upload takes the slot of the step BEFORE the current one: already enqueued,
+            # its `consumed` event recorded
+            nonlocal next_slot
+            while len(uploads) < self.prefetch_depth:
+                item = next(it, None)
+                if item is None:
+                    return
+                uploads.append(upload(item, next_slot) + (next_slot,))
+                next_slot = (next_slot + 1) % n_slots
+
+        top_up()
         pending, step = None, 0
-        while uploaded is not None:
-            audio, names, attributes, ready = uploaded
-            slot = step % 2
-            nxt = next(it, None)
-            uploaded = upload(nxt, 1 - slot) if nxt is not None else None
+        while uploads:
+            audio, names, attributes, ready, slot = uploads.popleft()
+            top_up()
             main.wait_event(ready)
             id_t, id_b = self._step(audio)
             consumed[slot] = torch.cuda.Event()
             consumed[slot].record(main)
-            host_t, host_b = host_pair(slot, id_t, id_b)
+            host_t, host_b = host_pair(step % 2, id_t, id_b)
             host_t.copy_(id_t, non_blocking=True)
             host_b.copy_(id_b, non_blocking=True)
             done = torch.cuda.Event()

@@ -38,7 +38,7 @@ for n in (1, 4, 300):
       timeout 900 python bench.py --steps 20 --warmup 3 2>&1 | tail -1 > gpurun_out/bench_$tag.json
       cut -c1-400 gpurun_out/bench_$tag.json ;;
     ncu_melif)
-      timeout 600 ncu --set full --clock-control none --import-source on -k regex:melif_kernel -s 3 -c 1 \
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:'^melif_(ws_)?kernel|isi::melif' -s 3 -c 1 \
         -o gpurun_out/melif_$tag python bench.py --steps 2 --warmup 3 --no-cpu-baseline --assign-algo simt > gpurun_out/ncu_melif_$tag.log 2>&1
       tail -1 gpurun_out/ncu_melif_$tag.log | cut -c1-200 ;;
     ncu_assign)
@@ -111,6 +111,8 @@ for n in (1, 4, 300):
       timeout 300 python __graft_entry__.py smoke 2>&1 | tail -2 ;;
     probe)
       timeout 120 ./tools/umma_probe.bin 2>&1 | tee gpurun_out/umma_probe_$tag.log ;;
+    diag)
+      timeout 200 python tools/diag_melif.py 2>&1 | tail -40 ;;
     e2e_parity)
       timeout 600 python -m pytest tests/test_gpu_e2e_parity.py -x -q -s 2>&1 | tail -30 > gpurun_out/pytest_e2e_parity_$tag.log
       tail -12 gpurun_out/pytest_e2e_parity_$tag.log ;;
