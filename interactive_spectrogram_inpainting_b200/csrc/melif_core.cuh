@@ -93,26 +93,14 @@ ISI_HD cpx2 cadd(cpx2 a, cpx2 b) { cpx2 r; r.re = add2(a.re, b.re); r.im = add2(
 ISI_HD cpx2 csub(cpx2 a, cpx2 b) { cpx2 r; r.re = sub2(a.re, b.re); r.im = sub2(a.im, b.im); return r; }
 ISI_HD cpx2 mul_neg_i(cpx2 a) { cpx2 r; r.re = a.im; r.im = neg2(a.re); return r; }
 
-// Storing a cpx2: ptxas fuses two adjacent 8-byte stores into one STS.128 and then spends up to
-// four MOVs lining the halves up in consecutive registers (the packed instructions leave their
-// results in arbitrary aligned pairs; loads have no such cost, LDS.128 writes a fresh quad).  An
-// offset the assembler cannot see through -- 8, read from constant memory at run time -- keeps
-// the two STS.64, straight from the registers the results were produced in.
-#ifdef __CUDACC__
-static __constant__ int kOpaqueEight = 8;
-#endif
-struct SplitPtr { f2* re; f2* im; };        // element k of the cpx2 array: re[2k], im[2k]
-ISI_HD SplitPtr split_ptr(cpx2* p) {
-  SplitPtr s;
-  s.re = reinterpret_cast<f2*>(p);
-#ifdef __CUDA_ARCH__
-  s.im = reinterpret_cast<f2*>(reinterpret_cast<char*>(p) + kOpaqueEight);
-#else
-  s.im = s.re + 1;
-#endif
-  return s;
-}
-ISI_HD void put(SplitPtr s, int k, cpx2 v) { s.re[2 * k] = v.re; s.im[2 * k] = v.im; }
+// Storing a cpx2 is ONE 16-byte store.  (ptxas then spends up to four MOVs lining the halves up
+// in consecutive registers, because the packed instructions leave their results in arbitrary
+// aligned pairs.  Measured alternative, profiles/r02_melif_ws_split_stores_r2e: two 8-byte
+// stores need no MOVs but sit 16 bytes apart across lanes, a 2-way bank conflict each -- 65.3 M
+// instead of 53.0 M shared-memory wavefronts per 444 notes and a slower kernel.)
+struct SplitPtr { cpx2* p; };
+ISI_HD SplitPtr split_ptr(cpx2* p) { SplitPtr s; s.p = p; return s; }
+ISI_HD void put(SplitPtr s, int k, cpx2 v) { s.p[k] = v; }
 // the scalar complex type stores as one 8-byte value
 ISI_HD cpx* split_ptr(cpx* p) { return p; }
 ISI_HD void put(cpx* s, int k, cpx v) { s[k] = v; }
@@ -374,15 +362,17 @@ ISI_HD void fft_pass2(int t, const cpx* tws, C* zA) {
 //      order (bin p1 + R1 p2 + 16 R1 p3).  Load + butterfly and store are two calls with the
 //      transform group's barrier between them, because the natural-order slots overlap other
 //      threads' quadruples.  Lanes run along p1, so the stores are contiguous. ----
-template <typename P, typename C>
-struct Pass3Regs { C q[P::R1 / 4][4]; };
+// NT3 = threads sharing one transform's quadruples (64: the transform group itself; 128: a
+// quarter of the warp-specialised kernel's polar/emit role, which takes this pass over).
+template <typename P, typename C, int NT3 = P::kFftThreads>
+struct Pass3Regs { C q[(P::M / 4) / NT3][4]; };
 
-template <typename P, typename C>
-ISI_HD void fft_pass3_load(int t, const C* zA, Pass3Regs<P, C>& r) {
-  constexpr int kStep = P::kFftThreads / P::R1;          // p2 values covered per sweep
+template <typename P, typename C, int NT3>
+ISI_HD void fft_pass3_load(int t, const C* zA, Pass3Regs<P, C, NT3>& r) {
+  constexpr int kStep = NT3 / P::R1;                     // p2 values covered per sweep
   const int p1 = t % P::R1;
 #pragma unroll
-  for (int i = 0; i < P::R1 / 4; ++i) {
+  for (int i = 0; i < (P::M / 4) / NT3; ++i) {
     const int p2 = t / P::R1 + kStep * i;
     const C* q = zA + P::kBlockPitch * p1 + 4 * p2;
     r.q[i][0] = q[0]; r.q[i][1] = q[1]; r.q[i][2] = q[2]; r.q[i][3] = q[3];
@@ -390,12 +380,12 @@ ISI_HD void fft_pass3_load(int t, const C* zA, Pass3Regs<P, C>& r) {
   }
 }
 
-template <typename P, typename C>
-ISI_HD void fft_pass3_store(int t, const Pass3Regs<P, C>& r, C* z) {
-  constexpr int kStep = P::kFftThreads / P::R1;
+template <typename P, typename C, int NT3>
+ISI_HD void fft_pass3_store(int t, const Pass3Regs<P, C, NT3>& r, C* z) {
+  constexpr int kStep = NT3 / P::R1;
   const int p1 = t % P::R1;
 #pragma unroll
-  for (int i = 0; i < P::R1 / 4; ++i) {
+  for (int i = 0; i < (P::M / 4) / NT3; ++i) {
     const int p2 = t / P::R1 + kStep * i;
     auto o = split_ptr(z + p1 + P::R1 * p2);
     put(o, 0, r.q[i][0]); put(o, 16 * P::R1, r.q[i][1]); put(o, 32 * P::R1, r.q[i][2]); put(o, 48 * P::R1, r.q[i][3]);
