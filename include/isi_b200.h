@@ -234,13 +234,6 @@ typedef struct isi_melif_params {
   /* converts on the CPU and uploads FP32; reading PCM halves the host->device bytes)          */
   int32_t audio_format;     /* isi_audio_format                                                */
   float pcm_scale;          /* PCM16 only: sample = (float)pcm * pcm_scale (e.g. 1/32768)      */
-  const int32_t* row_order; /* optional [n_fft/2] permutation, slot -> output row, that only   */
-                            /* moves rows inside their block of 32 (one warp).  Thread slot i  */
-                            /* emits row row_order[i]; a caller that groups, in every 8 slots,  */
-                            /* rows whose mel_start differ mod 8 makes the quarter-warps' 16-   */
-                            /* byte shared-memory reads bank-conflict free (the band of output  */
-                            /* row r starts mel_start[r] bins in: neighbouring rows 2-3 bins    */
-                            /* apart collide).  NULL = identity.  Results do not depend on it.  */
 } isi_melif_params;
 
 typedef enum { ISI_AUDIO_F32 = 0, ISI_AUDIO_PCM16 = 1 } isi_audio_format;

@@ -39,8 +39,7 @@ class MelifParams(ctypes.Structure):
                 ("mel_weight", ctypes.c_void_p), ("channels_last", ctypes.c_int32),
                 ("mask_phase", ctypes.c_int32), ("mask_threshold", ctypes.c_float),
                 ("out_scale", ctypes.c_float * 2), ("out_bias", ctypes.c_float * 2),
-                ("audio_format", ctypes.c_int32), ("pcm_scale", ctypes.c_float),
-                ("row_order", ctypes.c_void_p)]
+                ("audio_format", ctypes.c_int32), ("pcm_scale", ctypes.c_float)]
 
 
 class ImelifParams(ctypes.Structure):

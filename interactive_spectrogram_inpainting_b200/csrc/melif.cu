@@ -85,15 +85,11 @@ __device__ __forceinline__ void st_stream4(float* p, float4 v) {
 template <bool MEL>
 struct RowBand { int row, bin, cnt; float w[MEL ? kMaxMelWidth : 1]; };
 
-// `slot` = the thread's position; the row it emits is row_order[slot] when the caller ordered
-// the rows of each warp for conflict-free band reads (isi_melif_params.row_order).
 template <bool MEL>
-__device__ __forceinline__ RowBand<MEL> load_row_band(const isi_melif_params& p, int slot, int dc, bool w_vec) {
+__device__ __forceinline__ RowBand<MEL> load_row_band(const isi_melif_params& p, int row, int dc, bool w_vec) {
   RowBand<MEL> b;
-  const int row = p.row_order ? ld_table(p.row_order + slot) : slot;
   b.row = row;
   b.bin = row + dc;
-  if ((unsigned)row >= (unsigned)P_M_PLACEHOLDER) { b.cnt = 0; return b; }
   b.cnt = 0;
   if (MEL) {
     b.bin = ld_table(p.mel_start + row) + dc;
@@ -121,7 +117,6 @@ __device__ __forceinline__ void emit_row(const isi_melif_params& p, const cpx2* 
                                          int note_idx, int f0, int nf, float eps, float* out) {
   constexpr int M = P::M, NP = FB / 2;
   const int row = band.row;
-  if ((unsigned)row >= (unsigned)M) return;      // a malformed row_order must not write out of bounds
   f2 lg[NP], ph[NP];
   if (MEL) {
     const int cnt_warp = __reduce_max_sync(0xffffffffu, band.cnt);
@@ -359,11 +354,13 @@ melif_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params p,
 //
 // One CTA per SM, 24 warps in two roles that run CONCURRENTLY on consecutive batches of
 // FB = 8 frames through a double-buffered workspace:
-//   * 8 transform warps (4 groups of 64 threads, one frame pair each): stage wait and the two
-//     radix-16 FFT passes; 112 registers (setmaxnreg.inc) for the 16-point butterflies of a pair;
-//   * 16 polar/emit warps (512 threads, one untangle item and two output rows each): the cheap
-//     radix-4 pass 3 and polar of the batch the transform warps finished last, then the mel
-//     projection, log / wrap, epilogue and stores; 64 registers (setmaxnreg.dec).
+//   * 8 transform warps (4 groups of 64 threads, one frame pair each): stage wait, the three
+//     FFT passes; 112 registers (setmaxnreg.inc) for the 16-point butterflies of a pair;
+//   * 16 polar/emit warps (512 threads, one untangle item and two output rows each): polar
+//     of the batch the transform warps finished last, then the mel projection, log / wrap,
+//     epilogue and stores; 64 registers (setmaxnreg.dec).
+// (Measured, profiles/README.md: the two roles are balanced within a few percent -- moving the
+// radix-4 pass 3 to the polar/emit role made THAT role the critical path, 0.373 vs 0.328 ms.)
 // The generic kernel gives every thread the transform's register budget, which caps an SM at
 // 16 warps; here the registers are split by need, so 24 warps are resident, and the FMA-heavy
 // transform overlaps the LDS / MUFU / store-heavy emit instead of alternating with it.  The
@@ -432,6 +429,7 @@ melif_ws_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params
     // =========================== transform warps ===========================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kWsFftRegs));
     const int q = tid >> 6, j = tid & 63;                  // frame pair of this group, lane in it
+    const uint32_t group_bar = 3 + q;
     stage_span_bulk(stage, note, n_samples, p.hop, p.pad_left, NFFT, fs > 0 ? fs - 1 : fs,
                     fs > 0 ? 1 : min(FB, fe - fs), tid, kWsFftThreads, tid == 0, bar_stage);
     uint32_t it = 0;
@@ -455,8 +453,15 @@ melif_ws_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params
       if (next_nf > 0)
         stage_span_bulk(stage, note, n_samples, p.hop, p.pad_left, NFFT, next_f0, next_nf, tid,
                         kWsFftThreads, tid == 0, bar_stage);
-      if (active) fft_pass2<P>(j, twm, z);                 // pass 3 belongs to the polar/emit role
-      mbar_arrive(bar_full + buf);                         // release: passes 1 and 2 are in place
+      if (active) {
+        fft_pass2<P>(j, twm, z);
+        asm volatile("bar.sync %0, 64;" ::"r"(group_bar) : "memory");
+        Pass3Regs<P, cpx2> regs;
+        fft_pass3_load<P>(j, z, regs);
+        asm volatile("bar.sync %0, 64;" ::"r"(group_bar) : "memory");
+        fft_pass3_store<P>(j, regs, z);
+      }
+      mbar_arrive(bar_full + buf);                         // release: the spectrum is in place
     }
   } else {
     // =========================== polar / emit warps ===========================
@@ -473,19 +478,6 @@ melif_ws_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params
       const uint32_t buf = it & 1, use = it >> 1;
       cpx2* z = zA + buf * kBufElems;
       mbar_wait(bar_full + buf, use & 1);
-      // pass 3 (radix 4, natural-order rewrite) of pair t / 128 by its quarter of the role: the
-      // transform warps are the critical path, this role has the slack
-      {
-        constexpr int kQuarter = kWsPeThreads / NP;        // 128 threads per pair
-        const int q3 = t / kQuarter, u = t % kQuarter;
-        const bool active3 = lookback ? (q3 == NP - 1) : (q3 < nf);
-        cpx2* z3 = z + q3 * P::kPitchA;
-        Pass3Regs<P, cpx2, kQuarter> regs;
-        if (active3) fft_pass3_load<P>(u, z3, regs);
-        asm volatile("bar.sync %0, %1;" ::"r"(7 + q3), "n"(kQuarter) : "memory");
-        if (active3) fft_pass3_store<P>(u, regs, z3);
-        asm volatile("bar.sync 2, %0;" ::"n"(kWsPeThreads) : "memory");   // every pair is in natural order
-      }
       polar_item<P, MEL, NP, true>(t, z, P::kPitchA, w_item, dc ? M : 0, lookback, eps, st);
       if (!lookback) {
         // band constants after polar (held across it they spill): their L1/L2 latency hides
