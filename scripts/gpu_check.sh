@@ -116,12 +116,12 @@ for n in (1, 4, 300):
     stress)
       timeout 600 python -m pytest tests/test_gpu_stats_stress.py -q 2>&1 | tail -5 ;;
     ncu_pair)
-      timeout 600 ncu --set full --clock-control none --import-source on -k regex:vq_assign_pair_kernel -s 6 -c 1 \
-        -o gpurun_out/assign_pair_$tag python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_pair_$tag.log 2>&1
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:vq_assign_pair_kernel -s 3 -c 1 \
+        -o gpurun_out/assign_pair_$tag python tools/ncu_targets.py pair > gpurun_out/ncu_pair_$tag.log 2>&1
       tail -1 gpurun_out/ncu_pair_$tag.log | cut -c1-200 ;;
     ncu_pstream)
-      timeout 600 ncu --set full --clock-control none --import-source on -k regex:vq_assign_pstream -s 1 -c 1 \
-        -o gpurun_out/assign_pstream_$tag python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_pstream_$tag.log 2>&1
+      timeout 600 ncu --set full --clock-control none --import-source on -k regex:vq_assign_pstream -s 3 -c 1 \
+        -o gpurun_out/assign_pstream_$tag python tools/ncu_targets.py pstream > gpurun_out/ncu_pstream_$tag.log 2>&1
       tail -1 gpurun_out/ncu_pstream_$tag.log | cut -c1-200 ;;
     diag)
       timeout 200 python tools/diag_melif.py 2>&1 | tail -40 ;;
