@@ -262,7 +262,9 @@ def train_step_leg(dev, rank, world, local, steps=8, warmup=3, batch=64):
     model = VQVAE(**MODEL_KW).to(dev).to(memory_format=torch.channels_last).train()
     net = model
     if world > 1:       # the quantisers keep their own buffers in sync: no per-forward broadcast
-        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], broadcast_buffers=False)
+        # gradients live in the reducer's buckets (no copy kernels per step); the graph is static
+        net = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], broadcast_buffers=False,
+                                                        gradient_as_bucket_view=True, static_graph=True)
     opt = torch.optim.Adam(net.parameters(), lr=3e-4)
     audio = synthetic.synthetic_notes(batch, seed=synthetic.AUDIO_SEED + 1000 + rank).to(dev)
     model.ema_exchange.time_collective = True
@@ -320,7 +322,7 @@ def train_step_leg(dev, rank, world, local, steps=8, warmup=3, batch=64):
     return {"what": "cfg3: VQ-VAE-2 training step (front end + forward + loss + backward + Adam), "
                     f"batch {batch} per GPU" + (", DDP + one packed async EMA all-reduce per step" if world > 1 else ""),
             "ms_per_step": ms.item(), "notes_per_s": world * batch / (ms.item() * 1e-3), "steps": steps,
-            "loss": float(loss), "isi_kernels_ms_per_step": round(sum(per_call.values()), 4),
+            "loss": float(loss.detach()), "isi_kernels_ms_per_step": round(sum(per_call.values()), 4),
             "ema_allreduces_per_step": (len(span) / steps) if world > 1 else 0,
             "ema_allreduce_bytes": 4 * 2 * N_EMBED * (1 + DIM) if world > 1 else 0,
             "ema_allreduce_launch_to_wait_ms": (sum(span) / max(1, len(span))) if span else 0.0,
