@@ -74,21 +74,29 @@ class NvmlClockSampler:
         except Exception:
             self.nvml = None
 
-    def _run(self):
+    def sample_now(self):
+        """One sample from the calling thread (the sampler thread may not get the GIL inside a
+        50 ms window of back-to-back launches; the host runs ahead of the GPU, so a query from
+        inside the timed loop does not touch the device timeline)."""
         n = self.nvml
+        if n is None:
+            return
+        try:
+            sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
+            mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
+            try:
+                rs = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
+            except Exception:
+                rs = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
+            with self.lock:
+                self.samples.append((sm, mx, rs))
+        except Exception:
+            pass
+
+    def _run(self):
         while not self.done:
             if self.active:
-                try:
-                    sm = n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM)
-                    mx = n.nvmlDeviceGetMaxClockInfo(self.handle, n.NVML_CLOCK_SM)
-                    try:
-                        rs = n.nvmlDeviceGetCurrentClocksEventReasons(self.handle)
-                    except Exception:
-                        rs = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle)
-                    with self.lock:
-                        self.samples.append((sm, mx, rs))
-                except Exception:
-                    pass
+                self.sample_now()
             time.sleep(0.004)
 
     def start(self):
@@ -458,8 +466,10 @@ def b200_arm(args):
     t0, t1 = ev(), ev()
     t0.record()
     _lib.event_log = []            # every C-ABI call of the timed region gets CUDA events
-    for _ in range(K):
+    for i in range(K):
         step(audio)
+        if i in (K // 4, K // 2, (3 * K) // 4):
+            clocks.sample_now()
     t1.record()
     barrier()
     clocks.stop()

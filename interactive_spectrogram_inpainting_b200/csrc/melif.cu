@@ -176,21 +176,26 @@ __device__ __forceinline__ void emit_row(const isi_melif_params& p, const cpx2* 
   }
 }
 
-// Stage the audio span of frames [frame, frame + nfr) of `note`: threads [t, nt) zero-fill what
-// lies outside the note, `issuer` sends one bulk copy for the rest (completion on `bar`).
+// Stage the audio span of frames [frame, frame + nfr) of `note`: threads t of nt zero-fill what
+// lies outside the note (`fill`), ONE thread sends one bulk copy for the rest (`issue`;
+// completion on `bar`).  The zero-fill must be ordered before the issuer's arrive (a CTA / role
+// barrier, or __syncwarp when the filling threads are the issuer's warp).
 template <typename S>
-__device__ __forceinline__ void stage_span_bulk(S* stage, const S* note, int64_t n_samples, int hop, int pad_left,
-                                                int n_fft, int frame, int nfr, int t, int nt, bool issuer,
-                                                uint64_t* bar) {
-  const int span = (nfr - 1) * hop + n_fft;
-  const int64_t s0 = (int64_t)frame * hop - pad_left;
-  const int64_t lo = s0 < 0 ? -s0 : 0;                      // first valid index
-  int64_t hi = n_samples - s0;                              // one past the last valid index
-  hi = hi < 0 ? 0 : (hi > span ? span : hi);
-  const int64_t vlo = lo < hi ? lo : hi;
-  for (int i = t; i < vlo; i += nt) stage[i] = S(0);
-  for (int i = (int)hi + t; i < span; i += nt) stage[i] = S(0);
-  if (issuer) {
+struct StageSpan {
+  int span; int64_t s0, lo, hi;
+  __device__ StageSpan(int64_t n_samples, int hop, int pad_left, int n_fft, int frame, int nfr) {
+    span = (nfr - 1) * hop + n_fft;
+    s0 = (int64_t)frame * hop - pad_left;
+    lo = s0 < 0 ? -s0 : 0;                                  // first valid index
+    hi = n_samples - s0;                                    // one past the last valid index
+    hi = hi < 0 ? 0 : (hi > span ? span : hi);
+  }
+  __device__ void fill(S* stage, int t, int nt) const {
+    const int64_t vlo = lo < hi ? lo : hi;
+    for (int i = t; i < vlo; i += nt) stage[i] = S(0);
+    for (int i = (int)hi + t; i < span; i += nt) stage[i] = S(0);
+  }
+  __device__ void issue(S* stage, const S* note, uint64_t* bar) const {
     if (hi > lo) {
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       const uint32_t bytes = (uint32_t)(hi - lo) * (uint32_t)sizeof(S);
@@ -200,6 +205,14 @@ __device__ __forceinline__ void stage_span_bulk(S* stage, const S* note, int64_t
       mbar_arrive(bar);
     }
   }
+};
+template <typename S>
+__device__ __forceinline__ void stage_span_bulk(S* stage, const S* note, int64_t n_samples, int hop, int pad_left,
+                                                int n_fft, int frame, int nfr, int t, int nt, bool issuer,
+                                                uint64_t* bar) {
+  const StageSpan<S> sp(n_samples, hop, pad_left, n_fft, frame, nfr);
+  sp.fill(stage, t, nt);
+  if (issuer) sp.issue(stage, note, bar);
 }
 
 struct MelifSmem {
@@ -213,7 +226,7 @@ __host__ __device__ inline MelifSmem melif_smem_layout(int hop, int sample_bytes
   int off = 0;
   s.tw = off;    off += (NFFT / 2) * 8;                     // FFT twiddles (fft_table_source)
   s.win = off;   off += NFFT * 4;
-  s.stage = off; off += (((FB - 1) * hop + NFFT) * sample_bytes + 15) / 16 * 16;
+  s.stage = off; off += n_buffers * ((((FB - 1) * hop + NFFT) * sample_bytes + 15) / 16 * 16);
   s.za = off;    off += n_buffers * (FB / 2) * P::kPitchA * 16;   // FFT workspace, spectrum, polar values
   s.bar = off;   off += 64;
   s.total = off;
@@ -369,32 +382,48 @@ melif_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params p,
 // setmaxnreg.dec released, 8 x 32 x (112 - 80) = 16 x 32 x (80 - 64).  Hand-off: full[buf] / empty[buf] mbarriers
 // (transform -> polar/emit -> transform); role-wide named barriers inside each role.
 // ------------------------------------------------------------------------------------------
-constexpr int kWsFftThreads = 256, kWsPeThreads = 512, kWsThreads = kWsFftThreads + kWsPeThreads;
+// Geometry of one instantiation: FB = 8 is one CTA of 768 threads per SM, FB = 4 two CTAs of 384
+// (same 24 warps per SM and the same registers per thread; two CTAs fill each other's pipeline
+// fill / drain and set-up bubbles, at twice the per-batch fixed work).
+template <int FB>
+struct WsGeometry {
+  static constexpr int kPairs = FB / 2;
+  static constexpr int kFftThreads = 64 * kPairs;          // one group of 64 per frame pair
+  static constexpr int kPeThreads = 2 * kFftThreads;
+  static constexpr int kThreads = kFftThreads + kPeThreads;
+  static constexpr int kCtasPerSm = 768 / kThreads;
+  static_assert(kThreads * kCtasPerSm == 768, "24 warps per SM");
+};
 constexpr int kWsFftRegs = 112, kWsPeRegs = 64, kWsLaunchRegs = 80;
-static_assert(kWsFftThreads * (kWsFftRegs - kWsLaunchRegs) <= kWsPeThreads * (kWsLaunchRegs - kWsPeRegs),
+static_assert(1 * (kWsFftRegs - kWsLaunchRegs) <= 2 * (kWsLaunchRegs - kWsPeRegs),
               "setmaxnreg.inc would wait forever for registers nobody releases");
-static_assert(kWsThreads * kWsLaunchRegs <= 65536 && kWsThreads * (kWsLaunchRegs + 8) > 65536,
-              "kWsLaunchRegs must be what __launch_bounds__(kWsThreads, 1) gives");
+static_assert(768 * kWsLaunchRegs <= 65536 && 768 * (kWsLaunchRegs + 8) > 65536,
+              "kWsLaunchRegs must be what __launch_bounds__ gives 768 threads per SM");
 
 template <int FB, bool MEL, typename S>
-__global__ void __launch_bounds__(kWsThreads, 1)
+__global__ void __launch_bounds__(WsGeometry<FB>::kThreads, WsGeometry<FB>::kCtasPerSm)
 melif_ws_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params p,
                 float* __restrict__ out, int seg_frames, int n_segs) {
   constexpr int NFFT = 2048;
   using P = Plan<NFFT>;
   constexpr int M = P::M, NP = FB / 2;
+  constexpr int kWsFftThreads = WsGeometry<FB>::kFftThreads, kWsPeThreads = WsGeometry<FB>::kPeThreads;
+  constexpr int kWsThreads = WsGeometry<FB>::kThreads;
   static_assert(NP == kWsFftThreads / 64, "one transform group per frame pair");
-  static_assert(M / 2 == kWsPeThreads, "one untangle item per polar/emit thread");
-  constexpr int RPT = M / kWsPeThreads;
+  constexpr int IPT = (M / 2) / kWsPeThreads;         // untangle items per polar/emit thread
+  constexpr int RPT = M / kWsPeThreads;               // output rows per polar/emit thread
+  static_assert(IPT * kWsPeThreads == M / 2, "whole items per thread");
   extern __shared__ __align__(128) unsigned char smem[];
   const MelifSmem L = melif_smem_layout<NFFT, FB>(p.hop, (int)sizeof(S), 2);
   cpx* twm = reinterpret_cast<cpx*>(smem + L.tw);
   float* win = reinterpret_cast<float*>(smem + L.win);
   S* stage = reinterpret_cast<S*>(smem + L.stage);
   cpx2* zA = reinterpret_cast<cpx2*>(smem + L.za);         // [2][NP][kPitchA]
-  uint64_t* bar_stage = reinterpret_cast<uint64_t*>(smem + L.bar);
-  uint64_t* bar_full = bar_stage + 1;                      // [2] transform -> polar/emit
-  uint64_t* bar_empty = bar_stage + 3;                     // [2] polar/emit -> transform
+  uint64_t* bar_stage = reinterpret_cast<uint64_t*>(smem + L.bar);   // [2] audio of a batch has landed
+  uint64_t* bar_full = bar_stage + 2;                      // [2] transform -> polar/emit
+  uint64_t* bar_empty = bar_stage + 4;                     // [2] polar/emit -> transform
+  uint64_t* bar_pass1 = bar_stage + 6;                     // [2] every transform thread is done with a stage
+  const int stage_elems = ((((FB - 1) * p.hop + NFFT) * (int)sizeof(S) + 15) / 16 * 16) / (int)sizeof(S);
   constexpr int kBufElems = NP * P::kPitchA;
 
   const int tid = threadIdx.x;
@@ -413,7 +442,10 @@ melif_ws_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params
   for (int i = tid; i < NFFT; i += kWsThreads) win[i] = p.window[i] * win_scale;
   for (int i = tid; i < 2 * kBufElems; i += kWsThreads) { zA[i].re = bc(0.f); zA[i].im = bc(0.f); }
   if (tid == 0) {
-    mbar_init(bar_stage, 1);
+    mbar_init(bar_stage + 0, 1);
+    mbar_init(bar_stage + 1, 1);
+    mbar_init(bar_pass1 + 0, kWsFftThreads);
+    mbar_init(bar_pass1 + 1, kWsFftThreads);
     mbar_init(bar_full + 0, kWsFftThreads);
     mbar_init(bar_full + 1, kWsFftThreads);
     mbar_init(bar_empty + 0, kWsPeThreads);
@@ -425,13 +457,26 @@ melif_ws_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params
   const int n_batches = (fe - fs + FB - 1) / FB;
   const int b_begin = fs > 0 ? -1 : 0;
 
-  if (tid < kWsFftThreads) {
+  // The transform role takes the HIGHEST warp ids: the SMSP arbiter prefers the highest eligible
+  // warp, and the transform warps are the critical path (13 % of their stall samples were
+  // "not selected" while they sat below the polar/emit warps).
+  if (tid >= kWsPeThreads) {
     // =========================== transform warps ===========================
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kWsFftRegs));
-    const int q = tid >> 6, j = tid & 63;                  // frame pair of this group, lane in it
+    const int ft = tid - kWsPeThreads;                     // 0 .. kWsFftThreads - 1
+    const int q = ft >> 6, j = ft & 63;                    // frame pair of this group, lane in it
     const uint32_t group_bar = 3 + q;
-    stage_span_bulk(stage, note, n_samples, p.hop, p.pad_left, NFFT, fs > 0 ? fs - 1 : fs,
-                    fs > 0 ? 1 : min(FB, fe - fs), tid, kWsFftThreads, tid == 0, bar_stage);
+    // The audio stage is double-buffered and fed by the first transform warp alone (its lanes
+    // zero-fill what lies outside the note, lane 0 sends the bulk copy; the mbarrier's release /
+    // acquire carries both to the readers), so the four groups never meet on a role-wide
+    // barrier: they drift apart and their load bursts and butterfly phases interleave.
+    const bool feeder = ft < 32;
+    if (feeder) {
+      const StageSpan<S> sp(n_samples, p.hop, p.pad_left, NFFT, fs > 0 ? fs - 1 : fs, fs > 0 ? 1 : min(FB, fe - fs));
+      sp.fill(stage, ft, 32);
+      __syncwarp();
+      if (ft == 0) sp.issue(stage, note, bar_stage);
+    }
     uint32_t it = 0;
     for (int b = b_begin; b < n_batches; ++b, ++it) {
       const bool lookback = b < 0;
@@ -441,18 +486,26 @@ melif_ws_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params
       const int next_nf = (b + 1 < n_batches) ? min(FB, fe - next_f0) : 0;
       const uint32_t buf = it & 1, use = it >> 1;
       cpx2* z = zA + buf * kBufElems + q * P::kPitchA;
+      const S* st_cur = stage + buf * stage_elems;
       const bool active = lookback ? (q == NP - 1) : (q < nf);
 
-      mbar_wait(bar_stage, it & 1);                        // this batch's audio has landed
-      mbar_wait(bar_empty + buf, (use & 1) ^ 1);           // polar/emit released the buffer
-      asm volatile("bar.sync 1, %0;" ::"n"(kWsFftThreads) : "memory");   // zero-filled pads are visible
+      if (feeder && next_nf > 0) {
+        // the other stage buffer was read by pass 1 of the previous batch: all 256 threads have
+        // arrived on its barrier by now (they are at most a pass or two behind)
+        if (it > 0) mbar_wait(bar_pass1 + (buf ^ 1), ((it - 1) >> 1) & 1);
+        S* st_next = stage + (buf ^ 1) * stage_elems;
+        const StageSpan<S> sp(n_samples, p.hop, p.pad_left, NFFT, next_f0, next_nf);
+        sp.fill(st_next, ft, 32);
+        __syncwarp();
+        if (ft == 0) sp.issue(st_next, note, bar_stage + (buf ^ 1));
+      }
+      mbar_wait(bar_stage + buf, use & 1);                 // this batch's audio has landed
+      mbar_wait(bar_empty + buf, (use & 1) ^ 1);           // polar/emit released the workspace
       if (active)
-        fft_pass1_pair<P>(j, stage + (lookback ? 0 : q * p.hop), stage + (lookback ? 0 : (q + NP) * p.hop),
+        fft_pass1_pair<P>(j, st_cur + (lookback ? 0 : q * p.hop), st_cur + (lookback ? 0 : (q + NP) * p.hop),
                           true, sample_scale, win, twm, z);
-      asm volatile("bar.sync 1, %0;" ::"n"(kWsFftThreads) : "memory");   // every group is done with the stage
-      if (next_nf > 0)
-        stage_span_bulk(stage, note, n_samples, p.hop, p.pad_left, NFFT, next_f0, next_nf, tid,
-                        kWsFftThreads, tid == 0, bar_stage);
+      mbar_arrive(bar_pass1 + buf);                        // done with this stage buffer
+      if (active) asm volatile("bar.sync %0, 64;" ::"r"(group_bar) : "memory");
       if (active) {
         fft_pass2<P>(j, twm, z);
         asm volatile("bar.sync %0, 64;" ::"r"(group_bar) : "memory");
@@ -466,10 +519,14 @@ melif_ws_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params
   } else {
     // =========================== polar / emit warps ===========================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kWsPeRegs));
-    const int t = tid - kWsFftThreads;                     // 0 .. 511: untangle item and first row
-    const cpx w_item = tw_global[t];
+    const int t = tid;                                     // 0 .. 511: untangle item and first row
+    cpx w_item[IPT];
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) w_item[i] = tw_global[t + i * kWsPeThreads];
     const bool w_vec = MEL && p.mel_width == kMaxMelWidth && (reinterpret_cast<uintptr_t>(p.mel_weight) & 15) == 0;
-    BinState st = bin_state_init();
+    BinState st[IPT];
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) st[i] = bin_state_init();
     uint32_t it = 0;
     for (int b = b_begin; b < n_batches; ++b, ++it) {
       const bool lookback = b < 0;
@@ -478,7 +535,12 @@ melif_ws_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params
       const uint32_t buf = it & 1, use = it >> 1;
       cpx2* z = zA + buf * kBufElems;
       mbar_wait(bar_full + buf, use & 1);
-      polar_item<P, MEL, NP, true>(t, z, P::kPitchA, w_item, dc ? M : 0, lookback, eps, st);
+#pragma unroll
+      for (int i = 0; i < IPT; ++i)
+        if (i == 0)
+          polar_item<P, MEL, NP, true>(t, z, P::kPitchA, w_item[0], dc ? M : 0, lookback, eps, st[0]);
+        else
+          polar_item<P, MEL, NP, false>(t + i * kWsPeThreads, z, P::kPitchA, w_item[i], 0, lookback, eps, st[i]);
       if (!lookback) {
         // band constants after polar (held across it they spill): their L1/L2 latency hides
         // behind the role's barrier
@@ -530,18 +592,17 @@ static int launch_melif_t(const S* audio, int64_t n_notes, int64_t n_samples,
   return ISI_OK;
 }
 
-template <bool MEL, typename S>
+template <int FB, bool MEL, typename S>
 static int launch_melif_ws(const S* audio, int64_t n_notes, int64_t n_samples,
                            const isi_melif_params& p, float* out, cudaStream_t stream) {
-  constexpr int FB = 8;
   const MelifSmem L = melif_smem_layout<2048, FB>(p.hop, (int)sizeof(S), 2);
   cudaError_t e = cudaFuncSetAttribute(melif_ws_kernel<FB, MEL, S>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
   if (e != cudaSuccess) return (int)e;
   int seg_frames, n_segs;
-  choose_segments(n_notes, p.n_frames, FB, 1, &seg_frames, &n_segs);
+  choose_segments(n_notes, p.n_frames, FB, WsGeometry<FB>::kCtasPerSm, &seg_frames, &n_segs);
   if (n_notes * n_segs > 0x7fffffff) return ISI_ERR_SHAPE;
-  melif_ws_kernel<FB, MEL, S><<<(unsigned)(n_notes * n_segs), kWsThreads, L.total, stream>>>(
+  melif_ws_kernel<FB, MEL, S><<<(unsigned)(n_notes * n_segs), WsGeometry<FB>::kThreads, L.total, stream>>>(
       audio, n_samples, p, out, seg_frames, n_segs);
   ISI_LAUNCH_CHECK();
   return ISI_OK;
@@ -561,9 +622,15 @@ static int launch_melif_s(const S* audio, int64_t n_notes, int64_t n_samples,
   static const bool force_generic = getenv("ISI_MELIF_GENERIC") != nullptr;
   const bool geometry_ok = (n_samples % 8 == 0) && (p.hop % 8 == 0) && (p.pad_left % 8 == 0);
   if (!force_generic && p.n_fft == 2048 && bulk_ok && geometry_ok && p.hop <= 2048 &&
-      melif_smem_layout<2048, 8>(p.hop, (int)sizeof(S), 2).total <= 227 * 1024)
-    return p.use_mel ? launch_melif_ws<true, S>(audio, n_notes, n_samples, p, out, stream)
-                     : launch_melif_ws<false, S>(audio, n_notes, n_samples, p, out, stream);
+      melif_smem_layout<2048, 8>(p.hop, (int)sizeof(S), 2).total <= 227 * 1024) {
+    // ISI_MELIF_WS_FB=4 (testing / profiling): two 384-thread CTAs per SM instead of one of 768
+    static const bool fb4 = getenv("ISI_MELIF_WS_FB") != nullptr && atoi(getenv("ISI_MELIF_WS_FB")) == 4;
+    if (fb4)
+      return p.use_mel ? launch_melif_ws<4, true, S>(audio, n_notes, n_samples, p, out, stream)
+                       : launch_melif_ws<4, false, S>(audio, n_notes, n_samples, p, out, stream);
+    return p.use_mel ? launch_melif_ws<8, true, S>(audio, n_notes, n_samples, p, out, stream)
+                     : launch_melif_ws<8, false, S>(audio, n_notes, n_samples, p, out, stream);
+  }
 #define ISI_MELIF_CASE(N, FB, NT)                                                               \
   case N:                                                                                     \
     return p.use_mel ? launch_melif_t<N, FB, NT, true, S>(audio, n_notes, n_samples, p, out, stream, bulk_ok) \
