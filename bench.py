@@ -671,7 +671,8 @@ def b200_arm(args):
         "e2e": {"value": e2e_value, "unit": "notes/s",
                 "h2d_bytes_per_step": host_audio.numel() * host_audio.element_size(),
                 "audio": args.audio,
-                "d2h_bytes_per_step": (host_codes[0].numel() + host_codes[1].numel()) * 8,
+                "d2h_bytes_per_step": extractor.d2h_bytes_last_batch,
+                "d2h": "code maps as int32 on a side stream (widened to int64 on the host)",
                 "api": "extract.CodeExtractor(helper, model, device).run(pinned host audio batches)",
                 "cuda_graph": bool(args.e2e_cuda_graph) and not extractor.graph_failures,
                 "cuda_graph_failures": extractor.graph_failures[:2],

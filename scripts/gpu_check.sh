@@ -123,6 +123,11 @@ for n in (1, 4, 300):
       timeout 600 ncu --set full --clock-control none --import-source on -k regex:vq_assign_pstream -s 3 -c 1 \
         -o gpurun_out/assign_pstream_$tag python tools/ncu_targets.py pstream > gpurun_out/ncu_pstream_$tag.log 2>&1
       tail -1 gpurun_out/ncu_pstream_$tag.log | cut -c1-200 ;;
+    sanitize_frontend)
+      for tool in memcheck synccheck racecheck; do
+        timeout 400 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_smoke.py frontend > gpurun_out/sanitize_${tool}_frontend_$tag.log 2>&1
+        echo "$tool frontend rc=$? $(grep -c "=========     at\|========= Error\|========= Warning\|hazard" gpurun_out/sanitize_${tool}_frontend_$tag.log) findings; $(grep "ERROR SUMMARY\|RACECHECK SUMMARY" gpurun_out/sanitize_${tool}_frontend_$tag.log | tail -1)"
+      done ;;
     fb4)
       ISI_MELIF_WS_FB=4 timeout 300 python -m pytest tests/test_gpu_frontend.py -q 2>&1 | tail -3
       ISI_MELIF_WS_FB=4 timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_fb4_$tag.json
