@@ -123,6 +123,8 @@ for n in (1, 4, 300):
       timeout 600 ncu --set full --clock-control none --import-source on -k regex:vq_assign_pstream -s 3 -c 1 \
         -o gpurun_out/assign_pstream_$tag python tools/ncu_targets.py pstream > gpurun_out/ncu_pstream_$tag.log 2>&1
       tail -1 gpurun_out/ncu_pstream_$tag.log | cut -c1-200 ;;
+    train_test)
+      timeout 300 python -m pytest tests/test_gpu_train_step.py -q 2>&1 | tail -15 ;;
     sanitize_frontend)
       for tool in memcheck synccheck racecheck; do
         timeout 400 compute-sanitizer --tool $tool --print-limit 20 python tools/sanitize_smoke.py frontend > gpurun_out/sanitize_${tool}_frontend_$tag.log 2>&1
