@@ -7,13 +7,20 @@
 //
 // The mirror of melif.cu.  One CTA owns a run of frames of one note and walks it in batches
 // of FB frames; per batch the [2][M][FB] slab of input values is brought to shared memory with
-// 16-byte async copies issued a batch ahead, exponentiated in place, projected mel->linear
+// TMA tensor copies (cp.async.bulk.tensor.2d: eight [256 rows x FB frames] boxes of the
+// [notes*2*M, frames] view of the input, landing densely in the slab, completion on an mbarrier;
+// 16-byte cp.async gathers when no tensor map can be had) issued a batch ahead, exponentiated in place, projected mel->linear
 // row by row (banded transpose of the analysis filterbank) into FB natural-order spectra
 // with the running phase of every row in a register, folded into the half-size complex
 // spectrum, transformed by the forward FFT passes (conjugate trick), and overlap-added in
 // shared memory: HBM sees each input value and each output sample once.  A CTA that does
 // not start at frame 0 seeds its phases with one FP64 prefix sum over the earlier frames
 // and re-synthesises the few frames whose windows reach into its first hop.
+#include <stdlib.h>
+#include <string.h>
+
+#include <cuda.h>          // CUtensorMap and its enums only: the encoder is fetched at run time
+
 #include "common.cuh"
 #include "imelif_core.cuh"
 
@@ -35,8 +42,31 @@ __device__ __forceinline__ void st_stream4(float* p, float4 v) {
                :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_addr(bar)), "r"(parity) : "memory");
+}
+// one [box rows x box frames] tile of the 2-D view, coordinates (frame, row), dense in shared memory
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int frame, int row, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(smem_addr(dst)), "l"(map), "r"(frame), "r"(row), "r"(smem_addr(bar)) : "memory");
+}
+constexpr int kTmaBoxRows = 256;            // a TMA box dimension is at most 256
+
 struct ImelifSmem {
-  int tw, win, slab, za, carry, total;   // byte offsets into dynamic shared memory
+  int tw, win, slab, za, carry, bar, total;   // byte offsets into dynamic shared memory
 };
 
 template <int NFFT, int FB>
@@ -49,6 +79,7 @@ __host__ __device__ inline ImelifSmem imelif_smem_layout() {
   s.slab = off;  off += 2 * (NFFT / 2) * FB * 4;     // input values of one batch
   s.za = off;    off += FB * P::kPitchA * 8;         // spectra / FFT workspace / frame samples
   s.carry = off; off += 2 * NFFT * 4;                // overlap-add carry, ping-pong
+  s.bar = off;   off += 16;                          // mbarrier of the slab's tensor copies
   s.total = off;
   return s;
 }
@@ -58,7 +89,8 @@ __host__ __device__ inline ImelifSmem imelif_smem_layout() {
 template <int NFFT, int FB, int NT, bool MEL>
 __global__ void __launch_bounds__(NT, 2)
 imelif_kernel(const float* __restrict__ spec, isi_imelif_params p, float* __restrict__ audio,
-              int64_t n_samples, int vec_in, int vec_out, int seg_frames, int n_segs) {
+              int64_t n_samples, int vec_in, int vec_out, int seg_frames, int n_segs,
+              const __grid_constant__ CUtensorMap spec_map, int use_tma) {
   using P = Plan<NFFT>;
   constexpr int M = P::M;
   constexpr int IPT = (M / 2) / NT;           // tangle items per thread and frame
@@ -73,6 +105,7 @@ imelif_kernel(const float* __restrict__ spec, isi_imelif_params p, float* __rest
   float* slab = reinterpret_cast<float*>(smem + L.slab);
   cpx* zA = reinterpret_cast<cpx*>(smem + L.za);
   float* carry = reinterpret_cast<float*>(smem + L.carry);
+  uint64_t* slab_bar = reinterpret_cast<uint64_t*>(smem + L.bar);
 
   const int tid = threadIdx.x;
   const int note_idx = blockIdx.x / n_segs, seg = blockIdx.x - note_idx * n_segs;
@@ -95,6 +128,11 @@ imelif_kernel(const float* __restrict__ spec, isi_imelif_params p, float* __rest
   for (int i = tid; i < M; i += NT) twm[i] = tw_global[fft_table_source<P>(i)];
   for (int i = tid; i < NFFT; i += NT) win[i] = p.window[i];
   for (int i = tid; i < 2 * NFFT; i += NT) carry[i] = 0.f;
+  if (tid == 0) {
+    mbar_init(slab_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  uint32_t slab_phase = 0;
   cpx w_item[IPT];
 #pragma unroll
   for (int i = 0; i < IPT; ++i) w_item[i] = tw_global[tid + i * NT];
@@ -116,6 +154,18 @@ imelif_kernel(const float* __restrict__ spec, isi_imelif_params p, float* __rest
 
   // slab of frames [f0, f0 + nf): chunk q = tid + i NT is FB time steps of row q % M, channel q / M
   auto fill_slab = [&](int f0, int nf) {
+    if (use_tma) {
+      // (every batch of this path is a full one: n_frames and the segments are multiples of FB)
+      if (tid == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the slab was read / rewritten in place
+        mbar_expect_tx(slab_bar, 2 * M * FB * 4);
+        const int row0 = note_idx * 2 * M;
+#pragma unroll
+        for (int r = 0; r < 2 * M; r += kTmaBoxRows)
+          tma_load_2d(slab + r * FB, &spec_map, f0, row0 + r, slab_bar);
+      }
+      return;
+    }
     const bool vec = vec_in && nf == FB;
 #pragma unroll
     for (int i = 0; i < CPT; ++i) {
@@ -152,8 +202,9 @@ imelif_kernel(const float* __restrict__ spec, isi_imelif_params p, float* __rest
     float* carry_out = carry + (flip ^ 1) * NFFT;
     flip ^= 1;
 
-    // ---- slab: own chunks arrived; exponentiate / scale them in place ----
-    cp_async_wait_all();
+    // ---- slab: the batch's values arrived; exponentiate / scale them in place ----
+    if (use_tma) { mbar_wait(slab_bar, slab_phase & 1); ++slab_phase; }
+    else cp_async_wait_all();
 #pragma unroll
     for (int i = 0; i < CPT; ++i)
       slab_transform_chunk<FB>(slab, tid + i * NT, M, p.in_scale[0], p.in_bias[0], p.in_scale[1], p.in_bias[1]);
@@ -253,6 +304,35 @@ static void choose_segments(int64_t n_notes, int n_frames, int fb, int lookback,
   }
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      ptr = nullptr;
+    return (EncodeTiledFn)ptr;
+  }();
+  return fn;
+}
+
+// [n_notes * 2 * M rows, n_frames] FP32 view of the input, boxes of kTmaBoxRows x fb
+static bool make_spec_map(CUtensorMap* map, const float* spec, int64_t n_notes, int m, int n_frames, int fb) {
+  EncodeTiledFn encode = tensor_map_encoder();
+  if (!encode || getenv("ISI_IMELIF_NO_TMA")) return false;
+  const cuuint64_t dims[2] = {(cuuint64_t)n_frames, (cuuint64_t)n_notes * 2 * (cuuint64_t)m};
+  const cuuint64_t strides[1] = {(cuuint64_t)n_frames * 4};
+  const cuuint32_t box[2] = {(cuuint32_t)fb, (cuuint32_t)kTmaBoxRows};
+  const cuuint32_t elem[2] = {1, 1};
+  return encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(spec), dims, strides, box, elem,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int NFFT, int FB, int NT, bool MEL>
 static int launch_imelif_t(const float* spec, int64_t n_notes, const isi_imelif_params& p, float* audio,
                            int64_t n_samples, int seg_frames_override, cudaStream_t stream) {
@@ -270,8 +350,14 @@ static int launch_imelif_t(const float* spec, int64_t n_notes, const isi_imelif_
     n_segs = (p.n_frames + seg_frames - 1) / seg_frames;
   }
   if (n_notes * n_segs > 0x7fffffff) return ISI_ERR_SHAPE;
+  // the slab by TMA: full batches only (vec_in), whole boxes (2 M rows is a multiple of 256), and
+  // row coordinates that fit the instruction's 32-bit signed operands
+  CUtensorMap spec_map;
+  memset(&spec_map, 0, sizeof(spec_map));
+  const int use_tma = vec_in && (2 * (NFFT / 2)) % kTmaBoxRows == 0 && n_notes * 2 * (NFFT / 2) < 0x7fffffff &&
+                      make_spec_map(&spec_map, spec, n_notes, NFFT / 2, p.n_frames, FB);
   imelif_kernel<NFFT, FB, NT, MEL><<<(unsigned)(n_notes * n_segs), NT, L.total, stream>>>(
-      spec, p, audio, n_samples, vec_in, vec_out, seg_frames, n_segs);
+      spec, p, audio, n_samples, vec_in, vec_out, seg_frames, n_segs, spec_map, use_tma);
   ISI_LAUNCH_CHECK();
   return ISI_OK;
 }
