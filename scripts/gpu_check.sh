@@ -58,14 +58,6 @@ for n in (1, 4, 300):
       timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 20 --warmup 3 2>&1 | tail -2 > gpurun_out/bench_multi${n}_$tag.json
       cut -c1-300 gpurun_out/bench_multi${n}_$tag.json
       timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29512 bench.py --impl reference --gpus $n --steps 3 --warmup 1 2>&1 | tail -1 | cut -c1-200 ;;
-    train)
-      n=${NGPUS:-1}
-      if [ "$n" = 1 ]; then
-        timeout 600 python tools/bench_train.py 2>&1 | tail -1 > gpurun_out/train${n}_$tag.json
-      else
-        timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29533 tools/bench_train.py 2>&1 | tail -1 > gpurun_out/train${n}_$tag.json
-      fi
-      cut -c1-900 gpurun_out/train${n}_$tag.json ;;
     sanitize)
       for tool in memcheck racecheck synccheck; do
         for part in frontend quantizer; do
@@ -75,8 +67,6 @@ for n in (1, 4, 300):
       done ;;
     multi_test)
       timeout 600 python -m pytest tests/test_gpu_multi.py -q 2>&1 | tail -5 ;;
-    extra)
-      timeout 600 python tools/bench_extra.py > gpurun_out/extra_$tag.json 2> gpurun_out/extra_$tag.err; tail -3 gpurun_out/extra_$tag.err; head -c 600 gpurun_out/extra_$tag.json ;;
     inverse)
       timeout 900 python -m pytest tests/test_gpu_inverse.py -q -s 2>&1 | tail -40 > gpurun_out/pytest_inverse_$tag.log
       tail -8 gpurun_out/pytest_inverse_$tag.log ;;

@@ -158,3 +158,36 @@ def test_code_extractor_graph_replay_equals_the_eager_pipeline():
     for g, w in zip(eager.run(batches), want):
         assert (g.top == w.top).all() and (g.bottom == w.bottom).all()
     assert graphed.run([]) == []
+
+
+def test_code_extractor_carries_attributes_and_names_through_the_prefetch_ring(fp32_convs):
+    """extract_code.py:62-74: each row keeps ITS note's label-encoded attributes and file name.
+    With uploads two batches ahead and a ragged last batch, a slot mix-up in the ring would pair a
+    note's codes with another batch's attributes."""
+    from interactive_spectrogram_inpainting_b200 import extract
+    from interactive_spectrogram_inpainting_b200.utils.spectrograms_helper import MelSpectrogramsHelper
+    torch.manual_seed(8)
+    dev = torch.device(DEV)
+    model = (vq.VQVAE(in_channel=2, resolution_factors={"bottom": 16, "top": 2}, adapt_quantized_durations=False)
+             .to(dev).eval().to(memory_format=torch.channels_last))
+    helper = MelSpectrogramsHelper(space_to_depth=True).to(dev)
+    pcm = (synthetic.synthetic_notes(11) * 32767).round().to(torch.int16)
+    pitch = torch.arange(11) + 40
+    family = torch.arange(11) % 3
+    cuts = [(0, 3), (3, 6), (6, 9), (9, 11)]
+    batches = [(pcm[a:b].pin_memory(), [f"note_{i:02d}" for i in range(a, b)],
+                {"pitch": pitch[a:b], "instrument_family_str": family[a:b]}) for a, b in cuts]
+    alone = extract.CodeExtractor(helper, model, dev, prefetch_depth=1)
+    for depth in (1, 2, 3):
+        rows = extract.CodeExtractor(helper, model, dev, prefetch_depth=depth).run(batches)
+        assert [r.filename for r in rows] == [f"note_{i:02d}" for i in range(11)]
+        for i, row in enumerate(rows):
+            assert set(row.attributes) == {"pitch", "instrument_family_str"}
+            assert row.attributes["pitch"].shape == () and row.attributes["pitch"].dtype == torch.int64
+            assert int(row.attributes["pitch"]) == 40 + i and int(row.attributes["instrument_family_str"]) == i % 3
+            # the codes of note i, whichever batch and slot it travelled in
+            single = alone.run([(pcm[i:i + 1].pin_memory(), [f"note_{i:02d}"])])[0]
+            # (an identity check, not a parity check: cuDNN may pick another algorithm at batch 1,
+            # so a near-tie may flip; another note's codes would differ almost everywhere)
+            differing = int((row.top != single.top).sum()) + int((row.bottom != single.bottom).sum())
+            assert differing <= 2, (depth, i, differing)
