@@ -225,6 +225,11 @@ typedef struct isi_melif_params {
                             /*    the encoder's first conv (4x4, stride 2, 2 input      */
                             /*    channels, encoder_decoder.py:66-70) becomes a 3x3      */
                             /*    stride-1 conv over 8 channels; needs even n_frames     */
+                            /* 3: the same blocks with the frequency index fastest,      */
+                            /*    [B,T'/2,F/2,(f&1,t&1,c)]: the layout the kernel's lanes  */
+                            /*    (consecutive rows) write as whole 128-byte lines; the    */
+                            /*    encoder then runs on the transposed plane with transposed */
+                            /*    filters (vqvae.py: space_to_depth="transposed")          */
   /* fused epilogue (both live in GANsynth_pytorch in the reference):       */
   int32_t mask_phase;       /* 1: channel 1 := 0 where channel 0 < mask_threshold (the       */
   float mask_threshold;     /*    masked-phase transform, extract_code.py:178-181)           */
@@ -237,7 +242,8 @@ typedef struct isi_melif_params {
 } isi_melif_params;
 
 typedef enum { ISI_AUDIO_F32 = 0, ISI_AUDIO_PCM16 = 1 } isi_audio_format;
-typedef enum { ISI_SPEC_PLANAR = 0, ISI_SPEC_CHANNELS_LAST = 1, ISI_SPEC_SPACE_TO_DEPTH = 2 } isi_spec_layout;
+typedef enum { ISI_SPEC_PLANAR = 0, ISI_SPEC_CHANNELS_LAST = 1, ISI_SPEC_SPACE_TO_DEPTH = 2,
+               ISI_SPEC_SPACE_TO_DEPTH_T = 3 } isi_spec_layout;
 
 /*
  * audio [n_notes, n_samples] (contiguous; FP32 or int16 per h_params->audio_format)

@@ -18,7 +18,7 @@ _lock = threading.Lock()
 _lib = None
 
 AUDIO_F32, AUDIO_PCM16 = 0, 1
-SPEC_PLANAR, SPEC_CHANNELS_LAST, SPEC_SPACE_TO_DEPTH = 0, 1, 2
+SPEC_PLANAR, SPEC_CHANNELS_LAST, SPEC_SPACE_TO_DEPTH, SPEC_SPACE_TO_DEPTH_T = 0, 1, 2, 3
 ASSIGN_AUTO, ASSIGN_SIMT_FP32, ASSIGN_TCGEN05, ASSIGN_TCGEN05_PAIR, ASSIGN_TCGEN05_PAIR_STREAM = range(5)
 _ALGOS = {"auto": ASSIGN_AUTO, "simt": ASSIGN_SIMT_FP32, "tcgen05": ASSIGN_TCGEN05,
           "tcgen05_pair": ASSIGN_TCGEN05_PAIR, "tcgen05_pair_stream": ASSIGN_TCGEN05_PAIR_STREAM}

@@ -190,8 +190,8 @@ ISI_API int isi_melif_forward(const void* audio, int64_t n_notes, int64_t n_samp
     return ISI_ERR_SHAPE;
   if (hp->use_mel && hp->mel_width <= 0) return ISI_ERR_SHAPE;
   if (hp->audio_format != ISI_AUDIO_F32 && hp->audio_format != ISI_AUDIO_PCM16) return ISI_ERR_UNSUPPORTED;
-  if (hp->channels_last < ISI_SPEC_PLANAR || hp->channels_last > ISI_SPEC_SPACE_TO_DEPTH) return ISI_ERR_UNSUPPORTED;
-  if (hp->channels_last == ISI_SPEC_SPACE_TO_DEPTH && (hp->n_frames % 2 || (hp->n_fft / 2) % 2)) return ISI_ERR_SHAPE;
+  if (hp->channels_last < ISI_SPEC_PLANAR || hp->channels_last > ISI_SPEC_SPACE_TO_DEPTH_T) return ISI_ERR_UNSUPPORTED;
+  if (hp->channels_last >= ISI_SPEC_SPACE_TO_DEPTH && (hp->n_frames % 2 || (hp->n_fft / 2) % 2)) return ISI_ERR_SHAPE;
   if ((uintptr_t)audio % (hp->audio_format == ISI_AUDIO_PCM16 ? 2 : 4)) return ISI_ERR_ALIGN;
   if ((uintptr_t)out % 16 || (uintptr_t)hp->twiddle % 8) return ISI_ERR_ALIGN;
   if (n_notes == 0) return ISI_OK;

@@ -51,6 +51,32 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 }
+// Waits of the warp-specialised kernel.  A plain try_wait loop polls (the polar/emit warps,
+// which wait for the transform warps every batch, polled ~67 times per wait, each poll a SYNCS
+// plus a reload of the spilled barrier address).  Here the barrier is picked by a uniform
+// branch (address = uniform base + immediate, nothing to spill) and try_wait carries a
+// suspend-time hint, which ptxas turns into TRYWAIT / NANOSLEEP.SYNCS / re-check: the warp
+// sleeps until the barrier's phase flips.  A failed try backs off with nanosleep.
+// cfg = hint_ns | sleep_ns << 16.  (Measured: neutral for the kernel time -- the polls only
+// used idle issue slots -- but the ncu instruction and LSU counts no longer carry the noise.)
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t hint_ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns) : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t cfg) {
+  const uint32_t hint_ns = cfg & 0xffffu, sleep_ns = cfg >> 16;
+  while (!mbar_try_wait_hint(bar, parity, hint_ns))
+    if (sleep_ns) __nanosleep(sleep_ns);
+}
+__device__ __forceinline__ void mbar_wait_pair(uint64_t* bars, uint32_t which, uint32_t parity, uint32_t cfg) {
+  if (which) mbar_wait_backoff(bars + 1, parity, cfg);
+  else mbar_wait_backoff(bars, parity, cfg);
+}
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes,
                                          uint64_t* bar) {
   asm volatile(
@@ -72,6 +98,16 @@ __device__ __forceinline__ int ld_table(const int32_t* p) {
   int v;
   asm volatile("ld.global.nc.L1::evict_last.s32 %0, [%1];" : "=r"(v) : "l"(p));
   return v;
+}
+// 32-byte store (sm_100: STG.256): a row's 8 time steps of one channel in ONE instruction.  The
+// cost of a store instruction follows the number of 128-byte lines its lanes touch (measured:
+// writing the same bytes into an L2-resident buffer costs the same, so it is SM-side), and in
+// the time-fastest layouts every lane is in a line of its own: halving the instructions halved
+// the store time (planar output: 0.387 -> 0.311 ms per 444 notes).
+__device__ __forceinline__ void st_stream8(float* p, const float* v) {
+  asm volatile("st.global.L1::no_allocate.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               :: "l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
 }
 __device__ __forceinline__ void st_stream4(float* p, float4 v) {
   asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1, %2, %3, %4};"
@@ -127,13 +163,61 @@ __device__ __forceinline__ void emit_row(const isi_melif_params& p, const cpx2* 
   float v0[FB], v1[FB];      // frame-slot order
   finish_row<NP>(lg, ph, p.mask_phase != 0, p.mask_threshold, p.out_scale[0], p.out_bias[0],
                  p.out_scale[1], p.out_bias[1], v0, v1);
+  if (p.channels_last == ISI_SPEC_SPACE_TO_DEPTH_T) {
+    // [B, T'/2, F/2, (f&1, t&1, channel)]: the same 2x2 blocks with the FREQUENCY index running
+    // fastest.  Lanes are consecutive rows, so one store instruction writes 512 contiguous bytes
+    // (4 LSU wavefronts); in the time-fastest layout below the same instruction touches 16
+    // different 128-byte lines (16 wavefronts, a fifth of the kernel's time in stores).
+    const int64_t blk = (int64_t)(M / 2) * 8;               // one time block of all row pairs
+    float* d = out + (((int64_t)note_idx * (p.n_frames >> 1) + (f0 >> 1)) * (M / 2) + (row >> 1)) * 8 +
+               (row & 1) * 4;
+    if (nf == FB) {
+#pragma unroll
+      for (int k = 0; k < FB / 2; ++k)
+        st_stream4(d + k * blk, make_float4(v0[2 * k], v1[2 * k], v0[2 * k + 1], v1[2 * k + 1]));
+    } else {
+#pragma unroll
+      for (int s = 0; s < FB; ++s)
+        if (s < nf) {
+          float* e = d + (s >> 1) * blk + (s & 1) * 2;
+          e[0] = v0[s]; e[1] = v1[s];
+        }
+    }
+    return;
+  }
   if (p.channels_last == ISI_SPEC_SPACE_TO_DEPTH) {
     // [B, F/2, T'/2, (f&1, t&1, channel)]: 2x2 spectrogram blocks as 8 channels.  A row
     // writes 16 bytes per block; the odd/even row pair (neighbouring lanes of the same
     // instruction) completes each 32-byte sector.
     float* d = out + ((((int64_t)note_idx * (M / 2) + (row >> 1)) * (p.n_frames >> 1) + (f0 >> 1)) * 8) +
                (row & 1) * 4;
-    if (nf == FB) {
+    bool wide = false;
+    if constexpr (FB == 8) {
+      // A whole batch: the two lanes of a row pair (rows follow lanes, so lane parity = row
+      // parity) swap half of their pieces -- the even lane ends up with blocks 0 and 1 of BOTH
+      // rows, the odd lane with blocks 2 and 3 -- and each writes two 32-byte blocks: two store
+      // instructions per row instead of four (every lane pair is in a 128-byte line of its own,
+      // and a store instruction costs LSU cycles per line touched).
+      wide = nf == FB && (reinterpret_cast<uintptr_t>(out) & 31) == 0;       // warp-uniform
+      if (wide) {
+        const bool odd = (row & 1) != 0;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const float mine[4] = {v0[2 * j], v1[2 * j], v0[2 * j + 1], v1[2 * j + 1]};                  // block j
+          const float far[4] = {v0[2 * j + 4], v1[2 * j + 4], v0[2 * j + 5], v1[2 * j + 5]};           // block j + 2
+          float blk[8];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float got = __shfl_xor_sync(0xffffffffu, odd ? mine[e] : far[e], 1);
+            blk[e] = odd ? got : mine[e];          // parity-0 row's piece
+            blk[4 + e] = odd ? far[e] : got;       // parity-1 row's piece
+          }
+          st_stream8(d - (odd ? 4 : 0) + 8 * (odd ? j + 2 : j), blk);
+        }
+      }
+    }
+    if (wide) {
+    } else if (nf == FB) {
 #pragma unroll
       for (int k = 0; k < FB / 2; ++k)
         st_stream4(d + 8 * k, make_float4(v0[2 * k], v1[2 * k], v0[2 * k + 1], v1[2 * k + 1]));
@@ -150,7 +234,18 @@ __device__ __forceinline__ void emit_row(const isi_melif_params& p, const cpx2* 
   if (p.channels_last) {
     // [B, F, T', 2]: the FB time steps of both channels are one contiguous run
     float* d = out + (((int64_t)note_idx * M + row) * p.n_frames + f0) * 2;
-    if (nf == FB && (p.n_frames % 2 == 0)) {
+    bool wide = false;
+    if constexpr (FB == 8) {
+      wide = nf == FB && (p.n_frames % 4 == 0) && (reinterpret_cast<uintptr_t>(out) & 31) == 0;
+      if (wide) {
+        const float a[8] = {v0[0], v1[0], v0[1], v1[1], v0[2], v1[2], v0[3], v1[3]};
+        const float b[8] = {v0[4], v1[4], v0[5], v1[5], v0[6], v1[6], v0[7], v1[7]};
+        st_stream8(d, a);
+        st_stream8(d + 8, b);
+      }
+    }
+    if (wide) {
+    } else if (nf == FB && (p.n_frames % 2 == 0)) {
 #pragma unroll
       for (int k = 0; k < FB / 2; ++k)
         st_stream4(d + 4 * k, make_float4(v0[2 * k], v1[2 * k], v0[2 * k + 1], v1[2 * k + 1]));
@@ -163,7 +258,16 @@ __device__ __forceinline__ void emit_row(const isi_melif_params& p, const cpx2* 
   }
   float* d0 = out + (int64_t)note_idx * 2 * M * p.n_frames + (int64_t)row * p.n_frames + f0;
   float* d1 = d0 + (int64_t)M * p.n_frames;
-  if (nf == FB && (FB % 4 == 0) && (p.n_frames % 4 == 0)) {
+  bool wide = false;
+  if constexpr (FB == 8) {
+    wide = nf == FB && (p.n_frames % 8 == 0) && (reinterpret_cast<uintptr_t>(out) & 31) == 0;
+    if (wide) {
+      st_stream8(d0, v0);
+      st_stream8(d1, v1);
+    }
+  }
+  if (wide) {
+  } else if (nf == FB && (FB % 4 == 0) && (p.n_frames % 4 == 0)) {
 #pragma unroll
     for (int k = 0; k < FB / 4; ++k) {
       st_stream4(d0 + 4 * k, make_float4(v0[4 * k], v0[4 * k + 1], v0[4 * k + 2], v0[4 * k + 3]));
@@ -394,6 +498,7 @@ struct WsGeometry {
   static constexpr int kCtasPerSm = 768 / kThreads;
   static_assert(kThreads * kCtasPerSm == 768, "24 warps per SM");
 };
+constexpr uint32_t kWsWaitHintNs = 1000, kWsWaitSleepNs = 0;
 constexpr int kWsFftRegs = 112, kWsPeRegs = 64, kWsLaunchRegs = 80;
 static_assert(1 * (kWsFftRegs - kWsLaunchRegs) <= 2 * (kWsLaunchRegs - kWsPeRegs),
               "setmaxnreg.inc would wait forever for registers nobody releases");
@@ -403,7 +508,7 @@ static_assert(768 * kWsLaunchRegs <= 65536 && 768 * (kWsLaunchRegs + 8) > 65536,
 template <int FB, bool MEL, typename S>
 __global__ void __launch_bounds__(WsGeometry<FB>::kThreads, WsGeometry<FB>::kCtasPerSm)
 melif_ws_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params p,
-                float* __restrict__ out, int seg_frames, int n_segs) {
+                float* __restrict__ out, int seg_frames, int n_segs, uint32_t wait_cfg, int ablate) {
   constexpr int NFFT = 2048;
   using P = Plan<NFFT>;
   constexpr int M = P::M, NP = FB / 2;
@@ -487,20 +592,20 @@ melif_ws_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params
       const uint32_t buf = it & 1, use = it >> 1;
       cpx2* z = zA + buf * kBufElems + q * P::kPitchA;
       const S* st_cur = stage + buf * stage_elems;
-      const bool active = lookback ? (q == NP - 1) : (q < nf);
+      const bool active = (lookback ? (q == NP - 1) : (q < nf)) && !(ablate & 2);   // & 2: polar/emit role alone
 
       if (feeder && next_nf > 0) {
         // the other stage buffer was read by pass 1 of the previous batch: all 256 threads have
         // arrived on its barrier by now (they are at most a pass or two behind)
-        if (it > 0) mbar_wait(bar_pass1 + (buf ^ 1), ((it - 1) >> 1) & 1);
+        if (it > 0) mbar_wait_pair(bar_pass1, buf ^ 1, ((it - 1) >> 1) & 1, wait_cfg);
         S* st_next = stage + (buf ^ 1) * stage_elems;
         const StageSpan<S> sp(n_samples, p.hop, p.pad_left, NFFT, next_f0, next_nf);
         sp.fill(st_next, ft, 32);
         __syncwarp();
         if (ft == 0) sp.issue(st_next, note, bar_stage + (buf ^ 1));
       }
-      mbar_wait(bar_stage + buf, use & 1);                 // this batch's audio has landed
-      mbar_wait(bar_empty + buf, (use & 1) ^ 1);           // polar/emit released the workspace
+      mbar_wait_pair(bar_stage, buf, use & 1, wait_cfg);     // this batch's audio has landed
+      mbar_wait_pair(bar_empty, buf, (use & 1) ^ 1, wait_cfg);   // polar/emit released the workspace
       if (active)
         fft_pass1_pair<P>(j, st_cur + (lookback ? 0 : q * p.hop), st_cur + (lookback ? 0 : (q + NP) * p.hop),
                           true, sample_scale, win, twm, z);
@@ -534,7 +639,8 @@ melif_ws_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params
       const int nf = lookback ? 1 : min(FB, fe - f0);
       const uint32_t buf = it & 1, use = it >> 1;
       cpx2* z = zA + buf * kBufElems;
-      mbar_wait(bar_full + buf, use & 1);
+      mbar_wait_pair(bar_full, buf, use & 1, wait_cfg);
+      if (ablate & 1) { mbar_arrive(bar_empty + buf); continue; }     // profiling: transform role alone
 #pragma unroll
       for (int i = 0; i < IPT; ++i)
         if (i == 0)
@@ -592,6 +698,24 @@ static int launch_melif_t(const S* audio, int64_t n_notes, int64_t n_samples,
   return ISI_OK;
 }
 
+// ISI_MELIF_WAIT_HINT / ISI_MELIF_WAIT_SLEEP (ns; testing / profiling): see mbar_wait_backoff
+static uint32_t ws_wait_cfg() {
+  static const uint32_t cfg = [] {
+    const char* h = getenv("ISI_MELIF_WAIT_HINT");
+    const char* z = getenv("ISI_MELIF_WAIT_SLEEP");
+    const uint32_t hint = h ? (uint32_t)atoi(h) : kWsWaitHintNs, sleep = z ? (uint32_t)atoi(z) : kWsWaitSleepNs;
+    return (hint & 0xffffu) | (sleep & 0xffffu) << 16;
+  }();
+  return cfg;
+}
+// ISI_MELIF_ABLATE (profiling only, the output is WRONG): 1 = the polar/emit warps only hand the
+// buffers back (times the transform role alone), 2 = the transform warps only hand them over
+// (times the polar/emit role alone), 3 = both (the skeleton: staging, barriers, prologue).
+static int ws_ablate() {
+  static const int v = getenv("ISI_MELIF_ABLATE") ? atoi(getenv("ISI_MELIF_ABLATE")) : 0;
+  return v;
+}
+
 template <int FB, bool MEL, typename S>
 static int launch_melif_ws(const S* audio, int64_t n_notes, int64_t n_samples,
                            const isi_melif_params& p, float* out, cudaStream_t stream) {
@@ -603,7 +727,7 @@ static int launch_melif_ws(const S* audio, int64_t n_notes, int64_t n_samples,
   choose_segments(n_notes, p.n_frames, FB, WsGeometry<FB>::kCtasPerSm, &seg_frames, &n_segs);
   if (n_notes * n_segs > 0x7fffffff) return ISI_ERR_SHAPE;
   melif_ws_kernel<FB, MEL, S><<<(unsigned)(n_notes * n_segs), WsGeometry<FB>::kThreads, L.total, stream>>>(
-      audio, n_samples, p, out, seg_frames, n_segs);
+      audio, n_samples, p, out, seg_frames, n_segs, ws_wait_cfg(), ws_ablate());
   ISI_LAUNCH_CHECK();
   return ISI_OK;
 }

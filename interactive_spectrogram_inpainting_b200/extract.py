@@ -77,7 +77,7 @@ class SpectrogramBatches:
         self._side = None        # one copy stream per loader, so its allocator pool is reused
         # the helper may write 2x2 space-to-depth blocks (see SpectrogramsHelper); the encoder
         # has to be told (extract_codes reads this attribute)
-        self.space_to_depth = bool(getattr(spectrograms_helper, "space_to_depth", False))
+        self.space_to_depth = getattr(spectrograms_helper, "space_to_depth", False)     # False / True / "transposed"
 
     def _upload(self, item, stream):
         audio, names, attributes = _split_item(item)
@@ -164,11 +164,11 @@ def extract_codes(loader: Iterable[Tuple[torch.Tensor, Sequence[str]]], model,
         rows.extend(batch_rows)
 
     model.eval()
-    s2d = bool(getattr(loader, "space_to_depth", False))
+    s2d = getattr(loader, "space_to_depth", False)            # False / True / "transposed"
     for step, batch in enumerate(loader):
         spec, names, attributes = _unpack_batch(batch)
         if hasattr(model, "encode_codes"):
-            id_t, id_b = model.encode_codes(spec, space_to_depth=True) if s2d else model.encode_codes(spec)
+            id_t, id_b = model.encode_codes(spec, space_to_depth=s2d) if s2d else model.encode_codes(spec)
         else:
             if s2d:
                 raise ValueError("space-to-depth spectrograms need this repo's VQVAE.encode_codes")
@@ -193,14 +193,14 @@ class _GraphedStep:
     what matters when eight ranks share a host's cores.  The graph holds the addresses of the
     prepared codebooks and projection weights: eval mode, weights that no longer change."""
 
-    def __init__(self, helper, model, example: torch.Tensor, space_to_depth: bool, warmup: int = 3):
+    def __init__(self, helper, model, example: torch.Tensor, space_to_depth, warmup: int = 3):
         device = example.device
         self.audio = torch.empty_like(example)
         self.audio.copy_(example)
 
         def run():
             spec = helper.to_spectrogram(self.audio)
-            return model.encode_codes(spec, space_to_depth=True) if space_to_depth else model.encode_codes(spec)
+            return model.encode_codes(spec, space_to_depth=space_to_depth) if space_to_depth else model.encode_codes(spec)
         stream = torch.cuda.Stream(device)
         stream.wait_stream(torch.cuda.current_stream(device))
         with torch.no_grad(), torch.cuda.stream(stream):
@@ -236,7 +236,7 @@ class CodeExtractor:
             raise TypeError("CodeExtractor needs this repo's VQVAE (encode_codes)")
         self.helper, self.model, self.device = spectrograms_helper, model.eval(), device
         self.cuda_graph = cuda_graph
-        self.space_to_depth = bool(getattr(spectrograms_helper, "space_to_depth", False))
+        self.space_to_depth = getattr(spectrograms_helper, "space_to_depth", False)     # False / True / "transposed"
         self._graphs = {}
         self._side = torch.cuda.Stream(device)
         # uploads run `prefetch_depth` batches ahead of the compute (two: a slow copy -- eight
@@ -265,7 +265,7 @@ class CodeExtractor:
         if graphed:
             return graphed(audio)
         spec = self.helper.to_spectrogram(audio)
-        return (self.model.encode_codes(spec, space_to_depth=True) if self.space_to_depth
+        return (self.model.encode_codes(spec, space_to_depth=self.space_to_depth) if self.space_to_depth
                 else self.model.encode_codes(spec))
 
     @torch.no_grad()

@@ -122,7 +122,7 @@ class SpectrogramsHelper(nn.Module):
                  window_length: int = 2048, safelog_eps: float = 1e-6, *,
                  pad_left: Optional[int] = None, n_frames: Optional[int] = None,
                  drop_bin: str = "dc", window_periodic: bool = True,
-                 channels_last: bool = False, space_to_depth: bool = False,
+                 channels_last: bool = False, space_to_depth=False,
                  masked_phase_threshold: Optional[float] = None,
                  output_affine=None):
         super().__init__()
@@ -148,6 +148,13 @@ class SpectrogramsHelper(nn.Module):
         # (``from_space_to_depth`` undoes it).  The VQ-VAE's first convolution -- 4x4, stride 2
         # over 2 input channels, the slowest kernel of an extraction step -- is a 3x3 stride-1
         # convolution over these 8 channels (vqvae.Encoder, ``space_to_depth=True``).
+        # "transposed": the same blocks on the TRANSPOSED plane, ``[B, 8, T'/2, F/2]`` in
+        # channels_last storage (frequency runs fastest in memory): the layout the kernel's lanes
+        # -- consecutive rows -- write as whole 128-byte lines, a quarter of the store
+        # transactions of the time-fastest form.  ``VQVAE.encode_codes(x,
+        # space_to_depth="transposed")`` runs the encoder on that plane with transposed filters.
+        if space_to_depth not in (False, True, "transposed"):
+            raise ValueError("space_to_depth must be False, True or 'transposed'")
         self.space_to_depth = space_to_depth
         # Fused epilogue (both are GANsynth_pytorch features the reference applies right after
         # the transform): the masked-phase transform -- IF := 0 where the log-magnitude is below
@@ -192,7 +199,8 @@ class SpectrogramsHelper(nn.Module):
         p.safelog_eps = self.safelog_eps
         p.window, p.twiddle = self.window.data_ptr(), self.twiddle.data_ptr()
         p.mel_start = p.mel_count = p.mel_weight = None
-        p.channels_last = (_lib.SPEC_SPACE_TO_DEPTH if self.space_to_depth else
+        p.channels_last = (_lib.SPEC_SPACE_TO_DEPTH_T if self.space_to_depth == "transposed" else
+                           _lib.SPEC_SPACE_TO_DEPTH if self.space_to_depth else
                            _lib.SPEC_CHANNELS_LAST if self.channels_last else _lib.SPEC_PLANAR)
         p.mask_phase = 0 if self.masked_phase_threshold is None else 1
         p.mask_threshold = 0.0 if self.masked_phase_threshold is None else float(self.masked_phase_threshold)
@@ -225,8 +233,9 @@ class SpectrogramsHelper(nn.Module):
         if self.space_to_depth:
             if frames % 2 or self.n_freq % 2:
                 raise ValueError("space_to_depth needs an even number of frames and bins")
-            out = torch.empty(n_notes, self.n_freq // 2, frames // 2, 8, dtype=torch.float32,
-                              device=a.device).permute(0, 3, 1, 2)
+            plane = ((frames // 2, self.n_freq // 2) if self.space_to_depth == "transposed"
+                     else (self.n_freq // 2, frames // 2))
+            out = torch.empty(n_notes, *plane, 8, dtype=torch.float32, device=a.device).permute(0, 3, 1, 2)
         else:
             out = torch.empty(n_notes, 2, self.n_freq, frames, dtype=torch.float32, device=a.device,
                               memory_format=(torch.channels_last if self.channels_last
@@ -243,8 +252,11 @@ class SpectrogramsHelper(nn.Module):
     forward = to_spectrogram
 
     @staticmethod
-    def from_space_to_depth(blocks: torch.Tensor) -> torch.Tensor:
-        """``[B, 8, F/2, T/2]`` (channel = (f&1)*4 + (t&1)*2 + c) -> ``[B, 2, F, T]``."""
+    def from_space_to_depth(blocks: torch.Tensor, transposed: bool = False) -> torch.Tensor:
+        """``[B, 8, F/2, T/2]`` (channel = (f&1)*4 + (t&1)*2 + c) -> ``[B, 2, F, T]``;
+        ``transposed``: from the ``[B, 8, T/2, F/2]`` form."""
+        if transposed:
+            blocks = blocks.transpose(2, 3)
         b, c8, f2, t2 = blocks.shape
         x = blocks.reshape(b, 2, 2, c8 // 4, f2, t2)            # [B, pf, pt, c, F/2, T/2]
         return x.permute(0, 3, 4, 1, 5, 2).reshape(b, c8 // 4, 2 * f2, 2 * t2)

@@ -42,24 +42,80 @@ def _can_fuse(x: torch.Tensor) -> bool:
             and x.dtype in (torch.float32, torch.float16))
 
 
-def _conv_relu(conv: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
-    return torch.cudnn_convolution_relu(x, conv.weight, conv.bias, conv.stride, conv.padding,
-                                        conv.dilation, conv.groups)
+class TransposedFilters:
+    """Filters for running a conv stack on the TRANSPOSED plane: a convolution commutes with
+    swapping the two spatial axes if its kernel (and stride / padding pairs) are swapped too.
+    The front end writes the spectrogram blocks frequency-fastest (``SpectrogramsHelper(
+    space_to_depth="transposed")``: whole 128-byte lines per store); the encoder then reads them
+    as ``[B, C, T, F]`` and uses ``w.transpose(2, 3)`` of every filter -- kept here, contiguous in
+    channels_last, one copy per weight version."""
+
+    def __init__(self):
+        self._cache = {}
+
+    def weight(self, w: torch.Tensor) -> torch.Tensor:
+        key = (w._version, w.data_ptr(), w.device, w.dtype)
+        hit = self._cache.get(id(w))
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        wt = w.detach().transpose(2, 3).contiguous(memory_format=torch.channels_last)
+        self._cache[id(w)] = (key, wt)       # a racing thread stores an equal tensor
+        return wt
+
+    @staticmethod
+    def pair(v):
+        return tuple(reversed(v)) if isinstance(v, (tuple, list)) else v
 
 
-def _conv_add_relu(conv: nn.Conv2d, x: torch.Tensor, skip: torch.Tensor) -> torch.Tensor:
-    return torch.cudnn_convolution_add_relu(x, conv.weight, skip, 1.0, conv.bias, conv.stride,
-                                            conv.padding, conv.dilation, conv.groups)
+def _w(conv: nn.Module, tf: Optional[TransposedFilters]) -> torch.Tensor:
+    return conv.weight if tf is None else tf.weight(conv.weight)
 
 
-def _run_blocks(blocks: Sequence[nn.Module], x: torch.Tensor) -> torch.Tensor:
+def _hw(v, tf: Optional[TransposedFilters]):
+    return v if tf is None else TransposedFilters.pair(v)
+
+
+def _conv_relu(conv: nn.Conv2d, x: torch.Tensor, tf: Optional[TransposedFilters] = None) -> torch.Tensor:
+    return torch.cudnn_convolution_relu(x, _w(conv, tf), conv.bias, _hw(conv.stride, tf),
+                                        _hw(conv.padding, tf), _hw(conv.dilation, tf), conv.groups)
+
+
+def _conv_add_relu(conv: nn.Conv2d, x: torch.Tensor, skip: torch.Tensor,
+                   tf: Optional[TransposedFilters] = None) -> torch.Tensor:
+    return torch.cudnn_convolution_add_relu(x, _w(conv, tf), skip, 1.0, conv.bias, _hw(conv.stride, tf),
+                                            _hw(conv.padding, tf), _hw(conv.dilation, tf), conv.groups)
+
+
+def _apply_transposed(m: nn.Module, x: torch.Tensor, tf: TransposedFilters) -> torch.Tensor:
+    """``m(x)`` on the transposed plane, module by module (the stock ``forward`` would use the
+    untransposed filters)."""
+    F = torch.nn.functional
+    if type(m) is nn.Conv2d:
+        if m.padding_mode != 'zeros':
+            raise NotImplementedError("transposed plane: zero padding only")
+        return F.conv2d(x, tf.weight(m.weight), m.bias, tf.pair(m.stride), tf.pair(m.padding),
+                        tf.pair(m.dilation), m.groups)
+    if type(m) is nn.ConvTranspose2d:
+        return F.conv_transpose2d(x, tf.weight(m.weight), m.bias, tf.pair(m.stride), tf.pair(m.padding),
+                                  tf.pair(m.output_padding), m.groups, tf.pair(m.dilation))
+    if isinstance(m, nn.ReLU):
+        return torch.relu(x)
+    if isinstance(m, ResBlock):
+        x = torch.relu(x)
+        return _apply_transposed(m.conv[3], torch.relu(_apply_transposed(m.conv[1], x, tf)), tf) + x
+    raise NotImplementedError(f"transposed plane: no rule for {type(m).__name__}")
+
+
+def _run_blocks(blocks: Sequence[nn.Module], x: torch.Tensor,
+                tf: Optional[TransposedFilters] = None) -> torch.Tensor:
     """``blocks(x)``; with fusion, a conv absorbs the ReLU that follows it (explicit, or the
     one a ResBlock starts with), and a ResBlock absorbs the ReLU that follows IT (the next
     ResBlock's, or the stack's trailing one) -- so a ResBlock always sees a rectified input,
-    which is also the value its skip connection reads (see ResBlock)."""
+    which is also the value its skip connection reads (see ResBlock).  ``tf``: run on the
+    transposed plane (``TransposedFilters``)."""
     if not _can_fuse(x):
         for m in blocks:
-            x = m(x)
+            x = m(x) if tf is None else _apply_transposed(m, x, tf)
         return x
     mods, i, rectified = list(blocks), 0, False
     while i < len(mods):
@@ -67,12 +123,12 @@ def _run_blocks(blocks: Sequence[nn.Module], x: torch.Tensor) -> torch.Tensor:
         nxt = mods[i + 1] if i + 1 < len(mods) else None
         absorbs = isinstance(nxt, (nn.ReLU, ResBlock))
         if type(m) is nn.Conv2d and absorbs:
-            x = _conv_relu(m, x)
+            x = _conv_relu(m, x, tf)
         elif isinstance(m, ResBlock) and absorbs:
             x = x if rectified else torch.relu(x)
-            x = _conv_add_relu(m.conv[3], _conv_relu(m.conv[1], x), x)
+            x = _conv_add_relu(m.conv[3], _conv_relu(m.conv[1], x, tf), x, tf)
         else:
-            x, absorbs = m(x), False
+            x, absorbs = (m(x) if tf is None else _apply_transposed(m, x, tf)), False
         rectified = absorbs or isinstance(m, nn.ReLU)
         i += 2 if (absorbs and isinstance(nxt, nn.ReLU)) else 1
     return x
@@ -232,16 +288,19 @@ class Encoder(nn.Module):
             self._s2d_cache = (key, wp)
         return wp
 
-    def forward(self, x, space_to_depth: bool = False):
+    def forward(self, x, space_to_depth: bool = False, transposed: Optional[TransposedFilters] = None):
+        """``transposed``: ``x`` is on the transposed plane ``[B, C, T, F]`` (see TransposedFilters)."""
         if not space_to_depth:
-            return _run_blocks(self.blocks, x)
+            return _run_blocks(self.blocks, x, transposed)
         w, conv, rest = self.space_to_depth_weight(), self.blocks[0], list(self.blocks)[1:]
+        if transposed is not None:
+            w = transposed.weight(w)
         if _can_fuse(x) and rest and isinstance(rest[0], (nn.ReLU, ResBlock)):
             x = torch.cudnn_convolution_relu(x, w, conv.bias, (1, 1), (1, 1), (1, 1), 1)
             rest = rest[1:] if isinstance(rest[0], nn.ReLU) else rest
         else:
             x = torch.nn.functional.conv2d(x, w, conv.bias, 1, 1)
-        return _run_blocks(rest, x)
+        return _run_blocks(rest, x, transposed)
 
 
 class Decoder(nn.Module):
@@ -265,15 +324,17 @@ class Decoder(nn.Module):
             prev = w
         self.blocks = nn.Sequential(*blocks)
 
-    def forward(self, x, without_last_bias: bool = False):
+    def forward(self, x, without_last_bias: bool = False, transposed: Optional[TransposedFilters] = None):
         """``without_last_bias``: leave out the bias of the final transposed convolution (the
-        caller folds it into the 1x1 projection that consumes the result, PointwiseProjection)."""
+        caller folds it into the 1x1 projection that consumes the result, PointwiseProjection).
+        ``transposed``: ``x`` is on the transposed plane (see TransposedFilters)."""
         last = self.blocks[-1]
         if not (without_last_bias and type(last) is nn.ConvTranspose2d and last.bias is not None):
-            return _run_blocks(self.blocks, x)
-        x = _run_blocks(list(self.blocks)[:-1], x)
-        return torch.nn.functional.conv_transpose2d(x, last.weight, None, last.stride, last.padding,
-                                                    last.output_padding, last.groups, last.dilation)
+            return _run_blocks(self.blocks, x, transposed)
+        x = _run_blocks(list(self.blocks)[:-1], x, transposed)
+        return torch.nn.functional.conv_transpose2d(
+            x, _w(last, transposed), None, _hw(last.stride, transposed), _hw(last.padding, transposed),
+            _hw(last.output_padding, transposed), last.groups, _hw(last.dilation, transposed))
 
 
 class VQVAE(nn.Module):
@@ -389,6 +450,7 @@ class VQVAE(nn.Module):
                            use_local_kernels)
         self._project_t = PointwiseProjection(self.quantize_conv_t)
         self._project_b = PointwiseProjection(self.quantize_conv_b)
+        self._transposed_filters = TransposedFilters()
         # data-parallel training: ONE packed all-reduce of both quantisers' EMA statistics,
         # overlapped with the decoder; inert outside torch.distributed
         self.ema_exchange = (EmaExchange([self.quantize_t, self.quantize_b])
@@ -401,16 +463,18 @@ class VQVAE(nn.Module):
             return self._project_t([enc_t])
         return self.quantize_conv_t(enc_t).permute(0, 2, 3, 1)
 
-    def _prequant_bottom(self, quant_t: torch.Tensor, enc_b: torch.Tensor) -> torch.Tensor:
+    def _prequant_bottom(self, quant_t: torch.Tensor, enc_b: torch.Tensor,
+                         transposed: Optional[TransposedFilters] = None) -> torch.Tensor:
         last = self.dec_t.blocks[-1]
         fold = (not self.adapt_quantized_durations and type(last) is nn.ConvTranspose2d
                 and last.bias is not None and _can_fuse(enc_b) and _as_rows(enc_b) is not None
                 and enc_b.shape[1] % 64 == 0 and self.quantize_conv_b.out_channels == 64
                 and enc_b.shape[0] * enc_b.shape[2] * enc_b.shape[3] >= PointwiseProjection.min_rows)
-        dec_t = self.dec_t(quant_t, without_last_bias=fold)
+        dec_t = self.dec_t(quant_t, without_last_bias=fold, transposed=transposed)
         if self.adapt_quantized_durations:
-            n = min(dec_t.shape[-1], enc_b.shape[-1])
-            dec_t, enc_b = dec_t[..., :n], enc_b[..., :n]
+            time_axis = 3 if transposed is None else 2
+            n = min(dec_t.shape[time_axis], enc_b.shape[time_axis])
+            dec_t, enc_b = dec_t.narrow(time_axis, 0, n), enc_b.narrow(time_axis, 0, n)
         if fold and self._project_b.usable([dec_t, enc_b]):
             return self._project_b([dec_t, enc_b], folded_bias=last.bias)
         if fold:
@@ -441,10 +505,24 @@ class VQVAE(nn.Module):
         return (quant_t, quant_b, diff_t.unsqueeze(0) + diff_b.unsqueeze(0), id_t, id_b,
                 perplexity_t, perplexity_b)
 
-    def encode_codes(self, input: torch.Tensor, space_to_depth: bool = False):
+    def encode_codes(self, input: torch.Tensor, space_to_depth=False):
         """Top and bottom code maps only -- what ``extract_code.py`` stores.  Same codes as
         ``encode``; the bottom quantiser only searches (its lookup, commitment term and
-        perplexity feed nothing here)."""
+        perplexity feed nothing here).
+
+        ``space_to_depth="transposed"``: ``input`` is ``SpectrogramsHelper(space_to_depth=
+        "transposed")``'s ``[B, 8, T/2, F/2]``; the whole encoder runs on the transposed plane
+        (``TransposedFilters``) and the code maps are transposed back to ``[B, F', T']``."""
+        if space_to_depth == "transposed":
+            if self.training or not hasattr(self.quantize_b, "assign") or torch.is_grad_enabled():
+                raise ValueError("space_to_depth='transposed' is an inference path: eval() and no_grad()")
+            tf = self._transposed_filters
+            input = self._normalize(input, True)
+            enc_b = self.enc_b(input, space_to_depth=True, transposed=tf)
+            enc_t = self.enc_t(enc_b, transposed=tf)
+            quant_t, _, id_t, _ = self.quantize_t(self._prequant_top(enc_t))
+            id_b = self.quantize_b.assign(self._prequant_bottom(quant_t.permute(0, 3, 1, 2), enc_b, tf))
+            return id_t.transpose(1, 2), id_b.transpose(1, 2)
         if self.training or not hasattr(self.quantize_b, "assign"):
             out = self.encode(input, space_to_depth=space_to_depth)
             return out[3], out[4]

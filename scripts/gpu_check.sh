@@ -35,7 +35,7 @@ for n in (1, 4, 300):
       timeout 900 python -m pytest tests/test_gpu_quantizer.py -q 2>&1 | tail -40 > gpurun_out/pytest_quant_$tag.log
       tail -3 gpurun_out/pytest_quant_$tag.log ;;
     bench)
-      timeout 900 python bench.py --steps 20 --warmup 3 2>&1 | tail -1 > gpurun_out/bench_$tag.json
+      timeout 900 python bench.py --steps 20 --warmup 3 $BENCH_ARGS 2>&1 | tail -1 > gpurun_out/bench_$tag.json
       cut -c1-400 gpurun_out/bench_$tag.json ;;
     ncu_melif)
       timeout 600 ncu --set full --clock-control none --import-source on -k regex:'^melif_(ws_)?kernel|isi::melif' -s 3 -c 1 \
@@ -124,6 +124,8 @@ for n in (1, 4, 300):
       ISI_MELIF_WS_FB=4 timeout 300 python -m pytest tests/test_gpu_frontend.py -q 2>&1 | tail -3
       ISI_MELIF_WS_FB=4 timeout 600 python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_fb4_$tag.json
       cut -c1-200 gpurun_out/bench_fb4_$tag.json ;;
+    time_melif)
+      timeout 500 python tools/time_melif.py $TIME_MELIF_CONFIGS 2>&1 | tee gpurun_out/time_melif_$tag.log ;;
     diag)
       timeout 200 python tools/diag_melif.py 2>&1 | tail -40 ;;
     e2e_parity)

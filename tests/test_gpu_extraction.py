@@ -191,3 +191,55 @@ def test_code_extractor_carries_attributes_and_names_through_the_prefetch_ring(f
             # so a near-tie may flip; another note's codes would differ almost everywhere)
             differing = int((row.top != single.top).sum()) + int((row.bottom != single.bottom).sum())
             assert differing <= 2, (depth, i, differing)
+
+
+def test_transposed_plane_extraction_gives_the_same_codes(fp32_convs):
+    """The extraction path of the bench: the front end writes the 2x2 blocks frequency-fastest,
+    the encoder runs on the transposed plane with transposed filters (vqvae.TransposedFilters),
+    the code maps come back as ``[B, F', T']``.  Same codes as the plain path, every difference a
+    near tie on the plain path's features; the eager and the graphed extractor agree exactly."""
+    from interactive_spectrogram_inpainting_b200 import extract
+    from interactive_spectrogram_inpainting_b200.utils.spectrograms_helper import MelSpectrogramsHelper
+    import numpy as np
+    torch.manual_seed(9)
+    model = vq.VQVAE(in_channel=2, resolution_factors={"bottom": 16, "top": 2}, adapt_quantized_durations=False)
+    model = model.to(DEV).eval().to(memory_format=torch.channels_last)
+    audio = synthetic.synthetic_notes(6)
+    pcm = (audio * 32767).round().to(torch.int16)
+    names = [f"n{i}" for i in range(6)]
+    batches = [(pcm[:4].pin_memory(), names[:4]), (pcm[4:].pin_memory(), names[4:])]
+    helper_t = MelSpectrogramsHelper(space_to_depth="transposed").to(DEV)
+    with torch.no_grad():
+        # (1) the stacks alone: transposed plane == plain plane, transposed back
+        spec = MelSpectrogramsHelper(channels_last=True).to(DEV).to_spectrogram(pcm.to(DEV))
+        tblocks = helper_t.to_spectrogram(pcm.to(DEV))
+        tf = model._transposed_filters
+        enc_b = model.enc_b(spec)
+        enc_b_t = model.enc_b(tblocks, space_to_depth=True, transposed=tf)
+        torch.testing.assert_close(enc_b_t.transpose(2, 3), enc_b, rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(model.enc_t(enc_b_t, transposed=tf).transpose(2, 3), model.enc_t(enc_b),
+                                   rtol=1e-4, atol=1e-5)
+        q = torch.randn(6, 64, 32, 4, device=DEV).contiguous(memory_format=torch.channels_last)
+        torch.testing.assert_close(
+            model.dec_t(q.transpose(2, 3).contiguous(memory_format=torch.channels_last), transposed=tf).transpose(2, 3),
+            model.dec_t(q), rtol=1e-4, atol=1e-5)
+        # (2) the code maps
+        id_t, id_b = model.encode_codes(tblocks, space_to_depth="transposed")
+        assert id_t.shape == (6, 32, 4) and id_b.shape == (6, 64, 8) and id_t.dtype == torch.int64
+        plain = parity.encode_with_features(model, spec)
+        rep_t, rep_b, n_b = parity.explain_code_maps(plain, plain, id_t.cpu(), id_b.cpu(),
+                                                     model.quantize_t.embed.cpu(), model.quantize_b.embed.cpu())
+        print(f"[transposed plane] top: {rep_t}; bottom ({n_b}/6 notes): {rep_b}")
+        assert rep_t.unexplained == 0 and rep_b.unexplained == 0 and n_b >= 3
+    # (3) through the extractors
+    want_t, want_b = id_t.cpu().numpy(), id_b.cpu().numpy()
+    for graph in (False, True):
+        ex = extract.CodeExtractor(helper_t, model, torch.device(DEV), cuda_graph=graph)
+        rows = ex.run(batches)
+        assert ex.graph_failures == [] and [r.filename for r in rows] == names
+        assert np.array_equal(np.stack([r.top for r in rows]), want_t)
+        assert np.array_equal(np.stack([r.bottom for r in rows]), want_b)
+    rows = extract.extract_codes(extract.SpectrogramBatches(batches, helper_t, torch.device(DEV)), model)
+    assert np.array_equal(np.stack([r.top for r in rows]), want_t)
+    with pytest.raises(ValueError):
+        model.train().encode_codes(tblocks, space_to_depth="transposed")

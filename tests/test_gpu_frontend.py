@@ -148,8 +148,35 @@ def test_space_to_depth_output_is_the_same_spectrogram(samples):
         assert blocks.shape == (3, 8, 512, n_frames // 2)
         assert blocks.permute(0, 2, 3, 1).is_contiguous()
         assert torch.equal(MelSpectrogramsHelper.from_space_to_depth(blocks), plain)
+        # layout 3: the same blocks on the transposed plane (frequency fastest in memory)
+        tblocks = MelSpectrogramsHelper(n_frames=n_frames, space_to_depth="transposed", **extra).to(DEV).to_spectrogram(audio)
+        assert tblocks.shape == (3, 8, n_frames // 2, 512)
+        assert tblocks.permute(0, 2, 3, 1).is_contiguous()
+        assert torch.equal(tblocks.transpose(2, 3), blocks)
+        assert torch.equal(MelSpectrogramsHelper.from_space_to_depth(tblocks, transposed=True), plain)
     with pytest.raises(ValueError):
         MelSpectrogramsHelper(n_frames=127, space_to_depth=True).to(DEV).to_spectrogram(audio)
+    with pytest.raises(ValueError):
+        MelSpectrogramsHelper(space_to_depth="sideways")
+
+
+@pytest.mark.parametrize("n_frames", [128, 126, 124, 121])
+def test_every_layout_holds_the_same_values_at_any_frame_count(n_frames):
+    """The planar and channels-last stores take 32-byte vectors when the row pitch allows
+    (n_frames % 8 / % 4) and 16-byte or scalar stores otherwise; an unaligned view of the output
+    buffer must not matter either (the helper allocates, so alignment is torch's: 256 bytes)."""
+    audio = synthetic.synthetic_notes(5, n_samples=61000).to(DEV)            # fits in 121 frames
+    plain = MelSpectrogramsHelper(n_frames=n_frames).to(DEV).to_spectrogram(audio)
+    assert plain.shape == (5, 2, 1024, n_frames) and plain.is_contiguous()
+    cl = MelSpectrogramsHelper(n_frames=n_frames, channels_last=True).to(DEV).to_spectrogram(audio)
+    assert cl.is_contiguous(memory_format=torch.channels_last)
+    assert torch.equal(cl, plain)
+    reference = MelSpectrogramsHelper(n_frames=128).to(DEV).to_spectrogram(audio)
+    assert torch.equal(plain[..., :121], reference[..., :121])
+    if n_frames % 2 == 0:
+        for mode in (True, "transposed"):
+            blocks = MelSpectrogramsHelper(n_frames=n_frames, space_to_depth=mode).to(DEV).to_spectrogram(audio)
+            assert torch.equal(MelSpectrogramsHelper.from_space_to_depth(blocks, transposed=mode == "transposed"), plain)
 
 
 @pytest.mark.parametrize("n_fft,hop,samples", [(512, 125, 3001), (1024, 250, 5000), (2048, 500, 40000)])

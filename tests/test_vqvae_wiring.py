@@ -40,12 +40,13 @@ def test_fused_stack_walker_is_the_same_function(monkeypatch):
     import torch.nn.functional as F
     from interactive_spectrogram_inpainting_b200.vqvae import vqvae as mod
 
-    def conv(c, x):
-        return F.conv2d(x, c.weight, c.bias, c.stride, c.padding, c.dilation, c.groups)
+    def conv(c, x, tf=None):
+        return F.conv2d(x, mod._w(c, tf), c.bias, mod._hw(c.stride, tf), mod._hw(c.padding, tf),
+                        mod._hw(c.dilation, tf), c.groups)
 
     monkeypatch.setattr(mod, "_can_fuse", lambda x: True)
-    monkeypatch.setattr(mod, "_conv_relu", lambda c, x: torch.relu(conv(c, x)))
-    monkeypatch.setattr(mod, "_conv_add_relu", lambda c, x, skip: torch.relu(conv(c, x) + skip))
+    monkeypatch.setattr(mod, "_conv_relu", lambda c, x, tf=None: torch.relu(conv(c, x, tf)))
+    monkeypatch.setattr(mod, "_conv_add_relu", lambda c, x, skip, tf=None: torch.relu(conv(c, x, tf) + skip))
     torch.manual_seed(3)
     for factor, n_res in ((16, 2), (2, 2), (4, 0), (8, 1)):
         enc = mod.Encoder(2, 32, n_res, 8, factor).eval()
@@ -56,6 +57,11 @@ def test_fused_stack_walker_is_the_same_function(monkeypatch):
             got = enc(x)
             torch.testing.assert_close(got, want, rtol=1e-6, atol=1e-6)
             torch.testing.assert_close(dec(got), dec.blocks(want), rtol=1e-6, atol=1e-6)
+            # the same walk on the transposed plane
+            tf = mod.TransposedFilters()
+            got_t = enc(x.transpose(2, 3).contiguous(), transposed=tf)
+            torch.testing.assert_close(got_t.transpose(2, 3), want, rtol=1e-5, atol=1e-6)
+            torch.testing.assert_close(dec(got_t, transposed=tf).transpose(2, 3), dec.blocks(want), rtol=1e-5, atol=1e-6)
     # a ResBlock that does not follow a convolution still rectifies its own input
     stack = torch.nn.Sequential(mod.ResBlock(4, 2), torch.nn.ReLU()).eval()
     x = torch.randn(1, 4, 8, 8)
@@ -182,3 +188,43 @@ def test_unquantized_bottleneck_matches_reference():
     assert torch.isinf(o[5]).all() and float(o[2].sum()) == 0.0
     with pytest.raises(NotImplementedError):
         ours.quantize_t.embed_code(torch.zeros(1, 2, 2, dtype=torch.long))
+
+
+def test_conv_stacks_on_the_transposed_plane_equal_the_plain_ones():
+    """``TransposedFilters``: a conv stack run on ``x.transpose(2, 3)`` with every filter (and
+    stride / padding pair) transposed gives the transposed result -- encoder (plain and
+    space-to-depth first conv), decoder (with and without its last bias), CPU FP32."""
+    import torch
+    from interactive_spectrogram_inpainting_b200.utils.spectrograms_helper import MelSpectrogramsHelper as H
+    from interactive_spectrogram_inpainting_b200.vqvae import vqvae as vq
+    torch.manual_seed(3)
+    tf = vq.TransposedFilters()
+    x = torch.randn(2, 2, 64, 32)
+    for factor in (16, 4, 2):
+        enc = vq.Encoder(2, 64, 2, 16, factor).eval()
+        with torch.no_grad():
+            want = enc(x)
+            got = enc(x.transpose(2, 3).contiguous(), transposed=tf).transpose(2, 3)
+            torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-6)
+            blocks = H.to_space_to_depth(x).transpose(2, 3).contiguous()
+            got = enc(blocks, space_to_depth=True, transposed=tf).transpose(2, 3)
+            torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-6)
+    for factor in (16, 2):
+        dec = vq.Decoder(32, 2, 64, 2, 16, factor).eval()
+        q = torch.randn(2, 32, 6, 3)
+        with torch.no_grad():
+            for no_bias in (False, True):
+                want = dec(q, without_last_bias=no_bias)
+                got = dec(q.transpose(2, 3).contiguous(), without_last_bias=no_bias, transposed=tf).transpose(2, 3)
+                torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-6)
+    # one copy per weight version
+    w = enc.blocks[0].weight
+    first = tf.weight(w)
+    assert tf.weight(w) is first
+    with torch.no_grad():
+        w.add_(1.0)
+    assert tf.weight(w) is not first and torch.equal(tf.weight(w), w.detach().transpose(2, 3))
+    # the round trip of the block layout, both planes
+    spec = torch.randn(2, 2, 8, 6)
+    assert torch.equal(H.from_space_to_depth(H.to_space_to_depth(spec)), spec)
+    assert torch.equal(H.from_space_to_depth(H.to_space_to_depth(spec).transpose(2, 3), transposed=True), spec)

@@ -20,6 +20,8 @@ if which in ("all", "frontend"):
     audio = synthetic.synthetic_notes(2, n_samples=16000).to(dev)
     pcm = (audio * 32767).round().to(torch.int16)
     for helper in (MelSpectrogramsHelper(), MelSpectrogramsHelper(space_to_depth=True, n_frames=36),
+                   MelSpectrogramsHelper(space_to_depth="transposed", n_frames=36),
+                   MelSpectrogramsHelper(channels_last=True, n_frames=32), MelSpectrogramsHelper(n_frames=35),
                    SpectrogramsHelper(channels_last=True), MelSpectrogramsHelper(n_fft=512, hop_length=125, window_length=512)):
         helper = helper.to(dev)
         helper.to_spectrogram(audio)
