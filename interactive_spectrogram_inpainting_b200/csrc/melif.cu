@@ -15,10 +15,13 @@
 // the transform they spill); the complex spectrum, magnitudes and phase steps never leave
 // shared memory / registers.  HBM traffic is the audio once (frame overlap is served from
 // shared memory) and the final tensor, FB consecutive time steps per row at a time, in one of
-// three layouts (planes, channels-last, 2x2 space-to-depth blocks).  The whole working set is
-// one FB-frame buffer (65 KB with tables and stage at n_fft 2048), so three CTAs share an SM
-// and fill each other's barrier and latency stalls.
+// four layouts (planes, channels-last, 2x2 space-to-depth blocks time- or frequency-fastest),
+// as 32-byte stores where the layout allows.  Two kernels: the generic one below (every thread
+// runs every phase; one FB-frame buffer is its whole working set) and, for the NSynth shape, the
+// warp-specialised one further down.
 #include <stdlib.h>
+
+#include <type_traits>
 
 #include "common.cuh"
 #include "melif_core.cuh"
@@ -324,14 +327,14 @@ struct MelifSmem {
 };
 
 template <int NFFT, int FB>
-__host__ __device__ inline MelifSmem melif_smem_layout(int hop, int sample_bytes, int n_buffers = 1) {
-  using P = Plan<NFFT>;
+__host__ __device__ inline MelifSmem melif_smem_layout(int hop, int sample_bytes, int n_buffers = 1,
+                                                        int pitch_a = Plan<NFFT>::kPitchA) {
   MelifSmem s;
   int off = 0;
   s.tw = off;    off += (NFFT / 2) * 8;                     // FFT twiddles (fft_table_source)
   s.win = off;   off += NFFT * 4;
   s.stage = off; off += n_buffers * ((((FB - 1) * hop + NFFT) * sample_bytes + 15) / 16 * 16);
-  s.za = off;    off += n_buffers * (FB / 2) * P::kPitchA * 16;   // FFT workspace, spectrum, polar values
+  s.za = off;    off += n_buffers * (FB / 2) * pitch_a * 16;      // FFT workspace, spectrum, polar values
   s.bar = off;   off += 64;
   s.total = off;
   return s;
@@ -469,57 +472,65 @@ melif_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params p,
 // ------------------------------------------------------------------------------------------
 // Warp-specialised kernel (n_fft 2048, bulk-copyable audio, even hop): the NSynth shape.
 //
-// One CTA per SM, 24 warps in two roles that run CONCURRENTLY on consecutive batches of
-// FB = 8 frames through a double-buffered workspace:
-//   * 8 transform warps (4 groups of 64 threads, one frame pair each): stage wait, the three
-//     FFT passes; 112 registers (setmaxnreg.inc) for the 16-point butterflies of a pair;
+// One CTA per SM, two roles that run CONCURRENTLY on consecutive batches of FB = 8 frames through
+// a double-buffered workspace:
+//   * 4 transform warps, ONE WARP PER FRAME PAIR (melif_core.cuh, PlanW32): each lane holds 32
+//     complex points of the pair (128 of its 192 registers, setmaxnreg.inc), so the 1024-point
+//     transform is two radix-32 passes with one exchange through shared memory and no barrier
+//     but __syncwarp;
 //   * 16 polar/emit warps (512 threads, one untangle item and two output rows each): polar
 //     of the batch the transform warps finished last, then the mel projection, log / wrap,
-//     epilogue and stores; 64 registers (setmaxnreg.dec).
-// (Measured, profiles/README.md: the two roles are balanced within a few percent -- moving the
-// radix-4 pass 3 to the polar/emit role made THAT role the critical path, 0.373 vs 0.328 ms.)
+//     epilogue and stores; 72 registers (setmaxnreg.dec).
 // The generic kernel gives every thread the transform's register budget, which caps an SM at
-// 16 warps; here the registers are split by need, so 24 warps are resident, and the FMA-heavy
-// transform overlaps the LDS / MUFU / store-heavy emit instead of alternating with it.  The
-// split must CONSERVE the CTA's launch allocation (768 threads x 80 registers = 60 Ki): the
-// transform warps' setmaxnreg.inc spins until the pool holds what the polar/emit warps'
-// setmaxnreg.dec released, 8 x 32 x (112 - 80) = 16 x 32 x (80 - 64).  Hand-off: full[buf] / empty[buf] mbarriers
-// (transform -> polar/emit -> transform); role-wide named barriers inside each role.
+// 16 warps; here the registers are split by need.  The split must CONSERVE the CTA's launch
+// allocation (640 threads x 96 registers = 60 Ki): the transform warps' setmaxnreg.inc spins
+// until the pool holds what the polar/emit warps' setmaxnreg.dec released,
+// 4 x 32 x (192 - 96) = 16 x 32 x (96 - 72).  Hand-off: full[buf] / empty[buf] mbarriers
+// (transform -> polar/emit -> transform), suspended waits.
+// The previous plan (16 x 16 x 4 in three passes, 8 transform warps in groups of 64 with named
+// barriers, 112 / 64 registers) is still built: ISI_MELIF_WS_PLAN=3, and ISI_MELIF_WS_FB=4 (two
+// CTAs of 384 threads per SM) -- measurement knobs.  Measured per 444 notes: 0.307 ms -> 0.295 ms;
+// moving the last pass to the polar/emit role had made THAT role the critical path (0.373 ms).
 // ------------------------------------------------------------------------------------------
-// Geometry of one instantiation: FB = 8 is one CTA of 768 threads per SM, FB = 4 two CTAs of 384
-// (same 24 warps per SM and the same registers per thread; two CTAs fill each other's pipeline
-// fill / drain and set-up bubbles, at twice the per-batch fixed work).
-template <int FB>
+// Geometry of one instantiation.  (Three-pass plan: FB = 8 is one CTA of 768 threads per SM, FB = 4
+// two CTAs of 384 -- the same 24 warps per SM; two CTAs fill each other's pipeline fill / drain and
+// set-up bubbles, at twice the per-batch fixed work.)
+// W32 = the one-warp transform plan (melif_core.cuh, PlanW32): 4 transform warps (one per frame
+// pair, 32 points per lane: 192 registers) + 16 polar/emit warps at 72 registers, 640 threads
+// launched at 96 registers: 4 x 32 x (192 - 96) = 16 x 32 x (96 - 72).
+template <int FB, bool W32>
 struct WsGeometry {
   static constexpr int kPairs = FB / 2;
-  static constexpr int kFftThreads = 64 * kPairs;          // one group of 64 per frame pair
-  static constexpr int kPeThreads = 2 * kFftThreads;
+  static constexpr int kFftThreads = (W32 ? 32 : 64) * kPairs;    // a warp / a group of 64 per frame pair
+  static constexpr int kPeThreads = 128 * kPairs;
   static constexpr int kThreads = kFftThreads + kPeThreads;
-  static constexpr int kCtasPerSm = 768 / kThreads;
-  static_assert(kThreads * kCtasPerSm == 768, "24 warps per SM");
+  static constexpr int kCtasPerSm = W32 ? 1 : 768 / kThreads;
+  static constexpr int kFftRegs = W32 ? 192 : 112, kPeRegs = W32 ? 72 : 64, kLaunchRegs = W32 ? 96 : 80;
+  static_assert(W32 || kThreads * kCtasPerSm == 768, "24 warps per SM");
+  static_assert(!W32 || FB == 8, "the one-warp plan is built for FB = 8");
+  static_assert(kFftThreads * (kFftRegs - kLaunchRegs) <= kPeThreads * (kLaunchRegs - kPeRegs),
+                "setmaxnreg.inc would wait forever for registers nobody releases");
+  static_assert(kThreads * kCtasPerSm * kLaunchRegs <= 65536 && kThreads * kCtasPerSm * (kLaunchRegs + 8) > 65536,
+                "kLaunchRegs must be what __launch_bounds__ gives this many threads per SM");
 };
 constexpr uint32_t kWsWaitHintNs = 1000, kWsWaitSleepNs = 0;
-constexpr int kWsFftRegs = 112, kWsPeRegs = 64, kWsLaunchRegs = 80;
-static_assert(1 * (kWsFftRegs - kWsLaunchRegs) <= 2 * (kWsLaunchRegs - kWsPeRegs),
-              "setmaxnreg.inc would wait forever for registers nobody releases");
-static_assert(768 * kWsLaunchRegs <= 65536 && 768 * (kWsLaunchRegs + 8) > 65536,
-              "kWsLaunchRegs must be what __launch_bounds__ gives 768 threads per SM");
 
-template <int FB, bool MEL, typename S>
-__global__ void __launch_bounds__(WsGeometry<FB>::kThreads, WsGeometry<FB>::kCtasPerSm)
+template <int FB, bool MEL, typename S, bool W32>
+__global__ void __launch_bounds__(WsGeometry<FB, W32>::kThreads, WsGeometry<FB, W32>::kCtasPerSm)
 melif_ws_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params p,
                 float* __restrict__ out, int seg_frames, int n_segs, uint32_t wait_cfg, int ablate) {
   constexpr int NFFT = 2048;
-  using P = Plan<NFFT>;
+  using G = WsGeometry<FB, W32>;
+  using P = typename std::conditional<W32, PlanW32, Plan<NFFT>>::type;
   constexpr int M = P::M, NP = FB / 2;
-  constexpr int kWsFftThreads = WsGeometry<FB>::kFftThreads, kWsPeThreads = WsGeometry<FB>::kPeThreads;
-  constexpr int kWsThreads = WsGeometry<FB>::kThreads;
-  static_assert(NP == kWsFftThreads / 64, "one transform group per frame pair");
+  constexpr int kWsFftThreads = G::kFftThreads, kWsPeThreads = G::kPeThreads;
+  constexpr int kWsThreads = G::kThreads;
+  static_assert(NP == kWsFftThreads / P::kFftThreads, "one transform group per frame pair");
   constexpr int IPT = (M / 2) / kWsPeThreads;         // untangle items per polar/emit thread
   constexpr int RPT = M / kWsPeThreads;               // output rows per polar/emit thread
   static_assert(IPT * kWsPeThreads == M / 2, "whole items per thread");
   extern __shared__ __align__(128) unsigned char smem[];
-  const MelifSmem L = melif_smem_layout<NFFT, FB>(p.hop, (int)sizeof(S), 2);
+  const MelifSmem L = melif_smem_layout<NFFT, FB>(p.hop, (int)sizeof(S), 2, P::kPitchA);
   cpx* twm = reinterpret_cast<cpx*>(smem + L.tw);
   float* win = reinterpret_cast<float*>(smem + L.win);
   S* stage = reinterpret_cast<S*>(smem + L.stage);
@@ -540,7 +551,8 @@ melif_ws_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params
   const float eps = p.safelog_eps;
 
   const cpx* tw_global = reinterpret_cast<const cpx*>(p.twiddle);
-  for (int i = tid; i < M; i += kWsThreads) twm[i] = tw_global[fft_table_source<P>(i)];
+  for (int i = tid; i < M; i += kWsThreads)
+    twm[i] = tw_global[W32 ? fft32_table_source(i) : fft_table_source<Plan<NFFT>>(i)];
   const bool fold_scale = sizeof(S) == 2 && is_pow2_scale(p.pcm_scale);
   const float win_scale = 0.5f * (fold_scale ? p.pcm_scale : 1.f);
   const float sample_scale = (sizeof(S) == 2 && !fold_scale) ? p.pcm_scale : 1.f;
@@ -567,9 +579,9 @@ melif_ws_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params
   // "not selected" while they sat below the polar/emit warps).
   if (tid >= kWsPeThreads) {
     // =========================== transform warps ===========================
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kWsFftRegs));
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(G::kFftRegs));
     const int ft = tid - kWsPeThreads;                     // 0 .. kWsFftThreads - 1
-    const int q = ft >> 6, j = ft & 63;                    // frame pair of this group, lane in it
+    const int q = ft / P::kFftThreads, j = ft % P::kFftThreads;   // frame pair of this group, lane in it
     const uint32_t group_bar = 3 + q;
     // The audio stage is double-buffered and fed by the first transform warp alone (its lanes
     // zero-fill what lies outside the note, lane 0 sends the bulk copy; the mbarrier's release /
@@ -606,24 +618,37 @@ melif_ws_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params
       }
       mbar_wait_pair(bar_stage, buf, use & 1, wait_cfg);     // this batch's audio has landed
       mbar_wait_pair(bar_empty, buf, (use & 1) ^ 1, wait_cfg);   // polar/emit released the workspace
-      if (active)
-        fft_pass1_pair<P>(j, st_cur + (lookback ? 0 : q * p.hop), st_cur + (lookback ? 0 : (q + NP) * p.hop),
-                          true, sample_scale, win, twm, z);
-      mbar_arrive(bar_pass1 + buf);                        // done with this stage buffer
-      if (active) asm volatile("bar.sync %0, 64;" ::"r"(group_bar) : "memory");
-      if (active) {
-        fft_pass2<P>(j, twm, z);
-        asm volatile("bar.sync %0, 64;" ::"r"(group_bar) : "memory");
-        Pass3Regs<P, cpx2> regs;
-        fft_pass3_load<P>(j, z, regs);
-        asm volatile("bar.sync %0, 64;" ::"r"(group_bar) : "memory");
-        fft_pass3_store<P>(j, regs, z);
+      const S* fr_a = st_cur + (lookback ? 0 : q * p.hop);
+      const S* fr_b = st_cur + (lookback ? 0 : (q + NP) * p.hop);
+      if constexpr (W32) {
+        // one warp per pair: two radix-32 passes, the exchange stays inside the warp
+        if (active) fft32_passA(j, fr_a, fr_b, true, sample_scale, win, twm, z);
+        mbar_arrive(bar_pass1 + buf);                      // done with this stage buffer
+        if (active) {                                      // warp-uniform
+          __syncwarp();
+          PassB32Regs regs;
+          fft32_passB_load(j, z, regs);
+          __syncwarp();
+          fft32_passB_store(j, regs, z);
+        }
+      } else {
+        if (active) fft_pass1_pair<Plan<NFFT>>(j, fr_a, fr_b, true, sample_scale, win, twm, z);
+        mbar_arrive(bar_pass1 + buf);                      // done with this stage buffer
+        if (active) asm volatile("bar.sync %0, 64;" ::"r"(group_bar) : "memory");
+        if (active) {
+          fft_pass2<Plan<NFFT>>(j, twm, z);
+          asm volatile("bar.sync %0, 64;" ::"r"(group_bar) : "memory");
+          Pass3Regs<Plan<NFFT>, cpx2> regs;
+          fft_pass3_load<Plan<NFFT>>(j, z, regs);
+          asm volatile("bar.sync %0, 64;" ::"r"(group_bar) : "memory");
+          fft_pass3_store<Plan<NFFT>>(j, regs, z);
+        }
       }
       mbar_arrive(bar_full + buf);                         // release: the spectrum is in place
     }
   } else {
     // =========================== polar / emit warps ===========================
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kWsPeRegs));
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(G::kPeRegs));
     const int t = tid;                                     // 0 .. 511: untangle item and first row
     cpx w_item[IPT];
 #pragma unroll
@@ -698,6 +723,7 @@ static int launch_melif_t(const S* audio, int64_t n_notes, int64_t n_samples,
   return ISI_OK;
 }
 
+static constexpr int ws_pitch(bool w32) { return w32 ? PlanW32::kPitchA : Plan<2048>::kPitchA; }
 // ISI_MELIF_WAIT_HINT / ISI_MELIF_WAIT_SLEEP (ns; testing / profiling): see mbar_wait_backoff
 static uint32_t ws_wait_cfg() {
   static const uint32_t cfg = [] {
@@ -716,17 +742,18 @@ static int ws_ablate() {
   return v;
 }
 
-template <int FB, bool MEL, typename S>
+template <int FB, bool MEL, typename S, bool W32>
 static int launch_melif_ws(const S* audio, int64_t n_notes, int64_t n_samples,
                            const isi_melif_params& p, float* out, cudaStream_t stream) {
-  const MelifSmem L = melif_smem_layout<2048, FB>(p.hop, (int)sizeof(S), 2);
-  cudaError_t e = cudaFuncSetAttribute(melif_ws_kernel<FB, MEL, S>,
+  using G = WsGeometry<FB, W32>;
+  const MelifSmem L = melif_smem_layout<2048, FB>(p.hop, (int)sizeof(S), 2, ws_pitch(W32));
+  cudaError_t e = cudaFuncSetAttribute(melif_ws_kernel<FB, MEL, S, W32>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, L.total);
   if (e != cudaSuccess) return (int)e;
   int seg_frames, n_segs;
-  choose_segments(n_notes, p.n_frames, FB, WsGeometry<FB>::kCtasPerSm, &seg_frames, &n_segs);
+  choose_segments(n_notes, p.n_frames, FB, G::kCtasPerSm, &seg_frames, &n_segs);
   if (n_notes * n_segs > 0x7fffffff) return ISI_ERR_SHAPE;
-  melif_ws_kernel<FB, MEL, S><<<(unsigned)(n_notes * n_segs), WsGeometry<FB>::kThreads, L.total, stream>>>(
+  melif_ws_kernel<FB, MEL, S, W32><<<(unsigned)(n_notes * n_segs), G::kThreads, L.total, stream>>>(
       audio, n_samples, p, out, seg_frames, n_segs, ws_wait_cfg(), ws_ablate());
   ISI_LAUNCH_CHECK();
   return ISI_OK;
@@ -746,14 +773,19 @@ static int launch_melif_s(const S* audio, int64_t n_notes, int64_t n_samples,
   static const bool force_generic = getenv("ISI_MELIF_GENERIC") != nullptr;
   const bool geometry_ok = (n_samples % 8 == 0) && (p.hop % 8 == 0) && (p.pad_left % 8 == 0);
   if (!force_generic && p.n_fft == 2048 && bulk_ok && geometry_ok && p.hop <= 2048 &&
-      melif_smem_layout<2048, 8>(p.hop, (int)sizeof(S), 2).total <= 227 * 1024) {
+      melif_smem_layout<2048, 8>(p.hop, (int)sizeof(S), 2, ws_pitch(true)).total <= 227 * 1024) {
     // ISI_MELIF_WS_FB=4 (testing / profiling): two 384-thread CTAs per SM instead of one of 768
     static const bool fb4 = getenv("ISI_MELIF_WS_FB") != nullptr && atoi(getenv("ISI_MELIF_WS_FB")) == 4;
     if (fb4)
-      return p.use_mel ? launch_melif_ws<4, true, S>(audio, n_notes, n_samples, p, out, stream)
-                       : launch_melif_ws<4, false, S>(audio, n_notes, n_samples, p, out, stream);
-    return p.use_mel ? launch_melif_ws<8, true, S>(audio, n_notes, n_samples, p, out, stream)
-                     : launch_melif_ws<8, false, S>(audio, n_notes, n_samples, p, out, stream);
+      return p.use_mel ? launch_melif_ws<4, true, S, false>(audio, n_notes, n_samples, p, out, stream)
+                       : launch_melif_ws<4, false, S, false>(audio, n_notes, n_samples, p, out, stream);
+    // ISI_MELIF_WS_PLAN=3 (testing / profiling): the 16 x 16 x 4 transform plan (8 transform warps)
+    static const bool plan3 = getenv("ISI_MELIF_WS_PLAN") != nullptr && atoi(getenv("ISI_MELIF_WS_PLAN")) == 3;
+    if (plan3)
+      return p.use_mel ? launch_melif_ws<8, true, S, false>(audio, n_notes, n_samples, p, out, stream)
+                       : launch_melif_ws<8, false, S, false>(audio, n_notes, n_samples, p, out, stream);
+    return p.use_mel ? launch_melif_ws<8, true, S, true>(audio, n_notes, n_samples, p, out, stream)
+                     : launch_melif_ws<8, false, S, true>(audio, n_notes, n_samples, p, out, stream);
   }
 #define ISI_MELIF_CASE(N, FB, NT)                                                               \
   case N:                                                                                     \

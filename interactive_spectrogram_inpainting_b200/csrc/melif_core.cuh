@@ -392,6 +392,113 @@ ISI_HD void fft_pass3_store(int t, const Pass3Regs<P, C, NT3>& r, C* z) {
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// One-warp plan for n_fft = 2048 (the warp-specialised kernel): M = 1024 = 32 x 32.  A warp owns
+// a frame pair; each lane holds 32 complex points of the pair (128 registers), so the transform
+// is TWO radix-32 passes with ONE exchange through shared memory, inside the warp (no block or
+// group barrier, __syncwarp only):
+//   pass A  lane j: window + pack the points m = j + 32 r, DFT-32 over r, twiddle W_M^(j p),
+//           store element (p, j) at p * 33 + j  (lanes along j: contiguous)
+//   pass B  lane p: load (p, j) for all j (stride 33: a quarter warp hits 8 bank groups),
+//           DFT-32 over j, store bin p + 32 q in natural order (lanes along p: contiguous)
+//   X[p + 32 q] = sum_j W_32^(j q) [ W_M^(j p) sum_r W_32^(r p) x[j + 32 r] ]
+// Against the 16 x 16 x 4 plan above: 3 instead of 5 sweeps of the pair's 16 KB through shared
+// memory, half the threads (one warp instead of two per pair), no barriers.
+struct PlanW32 {
+  static constexpr int N = 2048, M = 1024;
+  static constexpr int kFftThreads = 32;
+  static constexpr int kBlockPitch = 33;
+  static constexpr int kPitchA = kBlockPitch * 32;      // 1056 >= M + 8 (band overrun)
+};
+
+// slot i of the shared twiddle table holds W_M^(j p), i = 32 p + j: index into the W_N^k table
+ISI_HD int fft32_table_source(int i) { return 2 * (i % 32) * (i / 32); }
+
+// forward 32-point DFT in registers, natural order in and out: even / odd 16-point halves, then
+// X[k] = E[k] + W_32^k O[k], X[k + 16] = E[k] - W_32^k O[k]
+template <typename C>
+ISI_HD void dft32(C* v) {
+  C e[16], o[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) { e[i] = v[2 * i]; o[i] = v[2 * i + 1]; }
+  dft16(e);
+  dft16(o);
+  // cos / sin of 2 pi k / 32, k = 0..15
+  const float c[16] = {1.f, 0.98078528040323044913f, 0.92387953251128675613f, 0.83146961230254523708f,
+                       0.70710678118654752440f, 0.55557023301960222474f, 0.38268343236508977173f,
+                       0.19509032201612826785f, 0.f, -0.19509032201612826785f, -0.38268343236508977173f,
+                       -0.55557023301960222474f, -0.70710678118654752440f, -0.83146961230254523708f,
+                       -0.92387953251128675613f, -0.98078528040323044913f};
+  const float s[16] = {0.f, 0.19509032201612826785f, 0.38268343236508977173f, 0.55557023301960222474f,
+                       0.70710678118654752440f, 0.83146961230254523708f, 0.92387953251128675613f,
+                       0.98078528040323044913f, 1.f, 0.98078528040323044913f, 0.92387953251128675613f,
+                       0.83146961230254523708f, 0.70710678118654752440f, 0.55557023301960222474f,
+                       0.38268343236508977173f, 0.19509032201612826785f};
+#pragma unroll
+  for (int k = 0; k < 16; ++k) {
+    C t;
+    if (k == 0) t = o[0];
+    else if (k == 8) t = mul_neg_i(o[8]);
+    else t = cmul(o[k], cpx{c[k], -s[k]});
+    v[k] = cadd(e[k], t);
+    v[k + 16] = csub(e[k], t);
+  }
+}
+
+template <typename S, bool ALIGNED, bool PRESCALE>
+ISI_HD void fft32_passA_t(int j, const S* frame_a, const S* frame_b, float sample_scale,
+                          const float* win, const cpx* tws, cpx2* zA) {
+  cpx2 v[32];
+#pragma unroll
+  for (int r = 0; r < 32; ++r) {
+    const int m = j + 32 * r;
+    const cpx a = load_pair<ALIGNED>(frame_a, m), b = load_pair<ALIGNED>(frame_b, m);
+    const cpx w = reinterpret_cast<const cpx*>(win)[m];
+    f2 re = mk2(a.re, b.re), im = mk2(a.im, b.im);
+    if (PRESCALE) { re = mul2(re, bc(sample_scale)); im = mul2(im, bc(sample_scale)); }
+    v[r].re = mul2(re, bc(w.re));
+    v[r].im = mul2(im, bc(w.im));
+  }
+  dft32(v);
+#pragma unroll
+  for (int p0 = 1; p0 < 32; p0 += 4) {          // four twiddle loads in flight at a time
+    cpx t[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) if (p0 + i < 32) t[i] = tws[32 * (p0 + i) + j];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) if (p0 + i < 32) v[p0 + i] = cmul(v[p0 + i], t[i]);
+  }
+  auto o = split_ptr(zA + j);
+#pragma unroll
+  for (int p = 0; p < 32; ++p) put(o, PlanW32::kBlockPitch * p, v[p]);
+}
+template <typename S>
+ISI_HD void fft32_passA(int j, const S* frame_a, const S* frame_b, bool pair_aligned,
+                        float sample_scale, const float* win, const cpx* tws, cpx2* zA) {
+  if (sample_scale != 1.f) {      // rare: a PCM scale that is not a power of two
+    if (pair_aligned) fft32_passA_t<S, true, true>(j, frame_a, frame_b, sample_scale, win, tws, zA);
+    else fft32_passA_t<S, false, true>(j, frame_a, frame_b, sample_scale, win, tws, zA);
+  } else {
+    if (pair_aligned) fft32_passA_t<S, true, false>(j, frame_a, frame_b, 1.f, win, tws, zA);
+    else fft32_passA_t<S, false, false>(j, frame_a, frame_b, 1.f, win, tws, zA);
+  }
+}
+
+// pass B in two calls with a __syncwarp between them: the natural-order slots overlap the
+// (p, j) slots other lanes of the warp still have to read
+struct PassB32Regs { cpx2 u[32]; };
+ISI_HD void fft32_passB_load(int p, const cpx2* zA, PassB32Regs& r) {
+  const cpx2* row = zA + PlanW32::kBlockPitch * p;
+#pragma unroll
+  for (int j = 0; j < 32; ++j) r.u[j] = row[j];
+  dft32(r.u);
+}
+ISI_HD void fft32_passB_store(int p, const PassB32Regs& r, cpx2* z) {
+  auto o = split_ptr(z + p);
+#pragma unroll
+  for (int q = 0; q < 32; ++q) put(o, 32 * q, r.u[q]);
+}
+
 // phase step folded into [-pi, pi] (round-to-nearest multiple of 2 pi; equals the
 // numpy/magenta unwrap rule except on exact +-pi ties)
 ISI_HD float wrap_step(float dd) {

@@ -5,23 +5,27 @@
 // can be checked against the oracle without a GPU.
 #include <algorithm>
 #include <cstdint>
+#include <type_traits>
 #include <vector>
 
 #include "melif_core.cuh"
 
 using namespace isi::melif;
 
-template <int NFFT, int FB, int NT, bool MEL>
+// W32: the warp-specialised kernel's one-warp transform (PlanW32: 32 lanes x 32 points, two
+// radix-32 passes) instead of the generic 16 x 16 x 4 plan; polar and emit are shared.
+template <int NFFT, int FB, int NT, bool MEL, bool W32 = false>
 static void emulate(const float* audio, int64_t n_notes, int64_t n_samples, int hop, int pad_left,
                     int n_frames, int drop_dc, int use_mel, int mel_width, float eps,
                     const float* window, const float* twiddle, const int32_t* mel_start,
                     const int32_t* mel_count, const float* mel_weight, float* out, int seg_frames,
                     int mask_phase, float mask_threshold, const float* affine) {
-  using P = Plan<NFFT>;
+  using P = typename std::conditional<W32, PlanW32, Plan<NFFT>>::type;
+  static_assert(!W32 || NFFT == 2048, "the one-warp plan is for n_fft 2048");
   constexpr int M = P::M, NP = FB / 2, IPT = (M / 2) / NT, RPT = M / NT, kGroups = NT / 64;
   const cpx* tw = reinterpret_cast<const cpx*>(twiddle);
   std::vector<cpx> twm(M);
-  for (int i = 0; i < M; ++i) twm[i] = tw[fft_table_source<P>(i)];
+  for (int i = 0; i < M; ++i) twm[i] = tw[W32 ? fft32_table_source(i) : fft_table_source<Plan<NFFT>>(i)];
   std::vector<float> win(NFFT);
   for (int i = 0; i < NFFT; ++i) win[i] = window[i] * 0.5f;   // the kernel's table: untangle's 1/2 folded in
   const bool aligned = (hop % 2) == 0;
@@ -37,22 +41,38 @@ static void emulate(const float* audio, int64_t n_notes, int64_t n_samples, int 
     for (int tid = 0; tid < NT; ++tid)
       stage_fill(tid, NT, stage.data(), span, note, n_samples, (int64_t)frame * hop - pad_left);
     auto active = [&](int q) { return lookback ? (q == NP - 1) : (q < nf); };
-    for (int tid = 0; tid < NT; ++tid)
-      for (int q = tid / 64; q < NP; q += kGroups)
-        if (active(q))
-          fft_pass1_pair<P>(tid & 63, stage.data() + (lookback ? 0 : q * hop),
-                            stage.data() + (lookback ? 0 : (q + NP) * hop), aligned, 1.f, win.data(),
-                            twm.data(), zA.data() + q * P::kPitchA);
-    for (int tid = 0; tid < NT; ++tid)
-      for (int q = tid / 64; q < NP; q += kGroups)
-        if (active(q)) fft_pass2<P>(tid & 63, twm.data(), zA.data() + q * P::kPitchA);
-    std::vector<Pass3Regs<P, cpx2>> regs((size_t)NT * NP);
-    for (int tid = 0; tid < NT; ++tid)
-      for (int q = tid / 64; q < NP; q += kGroups)
-        if (active(q)) fft_pass3_load<P>(tid & 63, zA.data() + q * P::kPitchA, regs[tid * NP + q]);
-    for (int tid = 0; tid < NT; ++tid)
-      for (int q = tid / 64; q < NP; q += kGroups)
-        if (active(q)) fft_pass3_store<P>(tid & 63, regs[tid * NP + q], zA.data() + q * P::kPitchA);
+    if constexpr (W32) {
+      std::vector<PassB32Regs> regs32((size_t)NP * 32);
+      for (int q = 0; q < NP; ++q) {
+        if (!active(q)) continue;
+        cpx2* z = zA.data() + q * P::kPitchA;
+        for (int j = 0; j < 32; ++j)
+          fft32_passA(j, stage.data() + (lookback ? 0 : q * hop), stage.data() + (lookback ? 0 : (q + NP) * hop),
+                      aligned, 1.f, win.data(), twm.data(), z);
+        for (int l = 0; l < 32; ++l) fft32_passB_load(l, z, regs32[q * 32 + l]);
+        for (int l = 0; l < 32; ++l) fft32_passB_store(l, regs32[q * 32 + l], z);
+      }
+      return;
+    }
+    if constexpr (!W32) {
+      using PG = Plan<NFFT>;
+      for (int tid = 0; tid < NT; ++tid)
+        for (int q = tid / 64; q < NP; q += kGroups)
+          if (active(q))
+            fft_pass1_pair<PG>(tid & 63, stage.data() + (lookback ? 0 : q * hop),
+                               stage.data() + (lookback ? 0 : (q + NP) * hop), aligned, 1.f, win.data(),
+                               twm.data(), zA.data() + q * P::kPitchA);
+      for (int tid = 0; tid < NT; ++tid)
+        for (int q = tid / 64; q < NP; q += kGroups)
+          if (active(q)) fft_pass2<PG>(tid & 63, twm.data(), zA.data() + q * P::kPitchA);
+      std::vector<Pass3Regs<PG, cpx2>> regs((size_t)NT * NP);
+      for (int tid = 0; tid < NT; ++tid)
+        for (int q = tid / 64; q < NP; q += kGroups)
+          if (active(q)) fft_pass3_load<PG>(tid & 63, zA.data() + q * P::kPitchA, regs[tid * NP + q]);
+      for (int tid = 0; tid < NT; ++tid)
+        for (int q = tid / 64; q < NP; q += kGroups)
+          if (active(q)) fft_pass3_store<PG>(tid & 63, regs[tid * NP + q], zA.data() + q * P::kPitchA);
+    }
   };
   auto polar = [&](std::vector<BinState>& st, bool seed_only) {
     for (int tid = 0; tid < NT; ++tid)
@@ -108,6 +128,10 @@ extern "C" int melif_emulate(const float* audio, int64_t n_notes, int64_t n_samp
 #define ARGS audio, n_notes, n_samples, hop, pad_left, n_frames, drop_dc, use_mel, mel_width, eps, \
              window, twiddle, mel_start, mel_count, mel_weight, out, seg_frames, mask_phase, mask_threshold, affine
   if (seg_frames <= 0) seg_frames = (n_frames + 7) / 8 * 8;
+  if (n_fft == -2048) {      // the warp-specialised kernel's one-warp transform plan
+    if (use_mel) emulate<2048, 8, 256, true, true>(ARGS); else emulate<2048, 8, 256, false, true>(ARGS);
+    return 0;
+  }
 #define CASE(N, FB, NT) case N: if (use_mel) emulate<N, FB, NT, true>(ARGS); else emulate<N, FB, NT, false>(ARGS); return 0;
   switch (n_fft) {
     CASE(2048, 8, 256)

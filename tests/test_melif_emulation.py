@@ -28,7 +28,7 @@ def emu(tmp_path_factory):
     return lib
 
 
-def _run(emu, helper, audio, seg_frames=0):
+def _run(emu, helper, audio, seg_frames=0, plan=None):
     n_notes, n_samples = audio.shape
     frames = helper.num_frames(n_samples)
     out = np.zeros((n_notes, 2, helper.n_freq, frames), dtype=np.float32)
@@ -43,7 +43,7 @@ def _run(emu, helper, audio, seg_frames=0):
     else:
         width, mel_args = 0, (None, None, None)
     rc = emu.melif_emulate(ptr(a), ctypes.c_int64(n_notes), ctypes.c_int64(n_samples),
-                           helper.n_fft, helper.hop_length, helper.pad_left, frames,
+                           -helper.n_fft if plan == "w32" else helper.n_fft, helper.hop_length, helper.pad_left, frames,
                            1 if helper.drop_bin == "dc" else 0, int(helper.use_mel_scale), width,
                            ctypes.c_float(helper.safelog_eps), ptr(win), ptr(tw), *mel_args,
                            ptr(out), seg_frames,
@@ -109,6 +109,26 @@ def test_emulated_kernel_matches_oracle_2048(emu, use_mel):
     got = _run(emu, helper, audio)
     assert got.shape == (2, 2, 1024, 128)
     check_against_oracle(got, audio, fo.FrontEndConfig(use_mel_scale=use_mel))
+
+
+@pytest.mark.parametrize("use_mel", [True, False])
+def test_emulated_one_warp_plan_matches_oracle_and_the_generic_plan(emu, use_mel):
+    """The warp-specialised kernel's transform (PlanW32: one warp per frame pair, two radix-32
+    passes with one exchange through shared memory): same oracle bars, segments and ragged
+    lengths included, and the same spectrum as the 16 x 16 x 4 plan up to FP32 rounding."""
+    audio = synthetic.synthetic_notes(2)
+    helper = (sh.MelSpectrogramsHelper() if use_mel else sh.SpectrogramsHelper())
+    got = _run(emu, helper, audio, plan="w32")
+    assert got.shape == (2, 2, 1024, 128)
+    check_against_oracle(got, audio, fo.FrontEndConfig(use_mel_scale=use_mel))
+    generic = _run(emu, helper, audio)
+    d0 = (got[:, 0] - generic[:, 0]).abs()
+    tol = 1e-4 * generic[:, 0].abs().max()                              # the oracle bar's scale
+    assert (d0 > tol).double().mean() < 2e-3 and d0.max() < 0.05, ((d0 > tol).double().mean(), d0.max())
+    for seg in (16, 40):
+        assert torch.equal(_run(emu, helper, audio[:1], seg_frames=seg, plan="w32"), got[:1])
+    short = synthetic.synthetic_notes(1, n_samples=9001)
+    check_against_oracle(_run(emu, helper, short, plan="w32"), short, fo.FrontEndConfig(use_mel_scale=use_mel))
 
 
 @pytest.mark.parametrize("n_fft,hop,samples", [(1024, 256, 9000), (512, 128, 4099)])
