@@ -690,7 +690,7 @@ def b200_arm(args):
         "gpu_launches": launches,
         "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"],
                    "reasons": clk["reasons"], "samples": clk["samples"]},
-        "roofline": {"kernel": "melif_ws_kernel<8,mel> (warp-specialised front end: 8 transform + 16 polar/emit warps)",
+        "roofline": {"kernel": "melif_ws_kernel<8,mel> (warp-specialised front end: 4 transform warps, one per frame pair, + 16 polar/emit warps)",
                      "bound": "hbm", "achieved": melif_gbs,
                      "peak": hbm_peak, "unit": "GB/s", "frac": melif_gbs / hbm_peak,
                      "peak_source": f"MEASURED_PEAKS.json ({peak_kind})",
