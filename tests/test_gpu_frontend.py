@@ -221,3 +221,30 @@ def test_repeated_launches_are_bit_identical_under_load():
         assert torch.equal(helper.to_spectrogram(pcm[:n]), first[:n]), n
     plain = MelSpectrogramsHelper().to(DEV)
     assert torch.equal(MelSpectrogramsHelper.from_space_to_depth(first[:9]), plain.to_spectrogram(pcm[:9]))
+
+
+@pytest.mark.parametrize("layout", ["planar", "channels_last", "blocks", "blocks_t"])
+def test_output_buffer_aligned_to_16_but_not_32_bytes(layout):
+    """C-ABI callers own the output buffer: 16-byte alignment is the contract (ISI_ERR_ALIGN below
+    it); the 32-byte stores must step aside for a buffer that is only 16-byte aligned."""
+    from interactive_spectrogram_inpainting_b200 import _lib
+    kw = {"planar": {}, "channels_last": dict(channels_last=True), "blocks": dict(space_to_depth=True),
+          "blocks_t": dict(space_to_depth="transposed")}[layout]
+    helper = MelSpectrogramsHelper(**kw).to(DEV)
+    pcm = (synthetic.synthetic_notes(3) * 32767).round().to(torch.int16).to(DEV)
+    want = helper.to_spectrogram(pcm)
+    params = helper._params(128)
+    params.audio_format, params.pcm_scale = _lib.AUDIO_PCM16, helper.pcm_scale
+    raw = torch.zeros(want.numel() + 8, dtype=torch.float32, device=DEV)
+    for offset, ok in ((4, True), (1, False)):
+        out = raw[offset:offset + want.numel()]
+        assert out.data_ptr() % 32 == (16 if ok else 4)
+        if ok:
+            _lib.invoke("isi_melif_forward", pcm.data_ptr(), 3, pcm.shape[1], params, out.data_ptr(),
+                        _lib.stream_ptr(pcm.device))
+            stored = want.permute(0, 2, 3, 1) if layout != "planar" else want       # memory order
+            assert torch.equal(out.view(stored.shape), stored.contiguous() if layout == "planar" else stored)
+        else:
+            with pytest.raises(RuntimeError):
+                _lib.invoke("isi_melif_forward", pcm.data_ptr(), 3, pcm.shape[1], params, out.data_ptr(),
+                            _lib.stream_ptr(pcm.device))
