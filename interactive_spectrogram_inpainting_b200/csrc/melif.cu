@@ -19,6 +19,7 @@
 // as 32-byte stores where the layout allows.  Two kernels: the generic one below (every thread
 // runs every phase; one FB-frame buffer is its whole working set) and, for the NSynth shape, the
 // warp-specialised one further down.
+#include <stdio.h>
 #include <stdlib.h>
 
 #include <type_traits>
@@ -738,7 +739,11 @@ static uint32_t ws_wait_cfg() {
 // buffers back (times the transform role alone), 2 = the transform warps only hand them over
 // (times the polar/emit role alone), 3 = both (the skeleton: staging, barriers, prologue).
 static int ws_ablate() {
-  static const int v = getenv("ISI_MELIF_ABLATE") ? atoi(getenv("ISI_MELIF_ABLATE")) : 0;
+  static const int v = [] {
+    const int a = getenv("ISI_MELIF_ABLATE") ? atoi(getenv("ISI_MELIF_ABLATE")) : 0;
+    if (a) fprintf(stderr, "libisi_b200: ISI_MELIF_ABLATE=%d -- profiling mode, isi_melif_forward's output is WRONG\n", a);
+    return a;
+  }();
   return v;
 }
 
