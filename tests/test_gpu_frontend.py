@@ -27,7 +27,10 @@ def test_nsynth_shape_matches_oracle(use_mel):
 
 
 @pytest.mark.parametrize("n_fft,hop,samples", [(1024, 256, 9000), (512, 128, 4099),
-                                               (2048, 512, 300), (2048, 512, 96001)])
+                                               (2048, 512, 300), (2048, 512, 96001),
+                                               # other hops on the warp-specialised kernel (n_fft 2048,
+                                               # sample count and hop multiples of 8)
+                                               (2048, 256, 16000), (2048, 1024, 32000), (2048, 128, 8000)])
 def test_other_sizes_and_ragged_lengths(n_fft, hop, samples):
     audio = synthetic.synthetic_notes(2, n_samples=samples)
     helper = MelSpectrogramsHelper(n_fft=n_fft, hop_length=hop, window_length=n_fft).to(DEV)
