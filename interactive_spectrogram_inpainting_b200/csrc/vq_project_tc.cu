@@ -86,6 +86,7 @@ vq_project_tc_kernel(const float* __restrict__ src0, int chunks0, int64_t stride
                      const char* __restrict__ w_tiles, const float* __restrict__ bias_global,
                      float* __restrict__ out) {
   using namespace proj;
+  const bool wide_out = (reinterpret_cast<uintptr_t>(out) & 31) == 0;
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t smem_base = s32(smem);
   float* bias = reinterpret_cast<float*>(smem + Smem::bias);
@@ -238,11 +239,27 @@ vq_project_tc_kernel(const float* __restrict__ src0, int chunks0, int64_t stride
       mbar_arrive(bar_acc_empty + 8 * sa);                 // the values are in registers
       const int64_t row = tile * kTileRows + warp * 32 + lane;
       if (row < n_rows) {
-        float4* dst = reinterpret_cast<float4*>(out + row * kOut);
+        // a lane owns a whole 256-byte output row, so every store instruction touches 32
+        // different lines and the LSU pays per line: 32-byte stores (STG.256) halve the count
+        float* dst = out + row * kOut;
+        if (wide_out) {
 #pragma unroll
-        for (int c = 0; c < kOut; c += 4) {
-          const float4 b = *reinterpret_cast<const float4*>(bias + c);
-          dst[c >> 2] = make_float4(v[c] + b.x, v[c + 1] + b.y, v[c + 2] + b.z, v[c + 3] + b.w);
+          for (int c = 0; c < kOut; c += 8) {
+            const float4 b0 = *reinterpret_cast<const float4*>(bias + c);
+            const float4 b1 = *reinterpret_cast<const float4*>(bias + c + 4);
+            asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                         :: "l"(dst + c), "f"(v[c] + b0.x), "f"(v[c + 1] + b0.y), "f"(v[c + 2] + b0.z),
+                            "f"(v[c + 3] + b0.w), "f"(v[c + 4] + b1.x), "f"(v[c + 5] + b1.y),
+                            "f"(v[c + 6] + b1.z), "f"(v[c + 7] + b1.w)
+                         : "memory");
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < kOut; c += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(bias + c);
+            reinterpret_cast<float4*>(dst)[c >> 2] =
+                make_float4(v[c] + b.x, v[c + 1] + b.y, v[c + 2] + b.z, v[c + 3] + b.w);
+          }
         }
       }
     }
