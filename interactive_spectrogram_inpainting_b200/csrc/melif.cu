@@ -690,20 +690,21 @@ melif_ws_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params
 }
 
 // Frames per CTA: whole notes when the batch fills the GPU on its own, else the split that
-// maximises (wave efficiency) x (useful / useful + look-back work).
+// minimises the estimated makespan, waves x (batches per CTA + the look-back transform of a CTA
+// that does not start at frame 0 + half a batch of set-up).  A single note (the interactive
+// server's request) becomes 16 CTAs of one batch each instead of 4 CTAs of four.
 static void choose_segments(int64_t n_notes, int n_frames, int fb, int ctas_per_sm, int* seg_frames, int* n_segs) {
   const int frames_padded = (n_frames + fb - 1) / fb * fb;
-  const int max_segs = frames_padded / (4 * fb) > 1 ? frames_padded / (4 * fb) : 1;
+  const int max_segs = frames_padded / fb;
   const double slots = (double)ctas_per_sm * kNumSms;   // resident CTAs: __launch_bounds__(NT, ctas_per_sm)
-  double best = -1.0;
+  double best = 1e30;
   *seg_frames = frames_padded; *n_segs = 1;
   for (int s = 1; s <= max_segs; ++s) {
     const int sf = ((frames_padded + s - 1) / s + fb - 1) / fb * fb;
     const int ns = (n_frames + sf - 1) / sf;
-    const double waves = (double)n_notes * ns / slots;
-    const double wave_eff = waves / (double)(int64_t)(waves + 0.999999);
-    const double eff = wave_eff * (ns == 1 ? 1.0 : (double)sf / (sf + 2.0));
-    if (eff > best + 1e-9) { best = eff; *seg_frames = sf; *n_segs = ns; }
+    const double waves = (double)(int64_t)((double)n_notes * ns / slots + 0.999999);
+    const double cost = waves * (sf / fb + (ns > 1 ? 1.0 : 0.0) + 0.5);
+    if (cost < best - 1e-9) { best = cost; *seg_frames = sf; *n_segs = ns; }
   }
 }
 
