@@ -519,7 +519,8 @@ constexpr uint32_t kWsWaitHintNs = 1000, kWsWaitSleepNs = 0;
 template <int FB, bool MEL, typename S, bool W32>
 __global__ void __launch_bounds__(WsGeometry<FB, W32>::kThreads, WsGeometry<FB, W32>::kCtasPerSm)
 melif_ws_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params p,
-                float* __restrict__ out, int seg_frames, int n_segs, uint32_t wait_cfg, int ablate) {
+                float* __restrict__ out, int seg_frames, int n_segs, int n_items_total, uint32_t wait_cfg,
+                int ablate) {
   constexpr int NFFT = 2048;
   using G = WsGeometry<FB, W32>;
   using P = typename std::conditional<W32, PlanW32, Plan<NFFT>>::type;
@@ -544,12 +545,26 @@ melif_ws_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params
   constexpr int kBufElems = NP * P::kPitchA;
 
   const int tid = threadIdx.x;
-  const int note_idx = blockIdx.x / n_segs, seg = blockIdx.x - note_idx * n_segs;
-  const int fs = seg * seg_frames;
-  const int fe = min(p.n_frames, fs + seg_frames);
-  const S* note = audio + (int64_t)note_idx * n_samples;
   const int dc = p.drop_dc ? 1 : 0;
   const float eps = p.safelog_eps;
+  // PERSISTENT: a CTA walks the work items blockIdx.x, blockIdx.x + gridDim.x, ... (an item = a
+  // run of frames of one note).  The tables, the barriers and the two-deep pipeline live across
+  // items: the first batch of the next item is staged and transformed while the polar/emit
+  // warps finish the last batch of this one, so only the first fill and the last drain of a CTA
+  // are exposed (with one CTA per item they were, for every note).
+  const int n_items = n_items_total;
+  const int item_step = (int)gridDim.x;
+  struct Item { int note_idx, fs, fe, n_batches, b_begin; };
+  auto make_item = [&](int item) {
+    Item w;
+    w.note_idx = item / n_segs;
+    const int seg = item - w.note_idx * n_segs;
+    w.fs = seg * seg_frames;
+    w.fe = min(p.n_frames, w.fs + seg_frames);
+    w.n_batches = (w.fe - w.fs + FB - 1) / FB;
+    w.b_begin = w.fs > 0 ? -1 : 0;
+    return w;
+  };
 
   const cpx* tw_global = reinterpret_cast<const cpx*>(p.twiddle);
   for (int i = tid; i < M; i += kWsThreads)
@@ -572,9 +587,6 @@ melif_ws_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params
   }
   __syncthreads();
 
-  const int n_batches = (fe - fs + FB - 1) / FB;
-  const int b_begin = fs > 0 ? -1 : 0;
-
   // The transform role takes the HIGHEST warp ids: the SMSP arbiter prefers the highest eligible
   // warp, and the transform warps are the critical path (13 % of their stall samples were
   // "not selected" while they sat below the polar/emit warps).
@@ -589,33 +601,53 @@ melif_ws_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params
     // acquire carries both to the readers), so the four groups never meet on a role-wide
     // barrier: they drift apart and their load bursts and butterfly phases interleave.
     const bool feeder = ft < 32;
+    // first batch of an item: the look-back frame of a segment that starts mid-note, else frames fs..
+    auto first_batch = [&](const Item& w, int* frame, int* nfr) {
+      *frame = w.fs > 0 ? w.fs - 1 : w.fs;
+      *nfr = w.fs > 0 ? 1 : min(FB, w.fe - w.fs);
+    };
     if (feeder) {
-      const StageSpan<S> sp(n_samples, p.hop, p.pad_left, NFFT, fs > 0 ? fs - 1 : fs, fs > 0 ? 1 : min(FB, fe - fs));
+      const Item w0 = make_item((int)blockIdx.x);
+      int frame, nfr;
+      first_batch(w0, &frame, &nfr);
+      const StageSpan<S> sp(n_samples, p.hop, p.pad_left, NFFT, frame, nfr);
       sp.fill(stage, ft, 32);
       __syncwarp();
-      if (ft == 0) sp.issue(stage, note, bar_stage);
+      if (ft == 0) sp.issue(stage, audio + (int64_t)w0.note_idx * n_samples, bar_stage);
     }
     uint32_t it = 0;
-    for (int b = b_begin; b < n_batches; ++b, ++it) {
+    for (int item = (int)blockIdx.x; item < n_items; item += item_step) {
+    const Item w = make_item(item);
+    const int fs = w.fs, fe = w.fe, n_batches = w.n_batches;
+    const S* note = audio + (int64_t)w.note_idx * n_samples;
+    for (int b = w.b_begin; b < n_batches; ++b, ++it) {
       const bool lookback = b < 0;
       const int f0 = lookback ? fs - 1 : fs + b * FB;
       const int nf = lookback ? 1 : min(FB, fe - f0);
-      const int next_f0 = fs + (b + 1) * FB;
-      const int next_nf = (b + 1 < n_batches) ? min(FB, fe - next_f0) : 0;
+      // the batch after this one: the item's next, or the first of the CTA's next item
+      int next_f0 = fs + (b + 1) * FB, next_nf = 0;
+      const S* next_note = note;
+      if (b + 1 < n_batches) {
+        next_nf = min(FB, fe - next_f0);
+      } else if (item + item_step < n_items) {
+        const Item wn = make_item(item + item_step);
+        first_batch(wn, &next_f0, &next_nf);
+        next_note = audio + (int64_t)wn.note_idx * n_samples;
+      }
       const uint32_t buf = it & 1, use = it >> 1;
       cpx2* z = zA + buf * kBufElems + q * P::kPitchA;
       const S* st_cur = stage + buf * stage_elems;
       const bool active = (lookback ? (q == NP - 1) : (q < nf)) && !(ablate & 2);   // & 2: polar/emit role alone
 
       if (feeder && next_nf > 0) {
-        // the other stage buffer was read by pass 1 of the previous batch: all 256 threads have
-        // arrived on its barrier by now (they are at most a pass or two behind)
+        // the other stage buffer was read by pass 1 of the previous batch: all transform threads
+        // have arrived on its barrier by now (they are at most a pass or two behind)
         if (it > 0) mbar_wait_pair(bar_pass1, buf ^ 1, ((it - 1) >> 1) & 1, wait_cfg);
         S* st_next = stage + (buf ^ 1) * stage_elems;
         const StageSpan<S> sp(n_samples, p.hop, p.pad_left, NFFT, next_f0, next_nf);
         sp.fill(st_next, ft, 32);
         __syncwarp();
-        if (ft == 0) sp.issue(st_next, note, bar_stage + (buf ^ 1));
+        if (ft == 0) sp.issue(st_next, next_note, bar_stage + (buf ^ 1));
       }
       mbar_wait_pair(bar_stage, buf, use & 1, wait_cfg);     // this batch's audio has landed
       mbar_wait_pair(bar_empty, buf, (use & 1) ^ 1, wait_cfg);   // polar/emit released the workspace
@@ -647,6 +679,7 @@ melif_ws_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params
       }
       mbar_arrive(bar_full + buf);                         // release: the spectrum is in place
     }
+    }
   } else {
     // =========================== polar / emit warps ===========================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(G::kPeRegs));
@@ -656,10 +689,13 @@ melif_ws_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params
     for (int i = 0; i < IPT; ++i) w_item[i] = tw_global[t + i * kWsPeThreads];
     const bool w_vec = MEL && p.mel_width == kMaxMelWidth && (reinterpret_cast<uintptr_t>(p.mel_weight) & 15) == 0;
     BinState st[IPT];
-#pragma unroll
-    for (int i = 0; i < IPT; ++i) st[i] = bin_state_init();
     uint32_t it = 0;
-    for (int b = b_begin; b < n_batches; ++b, ++it) {
+    for (int item = (int)blockIdx.x; item < n_items; item += item_step) {
+    const Item w = make_item(item);
+    const int fs = w.fs, fe = w.fe, note_idx = w.note_idx;
+#pragma unroll
+    for (int i = 0; i < IPT; ++i) st[i] = bin_state_init();     // no phase history across items
+    for (int b = w.b_begin; b < w.n_batches; ++b, ++it) {
       const bool lookback = b < 0;
       const int f0 = lookback ? fs - 1 : fs + b * FB;
       const int nf = lookback ? 1 : min(FB, fe - f0);
@@ -685,6 +721,7 @@ melif_ws_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params
           emit_row<P, FB, MEL>(p, z, band[r], note_idx, f0, nf, eps, out);
       }
       mbar_arrive(bar_empty + buf);                        // release: the buffer may be overwritten
+    }
     }
   }
 }
@@ -759,8 +796,9 @@ static int launch_melif_ws(const S* audio, int64_t n_notes, int64_t n_samples,
   int seg_frames, n_segs;
   choose_segments(n_notes, p.n_frames, FB, G::kCtasPerSm, &seg_frames, &n_segs);
   if (n_notes * n_segs > 0x7fffffff) return ISI_ERR_SHAPE;
-  melif_ws_kernel<FB, MEL, S, W32><<<(unsigned)(n_notes * n_segs), G::kThreads, L.total, stream>>>(
-      audio, n_samples, p, out, seg_frames, n_segs, ws_wait_cfg(), ws_ablate());
+  const int64_t n_items = n_notes * n_segs, slots = (int64_t)G::kCtasPerSm * kNumSms;
+  melif_ws_kernel<FB, MEL, S, W32><<<(unsigned)(n_items < slots ? n_items : slots), G::kThreads, L.total, stream>>>(
+      audio, n_samples, p, out, seg_frames, n_segs, (int)n_items, ws_wait_cfg(), ws_ablate());
   ISI_LAUNCH_CHECK();
   return ISI_OK;
 }
