@@ -476,17 +476,17 @@ melif_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params p,
 // One CTA per SM, two roles that run CONCURRENTLY on consecutive batches of FB = 8 frames through
 // a double-buffered workspace:
 //   * 4 transform warps, ONE WARP PER FRAME PAIR (melif_core.cuh, PlanW32): each lane holds 32
-//     complex points of the pair (128 of its 192 registers, setmaxnreg.inc), so the 1024-point
+//     complex points of the pair (128 of its 224 registers, setmaxnreg.inc), so the 1024-point
 //     transform is two radix-32 passes with one exchange through shared memory and no barrier
 //     but __syncwarp;
 //   * 16 polar/emit warps (512 threads, one untangle item and two output rows each): polar
 //     of the batch the transform warps finished last, then the mel projection, log / wrap,
-//     epilogue and stores; 72 registers (setmaxnreg.dec).
+//     epilogue and stores; 64 registers (setmaxnreg.dec).
 // The generic kernel gives every thread the transform's register budget, which caps an SM at
 // 16 warps; here the registers are split by need.  The split must CONSERVE the CTA's launch
 // allocation (640 threads x 96 registers = 60 Ki): the transform warps' setmaxnreg.inc spins
 // until the pool holds what the polar/emit warps' setmaxnreg.dec released,
-// 4 x 32 x (192 - 96) = 16 x 32 x (96 - 72).  Hand-off: full[buf] / empty[buf] mbarriers
+// 4 x 32 x (224 - 96) = 16 x 32 x (96 - 64).  Hand-off: full[buf] / empty[buf] mbarriers
 // (transform -> polar/emit -> transform), suspended waits.
 // The previous plan (16 x 16 x 4 in three passes, 8 transform warps in groups of 64 with named
 // barriers, 112 / 64 registers) is still built: ISI_MELIF_WS_PLAN=3, and ISI_MELIF_WS_FB=4 (two
@@ -497,8 +497,10 @@ melif_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params p,
 // two CTAs of 384 -- the same 24 warps per SM; two CTAs fill each other's pipeline fill / drain and
 // set-up bubbles, at twice the per-batch fixed work.)
 // W32 = the one-warp transform plan (melif_core.cuh, PlanW32): 4 transform warps (one per frame
-// pair, 32 points per lane: 192 registers) + 16 polar/emit warps at 72 registers, 640 threads
-// launched at 96 registers: 4 x 32 x (192 - 96) = 16 x 32 x (96 - 72).
+// pair, 32 points per lane: 224 registers) + 16 polar/emit warps at 64 registers, 640 threads
+// launched at 96 registers: 4 x 32 x (224 - 96) = 16 x 32 x (96 - 64).  The transform warps are
+// the critical path and schedule better with room to spare (measured per 444 notes, same box:
+// 160 / 80 0.297 ms, 192 / 72 0.293, 224 / 64 0.283, 256 / 56 0.289).
 template <int FB, bool W32>
 struct WsGeometry {
   static constexpr int kPairs = FB / 2;
@@ -506,7 +508,7 @@ struct WsGeometry {
   static constexpr int kPeThreads = 128 * kPairs;
   static constexpr int kThreads = kFftThreads + kPeThreads;
   static constexpr int kCtasPerSm = W32 ? 1 : 768 / kThreads;
-  static constexpr int kFftRegs = W32 ? 192 : 112, kPeRegs = W32 ? 72 : 64, kLaunchRegs = W32 ? 96 : 80;
+  static constexpr int kFftRegs = W32 ? 224 : 112, kPeRegs = 64, kLaunchRegs = W32 ? 96 : 80;
   static_assert(W32 || kThreads * kCtasPerSm == 768, "24 warps per SM");
   static_assert(!W32 || FB == 8, "the one-warp plan is built for FB = 8");
   static_assert(kFftThreads * (kFftRegs - kLaunchRegs) <= kPeThreads * (kLaunchRegs - kPeRegs),
