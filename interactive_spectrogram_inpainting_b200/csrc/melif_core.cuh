@@ -468,9 +468,19 @@ ISI_HD void fft32_passA_t(int j, const S* frame_a, const S* frame_b, float sampl
 #pragma unroll
     for (int i = 0; i < 4; ++i) if (p0 + i < 32) v[p0 + i] = cmul(v[p0 + i], t[i]);
   }
-  auto o = split_ptr(zA + j);
+  // The exchange is stored as two planes of 8-byte values (re pairs, im pairs): a packed
+  // instruction leaves its result in an aligned register PAIR, which is exactly what an 8-byte
+  // store takes.  A 16-byte store of (re, im) needs an aligned QUAD: ptxas copied every value
+  // into one staging quad, and each copy waited for the previous store to read it -- a fifth of
+  // the transform warps' stall samples.  Same bytes, same wavefronts (lanes along j: 256
+  // contiguous bytes per store; pass B reads at stride 33 x 8 bytes: conflict-free per half warp).
+  f2* re_plane = reinterpret_cast<f2*>(zA);
+  f2* im_plane = re_plane + PlanW32::kPitchA;
 #pragma unroll
-  for (int p = 0; p < 32; ++p) put(o, PlanW32::kBlockPitch * p, v[p]);
+  for (int p = 0; p < 32; ++p) {
+    re_plane[PlanW32::kBlockPitch * p + j] = v[p].re;
+    im_plane[PlanW32::kBlockPitch * p + j] = v[p].im;
+  }
 }
 template <typename S>
 ISI_HD void fft32_passA(int j, const S* frame_a, const S* frame_b, bool pair_aligned,
@@ -488,9 +498,10 @@ ISI_HD void fft32_passA(int j, const S* frame_a, const S* frame_b, bool pair_ali
 // (p, j) slots other lanes of the warp still have to read
 struct PassB32Regs { cpx2 u[32]; };
 ISI_HD void fft32_passB_load(int p, const cpx2* zA, PassB32Regs& r) {
-  const cpx2* row = zA + PlanW32::kBlockPitch * p;
+  const f2* re_row = reinterpret_cast<const f2*>(zA) + PlanW32::kBlockPitch * p;
+  const f2* im_row = re_row + PlanW32::kPitchA;
 #pragma unroll
-  for (int j = 0; j < 32; ++j) r.u[j] = row[j];
+  for (int j = 0; j < 32; ++j) { r.u[j].re = re_row[j]; r.u[j].im = im_row[j]; }
   dft32(r.u);
 }
 ISI_HD void fft32_passB_store(int p, const PassB32Regs& r, cpx2* z) {
