@@ -473,8 +473,8 @@ melif_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params p,
 // ------------------------------------------------------------------------------------------
 // Warp-specialised kernel (n_fft 2048, bulk-copyable audio, even hop): the NSynth shape.
 //
-// One CTA per SM, two roles that run CONCURRENTLY on consecutive batches of FB = 8 frames through
-// a double-buffered workspace:
+// One PERSISTENT CTA per SM (it walks its work items, see the kernel), two roles that run
+// CONCURRENTLY on consecutive batches of FB = 8 frames through a double-buffered workspace:
 //   * 4 transform warps, ONE WARP PER FRAME PAIR (melif_core.cuh, PlanW32): each lane holds 32
 //     complex points of the pair (128 of its 224 registers, setmaxnreg.inc), so the 1024-point
 //     transform is two radix-32 passes with one exchange through shared memory and no barrier
@@ -490,8 +490,9 @@ melif_kernel(const S* __restrict__ audio, int64_t n_samples, isi_melif_params p,
 // (transform -> polar/emit -> transform), suspended waits.
 // The previous plan (16 x 16 x 4 in three passes, 8 transform warps in groups of 64 with named
 // barriers, 112 / 64 registers) is still built: ISI_MELIF_WS_PLAN=3, and ISI_MELIF_WS_FB=4 (two
-// CTAs of 384 threads per SM) -- measurement knobs.  Measured per 444 notes: 0.307 ms -> 0.295 ms;
-// moving the last pass to the polar/emit role had made THAT role the critical path (0.373 ms).
+// CTAs of 384 threads per SM) -- measurement knobs.  Measured per 444 notes: 0.299 ms (three-pass)
+// against 0.277 ms; moving the last pass to the polar/emit role had made THAT role the critical
+// path (0.373 ms).
 // ------------------------------------------------------------------------------------------
 // Geometry of one instantiation.  (Three-pass plan: FB = 8 is one CTA of 768 threads per SM, FB = 4
 // two CTAs of 384 -- the same 24 warps per SM; two CTAs fill each other's pipeline fill / drain and
